@@ -1,0 +1,32 @@
+# Build libamgb200.so (the product: sm_100a CUDA kernels + C ABI + host helpers) and
+# oracle/liboracle.so (the CPU checker; test infrastructure only).
+NVCC      ?= nvcc
+CC        ?= gcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+# -fmad=false: the reference's CPU objects contain no FMA (gcc, baseline x86-64); kernels that
+# promise bit-identical rows additionally use __dmul_rn/__dadd_rn explicitly.
+NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -fmad=false -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off,-fopenmp -Iinclude
+CSRC      := amg_b200/csrc
+CU_SRCS   := $(wildcard $(CSRC)/*.cu)
+CPP_SRCS  := $(wildcard $(CSRC)/*.cpp)
+OBJS      := $(CU_SRCS:.cu=.o) $(CPP_SRCS:.cpp=.o)
+HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/amg_b200.h
+
+all: amg_b200/libamgb200.so oracle/liboracle.so
+
+amg_b200/libamgb200.so: $(OBJS)
+	$(NVCC) -shared $(ARCH) -Xcompiler -fopenmp -o $@ $(OBJS) -lcudart
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(@:.o=.ptxas.log) || (cat $(@:.o=.ptxas.log); false)
+
+$(CSRC)/%.o: $(CSRC)/%.cpp $(HDRS)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+oracle/liboracle.so: oracle/amg_oracle.c include/amg_b200.h
+	$(CC) -O2 -ffp-contract=off -fPIC -shared -o $@ oracle/amg_oracle.c -lm
+
+clean:
+	rm -f $(CSRC)/*.o $(CSRC)/*.ptxas.log amg_b200/libamgb200.so oracle/liboracle.so
+
+.PHONY: all clean

@@ -1,0 +1,226 @@
+/*
+ * amg_b200.h -- C ABI of libamgb200.so: the B200-native (sm_100a) solve phase of the
+ * txthpc/amg classical AMG solver.
+ *
+ * The library is a drop-in for the four solve-phase objects of the reference link line
+ * (amg/Makefile.sh:19: SSS_SOLVE.o SSS_cycle.o SSS_smooth.o SSS_cuda.o).  Its primary entry
+ * point has the reference's own name and signature, so the reference's unmodified C host
+ * (main, mmio loaders, SSS_solver_amg -> SSS_amg_setup -> SSS_amg_solve) links against it.
+ *
+ * All structs below are layout-compatible restatements of the reference's public types
+ * (amg/SSS_main.h); the static asserts at the bottom pin the LP64 layout.  When the
+ * reference's own header is included first (_SSS_MAIN_H_ defined) the reference-named entry
+ * points are declared with the reference's types instead.
+ *
+ * There is NO CPU fallback: every entry point that computes needs a CUDA device and aborts
+ * with a message on stderr when none is usable.
+ */
+#ifndef AMG_B200_H_
+#define AMG_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+
+/* ---- layout-compatible types (amg/SSS_main.h) ------------------------------------------ */
+typedef struct amgb200_mat_ {   /* SSS_MAT, SSS_main.h:95-105: CSR, int32 indices, fp64 values */
+    int num_rows, num_cols, num_nnzs;
+    int *row_ptr;
+    int *col_idx;
+    double *val;
+} amgb200_mat;
+
+typedef struct amgb200_vec_ { int n; double *d; } amgb200_vec;   /* SSS_VEC,  SSS_main.h:119-124 */
+typedef struct amgb200_ivec_ { int n; int *d; } amgb200_ivec;    /* SSS_IVEC, SSS_main.h:126-131 */
+
+typedef struct amgb200_rtn_ {   /* SSS_RTN, SSS_main.h:154-160 */
+    double ares;                /* absolute residual ||b - A x||_2 */
+    double rres;                /* relative residual ||r|| / ||b|| */
+    int nits;                   /* V-cycles done */
+} amgb200_rtn;
+
+typedef struct amgb200_pars_ {  /* SSS_AMG_PARS, SSS_main.h:170-194 */
+    int cycle_type;             /* <=1: V-cycle, 2: W-cycle */
+    double tol;                 /* outer stopping tolerance on ||r||/||b|| */
+    double ctol;                /* coarsest-level tolerance (clamped to 0.1*tol, SSS_cycle.cu:858) */
+    int max_it;
+    int cs_type;                /* 1 = classical RS */
+    int max_levels;
+    int coarse_dof;
+    int smoother;               /* 2 = Gauss-Seidel (the only smoother the reference implements) */
+    double relax;
+    int cf_order;               /* 1 = C/F ordering (F rows first, then C rows) */
+    int pre_iter, post_iter;
+    int poly_deg;
+    int interp_type;            /* 1 = direct interpolation */
+    double strong_threshold, max_row_sum, trunc_threshold;
+} amgb200_pars;
+
+typedef struct amgb200_comp_ {  /* SSS_AMG_COMP, SSS_main.h:196-207: one level */
+    amgb200_mat A, R, P;
+    amgb200_vec b, x;
+    amgb200_ivec cfmark;        /* 0 = F, 1 = C, 2 = isolated */
+    amgb200_vec wp;
+} amgb200_comp;
+
+typedef struct amgb200_amg_ {   /* SSS_AMG, SSS_main.h:209-218 */
+    int num_levels;
+    amgb200_comp *cg;
+    amgb200_pars pars;
+    amgb200_rtn rtn;
+} amgb200_amg;
+
+typedef struct amgb200_smtr_ {  /* SSS_SMTR, SSS_main.h:221-238 */
+    int smoother;
+    amgb200_mat *A;
+    amgb200_vec *b;
+    amgb200_vec *x;
+    double relax;
+    int nsweeps, istart, iend, istep, ndeg, cf_order;
+    int *ordering;
+} amgb200_smtr;
+
+#ifdef _SSS_MAIN_H_
+#define AMGB200_T_AMG  SSS_AMG
+#define AMGB200_T_VEC  SSS_VEC
+#define AMGB200_T_MAT  SSS_MAT
+#define AMGB200_T_RTN  SSS_RTN
+#define AMGB200_T_SMTR SSS_SMTR
+#else
+#define AMGB200_T_AMG  amgb200_amg
+#define AMGB200_T_VEC  amgb200_vec
+#define AMGB200_T_MAT  amgb200_mat
+#define AMGB200_T_RTN  amgb200_rtn
+#define AMGB200_T_SMTR amgb200_smtr
+#endif
+
+/* ---- 1. reference-named drop-in entry points ------------------------------------------- */
+
+/* Replaces amg/Solve/SSS_SOLVE.c:4-87 (declared Solve/SSS_SOLVE.h:9; sole caller SSS_AMG.c:51).
+ * Host hierarchy in, solution written to x->d, residual table printed in the reference's
+ * format, {ares,rres,nits} returned and stored in mg->rtn, mg->cg[0].x/.b left aliased to the
+ * caller's vectors.  Uploads the hierarchy, solves on the device, frees the device mirror. */
+AMGB200_T_RTN SSS_amg_solve(AMGB200_T_AMG *mg, AMGB200_T_VEC *x, AMGB200_T_VEC *b);
+
+/* Replaces amg/Solve/SSS_cycle.cu:848-967 (Solve/SSS_cycle.h:18): one V/W-cycle on the host
+ * hierarchy (reads cg[0].b, cg[0].x; writes cg[l].x, cg[l].b, cg[l].wp like the reference). */
+void SSS_amg_cycle(AMGB200_T_AMG *mg);
+
+/* Replaces amg/Solve/SSS_cycle.cu:819-846 (Solve/SSS_cycle.h:17): CG, then GMRES(30) on failure. */
+void SSS_amg_coarest_solve(AMGB200_T_MAT *A, AMGB200_T_VEC *b, AMGB200_T_VEC *x, const double ctol);
+
+/* Replace amg/Solve/SSS_smooth.c:138-220 / :223-304 (Solve/SSS_smooth.h:18-20). */
+void SSS_amg_smoother_pre(AMGB200_T_SMTR *s);
+void SSS_amg_smoother_post(AMGB200_T_SMTR *s);
+
+/* GPU versions of amg/SSS_utils.c:182-201 (y = A x) and :161-178 (y += alpha A x).  New names:
+ * the reference's SSS_blas_mv_* live in SSS_utils.o, which stays in the link line. */
+void amgb200_blas_mv_mxy(const AMGB200_T_MAT *A, const AMGB200_T_VEC *x, AMGB200_T_VEC *y);
+void amgb200_blas_mv_amxpy(double alpha, const AMGB200_T_MAT *A, const AMGB200_T_VEC *x, AMGB200_T_VEC *y);
+
+/* ---- 2. resident-hierarchy API (what SSS_amg_solve is built from) ----------------------- */
+typedef struct amgb200_hier amgb200_hier;   /* opaque device mirror of an SSS_AMG */
+
+enum {                           /* amgb200_options.coarse_mode: the reference's CG beta line is UB */
+    AMGB200_BETA_FIX = 0,        /* beta = (z_k,r_k)/(z_{k-1},r_{k-1})  (author's stated formula) */
+    AMGB200_BETA_AS_COMPILED = 1 /* beta = 1, temp1 frozen              (what the shipped object runs) */
+};
+
+typedef struct amgb200_options_ {
+    int coarse_mode;             /* AMGB200_BETA_* (default FIX; env AMGB200_COARSE_MODE=asc overrides) */
+    int verbose;                 /* 0 quiet, 1 reference's iteration table, 2 + level/kernel table */
+    int device;                  /* CUDA device ordinal, -1 = current */
+    int reserved[5];
+} amgb200_options;
+
+void amgb200_default_options(amgb200_options *o);
+
+/* Analyse (wavefront schedule, per-level kernel choice) and upload.  Host hierarchy is only read. */
+amgb200_hier *amgb200_upload(const AMGB200_T_AMG *mg, const amgb200_options *opt);
+void amgb200_free(amgb200_hier *h);
+
+/* Full solve on a resident hierarchy; x, b host arrays of n_0 doubles (natural numbering).
+ * res_hist (may be NULL) receives ||r||_2 after each V-cycle (up to hist_cap entries). */
+amgb200_rtn amgb200_solve(amgb200_hier *h, double *x, const double *b, double *res_hist, int hist_cap);
+
+/* Same, but x/b already on the device (natural numbering, device pointers); nothing crosses
+ * PCIe except one double per V-cycle.  Used for the kernel-only bench number. */
+amgb200_rtn amgb200_solve_device(amgb200_hier *h, double *d_x, const double *d_b, double *res_hist, int hist_cap);
+
+/* One V-cycle on resident level-0 vectors (host arrays in/out), for function-level parity. */
+void amgb200_cycle(amgb200_hier *h, double *x, const double *b);
+
+/* Function-level hooks on one resident level (host arrays, natural numbering):
+ *   which: 0 = A_l, 1 = P_l (coarse -> fine), 2 = R_l (fine -> coarse)
+ *   y = beta*y + alpha * M x   with beta in {0,1}  (beta=0: SSS_blas_mv_mxy, beta=1: _amxpy) */
+void amgb200_level_spmv(amgb200_hier *h, int level, int which, double alpha, const double *x, int beta, double *y);
+/* nsweeps C/F-ordered Gauss-Seidel sweeps (SSS_smooth.c:4-87, order != 0 branch) on level l */
+void amgb200_level_smooth(amgb200_hier *h, int level, int nsweeps, double *x, const double *b);
+/* r = b - A_l x, returns ||r||_2 */
+double amgb200_level_residual(amgb200_hier *h, int level, const double *x, const double *b, double *r);
+/* coarsest-level solve on the resident coarsest matrix; returns the Krylov status
+ * (iterations, or a negative SSS error code) of the last solver that ran; its[0]=CG its/status,
+ * its[1]=GMRES its/status or 0 if not run */
+int amgb200_coarse_solve(amgb200_hier *h, double *x, const double *b, double tol, int its[2]);
+
+/* Introspection */
+int amgb200_num_levels(const amgb200_hier *h);
+/* info[0]=rows info[1]=nnz info[2]=F-pass wavefronts info[3]=C-pass wavefronts
+ * info[4]=kernel kind (0 SELL-32 thread/row, 1 CSR warp/row) info[5]=rows in F pass
+ * info[6]=P nnz info[7]=R nnz */
+void amgb200_level_info(const amgb200_hier *h, int level, long long info[8]);
+/* algorithmic bytes (SURVEY.md section 8d formulas) of: op 0 = one GS sweep, 1 = residual,
+ * 2 = restrict, 3 = prolong-add, 4 = y=A x  on that level; op 5 (level ignored) = one V-cycle */
+double amgb200_algorithmic_bytes(const amgb200_hier *h, int level, int op);
+/* time `reps` back-to-back launches of op (as above, 0..4) on level l with CUDA events on the
+ * library's stream; returns average milliseconds per launch (ops run on scratch vectors) */
+double amgb200_time_op(amgb200_hier *h, int level, int op, int reps);
+/* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
+long long amgb200_launch_count(void);
+/* per-phase device time of the last solve in ms: [0] GS, [1] residual, [2] restrict,
+ * [3] prolong, [4] coarse solve, [5] outer residual+norm, [6] total (only when
+ * AMGB200_PROFILE=1 in the environment; otherwise zeros) */
+void amgb200_last_phase_ms(const amgb200_hier *h, double ms[8]);
+const char *amgb200_version(void);
+
+/* ---- 3. host-side helpers (pure C++, no device): synthetic operators + RS setup ---------- */
+/* Synthetic level-0 operators of SURVEY.md Appendix B, CSR with ascending columns:
+ *   kind 0 = p2d N (5-point), 1 = p3d N (7-point), 2 = aniso3d N (1,1,eps_z), 3 = v27 N
+ * Returns 0 on success; arrays are malloc'ed, release with amgb200_mat_free. */
+int amgb200_generate(int kind, int N, double eps_z, amgb200_mat *A);
+void amgb200_mat_free(amgb200_mat *A);
+/* From-scratch restatement of the reference's setup phase (Setup/SSS_SETUP.cu:36-177 and below:
+ * RS coarsening, direct interpolation + truncation, R = P^T, Galerkin RAP) producing a host
+ * hierarchy that is bit-identical to the reference's.  Needed so the product runs without any
+ * reference object; the reference's own setup can be used instead (it is the kept host). */
+void amgb200_setup(amgb200_amg *mg, const amgb200_mat *A, const amgb200_pars *pars, int verbose);
+void amgb200_amg_destroy(amgb200_amg *mg);
+void amgb200_default_pars(amgb200_pars *p);   /* SSS_main.c:25-64 */
+
+#pragma GCC visibility pop
+#ifdef __cplusplus
+}
+#endif
+
+/* ---- layout pins (LP64) ------------------------------------------------------------------ */
+#if defined(__cplusplus)
+#define AMGB200_SA(c, m) static_assert(c, m)
+#else
+#define AMGB200_SA(c, m) _Static_assert(c, m)
+#endif
+AMGB200_SA(sizeof(amgb200_mat) == 40, "SSS_MAT layout");
+AMGB200_SA(offsetof(amgb200_mat, row_ptr) == 16 && offsetof(amgb200_mat, val) == 32, "SSS_MAT layout");
+AMGB200_SA(sizeof(amgb200_vec) == 16 && sizeof(amgb200_ivec) == 16, "SSS_VEC layout");
+AMGB200_SA(sizeof(amgb200_rtn) == 24, "SSS_RTN layout");
+AMGB200_SA(sizeof(amgb200_pars) == 104, "SSS_AMG_PARS layout");
+AMGB200_SA(sizeof(amgb200_comp) == 184 && offsetof(amgb200_comp, R) == 40 && offsetof(amgb200_comp, P) == 80 &&
+           offsetof(amgb200_comp, b) == 120 && offsetof(amgb200_comp, x) == 136 &&
+           offsetof(amgb200_comp, cfmark) == 152 && offsetof(amgb200_comp, wp) == 168, "SSS_AMG_COMP layout");
+AMGB200_SA(sizeof(amgb200_amg) == 144 && offsetof(amgb200_amg, cg) == 8 && offsetof(amgb200_amg, pars) == 16 &&
+           offsetof(amgb200_amg, rtn) == 120, "SSS_AMG layout");
+AMGB200_SA(sizeof(amgb200_smtr) == 72, "SSS_SMTR layout");
+
+#endif /* AMG_B200_H_ */
