@@ -58,7 +58,8 @@ class Smtr(C.Structure):         # SSS_SMTR
 
 
 class Options(C.Structure):      # amgb200_options
-    _fields_ = [("coarse_mode", C.c_int), ("verbose", C.c_int), ("device", C.c_int), ("reserved", C.c_int * 5)]
+    _fields_ = [("coarse_mode", C.c_int), ("verbose", C.c_int), ("device", C.c_int), ("fast", C.c_int),
+                ("reserved", C.c_int * 4)]
 
 
 assert C.sizeof(Mat) == 40 and C.sizeof(Vec) == 16 and C.sizeof(Rtn) == 24

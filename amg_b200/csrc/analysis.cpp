@@ -1,0 +1,150 @@
+// Host-side analysis: wavefront (level-set) schedule of the reference's ordered Gauss-Seidel
+// and construction of the permuted device layouts.  See DESIGN.md "Data layout in HBM".
+//
+// The reference's smoother (amg/Solve/SSS_smooth.c:16-49) is a true Gauss-Seidel in ascending
+// row order, F rows (cfmark != 1) first, then C rows.  Row i of a pass needs the *new* x_j of
+// every same-pass neighbour j < i and the *old* x_j of every same-pass neighbour j > i.  The
+// wavefront number of a row is therefore 1 + max over same-pass neighbours j < i, where
+// "neighbour" is taken in the symmetrised pattern (a_ij or a_ji stored) so that the
+// read-old-value anti-dependencies are honoured for non-symmetric patterns too.  Rows of one
+// wavefront are mutually independent; executing wavefronts in order with any intra-wavefront
+// order reproduces the sequential iterates exactly.
+#include "analysis.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace amgb200 {
+
+int choose_kind(const amgb200_mat &M, double sell_max_mean) {
+    const double mean = M.num_rows ? (double)M.num_nnzs / M.num_rows : 0.0;
+    return mean <= sell_max_mean ? KIND_SELL : KIND_CSR;
+}
+
+void identity_schedule(int n, Schedule &S) {
+    S = Schedule();
+    S.n = n;
+    S.order.resize(n);
+    S.pos.resize(n);
+    for (int i = 0; i < n; ++i) S.order[i] = S.pos[i] = i;
+    S.pass_rows[0] = n;
+    S.wf_count[0] = n ? 1 : 0;
+    S.wf_row_ptr = {0, n};
+}
+
+void build_schedule(const amgb200_mat &A, const int *mark, Schedule &S) {
+    const int n = A.num_rows;
+    S = Schedule();
+    S.n = n;
+    std::vector<int> lvl(n, 0), pend(n, 0);
+    std::vector<unsigned char> pass(n, 0);
+    if (mark) for (int i = 0; i < n; ++i) pass[i] = mark[i] == 1 ? 1 : 0;
+    int depth[2] = {0, 0};
+    for (int i = 0; i < n; ++i) {
+        const int p = pass[i];
+        const int b = A.row_ptr[i], e = A.row_ptr[i + 1];
+        int L = 1;
+        bool diag = false;
+        for (int k = b; k < e; ++k) {
+            const int j = A.col_idx[k];
+            if (j == i) { diag = true; continue; }
+            if (j < i && pass[j] == p && lvl[j] + 1 > L) L = lvl[j] + 1;
+        }
+        if (pend[i] > L) { L = pend[i]; S.pattern_symmetric = false; }
+        lvl[i] = L;
+        if (!diag) S.rows_without_diag++;
+        for (int k = b; k < e; ++k) {
+            const int j = A.col_idx[k];
+            if (j > i && pass[j] == p && pend[j] < L + 1) pend[j] = L + 1;
+        }
+        if (L > depth[p]) depth[p] = L;
+        S.pass_rows[p]++;
+    }
+    S.wf_count[0] = depth[0];
+    S.wf_count[1] = depth[1];
+    const int W = depth[0] + depth[1];
+    S.wf_row_ptr.assign(W + 1, 0);
+    for (int i = 0; i < n; ++i) S.wf_row_ptr[(pass[i] ? depth[0] : 0) + lvl[i] - 1 + 1]++;
+    for (int w = 0; w < W; ++w) S.wf_row_ptr[w + 1] += S.wf_row_ptr[w];
+    std::vector<int> fill(S.wf_row_ptr.begin(), S.wf_row_ptr.end() - 1);
+    S.order.resize(n);
+    S.pos.resize(n);
+    for (int i = 0; i < n; ++i) {
+        const int k = fill[(pass[i] ? depth[0] : 0) + lvl[i] - 1]++;
+        S.order[k] = i;
+        S.pos[i] = k;
+    }
+}
+
+void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos, int kind,
+                  const std::vector<int> *breaks, DevLayout &L) {
+    L = DevLayout();
+    L.kind = kind;
+    const int n = M.num_rows;
+    L.nrows = n;
+    L.ncols = M.num_cols;
+    L.nnz = M.row_ptr[n];
+    auto nat = [&](int k) { return row_order ? row_order[k] : k; };
+    int maxlen = 0;
+    for (int i = 0; i < n; ++i) maxlen = std::max(maxlen, M.row_ptr[i + 1] - M.row_ptr[i]);
+    L.max_row = maxlen;
+
+    if (kind == KIND_CSR) {
+        L.rptr.resize((size_t)n + 1);
+        L.rptr[0] = 0;
+        for (int k = 0; k < n; ++k) { const int i = nat(k); L.rptr[k + 1] = L.rptr[k] + (M.row_ptr[i + 1] - M.row_ptr[i]); }
+        L.col.resize((size_t)L.nnz);
+        L.val.resize((size_t)L.nnz);
+#pragma omp parallel for schedule(static)
+        for (int k = 0; k < n; ++k) {
+            const int i = nat(k);
+            int w = L.rptr[k];
+            for (int q = M.row_ptr[i]; q < M.row_ptr[i + 1]; ++q, ++w) {
+                const int j = M.col_idx[q];
+                L.col[w] = col_pos ? col_pos[j] : j;
+                L.val[w] = M.val[q];
+            }
+        }
+        if (breaks) L.wf_item_ptr = *breaks;
+        return;
+    }
+
+    // SELL-32
+    std::vector<int> seg;
+    if (breaks) seg = *breaks; else seg = {0, n};
+    L.slice_row.clear();
+    if (breaks) L.wf_item_ptr.clear();
+    for (size_t s = 0; s + 1 < seg.size(); ++s) {
+        if (breaks) L.wf_item_ptr.push_back((int)L.slice_row.size());
+        for (int r = seg[s]; r < seg[s + 1]; r += 32) L.slice_row.push_back(r);
+    }
+    if (breaks) L.wf_item_ptr.push_back((int)L.slice_row.size());
+    L.slice_row.push_back(n);
+    const int ns = (int)L.slice_row.size() - 1;
+    L.slice_ptr.assign((size_t)ns + 1, 0);
+    for (int s = 0; s < ns; ++s) {
+        int w = 0;
+        for (int k = L.slice_row[s]; k < L.slice_row[s + 1]; ++k) { const int i = nat(k); w = std::max(w, M.row_ptr[i + 1] - M.row_ptr[i]); }
+        L.slice_ptr[s + 1] = L.slice_ptr[s] + 32LL * w;
+    }
+    const size_t total = (size_t)L.slice_ptr[ns];
+    L.col.assign(total, -1);
+    L.val.assign(total, 0.0);
+#pragma omp parallel for schedule(static)
+    for (int s = 0; s < ns; ++s) {
+        const long long base = L.slice_ptr[s];
+        for (int k = L.slice_row[s]; k < L.slice_row[s + 1]; ++k) {
+            const int i = nat(k), lane = k - L.slice_row[s];
+            long long w = base + lane;
+            for (int q = M.row_ptr[i]; q < M.row_ptr[i + 1]; ++q, w += 32) {
+                const int j = M.col_idx[q];
+                L.col[(size_t)w] = col_pos ? col_pos[j] : j;
+                L.val[(size_t)w] = M.val[q];
+            }
+        }
+    }
+}
+
+}  // namespace amgb200

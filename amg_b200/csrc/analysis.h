@@ -1,0 +1,56 @@
+// Host-side analysis of a level: Gauss-Seidel wavefront schedule and device matrix layouts.
+#pragma once
+#include <vector>
+
+#include "../../include/amg_b200.h"
+
+namespace amgb200 {
+
+enum MatKind { KIND_SELL = 0, KIND_CSR = 1 };
+
+// Row schedule of one smoothed level.  "Schedule numbering" k = position of a row in the order
+// [F-pass wavefront 0 | F-pass wavefront 1 | ... | C-pass wavefront 0 | ...], rows inside a
+// wavefront in ascending natural index.  All device vectors of the level live in this numbering.
+struct Schedule {
+    int n = 0;
+    std::vector<int> order;        // schedule position -> natural row
+    std::vector<int> pos;          // natural row -> schedule position
+    int pass_rows[2] = {0, 0};     // rows in the F pass (mark != 1) and the C pass (mark == 1)
+    int wf_count[2] = {0, 0};      // dependency-DAG depth of each pass
+    std::vector<int> wf_row_ptr;   // wf_count[0]+wf_count[1]+1 entries: first schedule row of each wavefront
+    bool pattern_symmetric = true; // informational: a_ij stored <=> a_ji stored (same-pass pairs)
+    int rows_without_diag = 0;
+};
+
+// A matrix permuted into schedule numbering, in the layout the kernels stream.
+//  KIND_SELL: sliced ELLPACK, slice height 32 (one warp, one thread per row); entry k of lane r of
+//             slice s sits at slice_ptr[s] + 32*k + r; padding has col = -1, val = 0.  Slices never
+//             straddle a wavefront boundary.  Row-internal storage order is the reference's.
+//  KIND_CSR : plain CSR (one warp per row, lanes stride the row).
+struct DevLayout {
+    int kind = KIND_SELL;
+    int nrows = 0, ncols = 0;
+    long long nnz = 0;             // true (unpadded) entries
+    int max_row = 0;
+    std::vector<int> slice_row;    // SELL: nslices+1, first schedule row of each slice
+    std::vector<long long> slice_ptr;  // SELL: nslices+1
+    std::vector<int> rptr;         // CSR: nrows+1
+    std::vector<int> col;
+    std::vector<double> val;
+    std::vector<int> wf_item_ptr;  // (A of smoothed levels) first item (slice | row) of each wavefront
+    int nitems() const { return kind == KIND_SELL ? (int)slice_row.size() - 1 : nrows; }
+};
+
+// mark == nullptr: single pass over all rows in natural order (no C/F ordering).
+void build_schedule(const amgb200_mat &A, const int *mark, Schedule &S);
+void identity_schedule(int n, Schedule &S);
+
+// rows of M taken in `row_order` (schedule position -> natural row; nullptr = identity),
+// columns renumbered through `col_pos` (natural -> schedule; nullptr = identity).
+// `breaks` (optional, ascending schedule-row offsets incl. 0 and nrows) forces slice boundaries.
+void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos, int kind,
+                  const std::vector<int> *breaks, DevLayout &L);
+
+int choose_kind(const amgb200_mat &M, double sell_max_mean);
+
+}  // namespace amgb200

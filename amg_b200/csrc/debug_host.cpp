@@ -1,0 +1,100 @@
+// Host-only introspection hooks used by the CPU test-suite (tests/test_schedule.py) to validate
+// the analysis without a GPU: the wavefront schedule and a layout walk that executes the
+// Gauss-Seidel rows wavefront by wavefront in REVERSE intra-wavefront order.  If the schedule is
+// right (rows of one wavefront are independent) the result is bit-identical to the reference's
+// sequential sweep.  Not a compute path of the product: nothing in hier.cu calls these.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/amg_b200.h"
+#include "analysis.h"
+
+using namespace amgb200;
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+// order[n], wf_row_ptr[cap]; returns the number of wavefronts (F + C), counts[0..1] = per pass,
+// counts[2] = pattern_symmetric, counts[3] = rows without diagonal; -1 if cap is too small
+int amgb200_debug_schedule(const amgb200_mat *A, const int *mark, int *order, int *wf_row_ptr, int cap, int counts[4]) {
+    Schedule S;
+    build_schedule(*A, mark, S);
+    const int W = S.wf_count[0] + S.wf_count[1];
+    if (W + 1 > cap) return -1;
+    memcpy(order, S.order.data(), (size_t)S.n * sizeof(int));
+    memcpy(wf_row_ptr, S.wf_row_ptr.data(), (size_t)(W + 1) * sizeof(int));
+    counts[0] = S.wf_count[0]; counts[1] = S.wf_count[1];
+    counts[2] = S.pattern_symmetric; counts[3] = S.rows_without_diag;
+    return W;
+}
+
+// x, b in natural numbering; kind 0 = SELL walk (sequential per row), 1 = CSR walk
+void amgb200_debug_gs_walk(const amgb200_mat *A, const int *mark, int kind, int nsweeps, double *x, const double *b) {
+    Schedule S;
+    build_schedule(*A, mark, S);
+    DevLayout L;
+    build_layout(*A, S.order.data(), S.pos.data(), kind, &S.wf_row_ptr, L);
+    const int n = S.n, W = S.wf_count[0] + S.wf_count[1];
+    std::vector<double> xs(n), bs(n);
+    for (int k = 0; k < n; ++k) { xs[k] = x[S.order[k]]; bs[k] = b[S.order[k]]; }
+    for (int s = 0; s < nsweeps; ++s)
+        for (int w = 0; w < W; ++w)
+            for (int it = L.wf_item_ptr[w + 1] - 1; it >= L.wf_item_ptr[w]; --it) {     // reverse order inside the wavefront
+                if (kind == KIND_SELL) {
+                    const long long p0 = L.slice_ptr[it];
+                    const int width = (int)((L.slice_ptr[it + 1] - p0) / 32);
+                    for (int k = L.slice_row[it + 1] - 1; k >= L.slice_row[it]; --k) {
+                        const int lane = k - L.slice_row[it];
+                        double t = bs[k], d = 0.0;
+                        for (int e = 0; e < width; ++e) {
+                            const int j = L.col[(size_t)(p0 + 32LL * e + lane)];
+                            const double a = L.val[(size_t)(p0 + 32LL * e + lane)];
+                            if (j == k) d = a;
+                            else if (j >= 0) t -= a * xs[j];
+                        }
+                        if (fabs(d) > 1e-20) xs[k] = t / d;
+                    }
+                } else {
+                    const int k = it;
+                    double t = bs[k], d = 0.0;
+                    for (int p = L.rptr[k]; p < L.rptr[k + 1]; ++p) {
+                        if (L.col[p] == k) d = L.val[p];
+                        else t -= L.val[p] * xs[L.col[p]];
+                    }
+                    if (fabs(d) > 1e-20) xs[k] = t / d;
+                }
+            }
+    for (int k = 0; k < n; ++k) x[S.order[k]] = xs[k];
+}
+
+// y = M x through the device layout (rows in row_order, columns through col_pos), natural in/out
+void amgb200_debug_spmv_walk(const amgb200_mat *M, int kind, const double *x, double *y) {
+    DevLayout L;
+    build_layout(*M, nullptr, nullptr, kind, nullptr, L);
+    if (kind == KIND_SELL) {
+        const int ns = (int)L.slice_row.size() - 1;
+        for (int s = 0; s < ns; ++s) {
+            const long long p0 = L.slice_ptr[s];
+            const int width = (int)((L.slice_ptr[s + 1] - p0) / 32);
+            for (int k = L.slice_row[s]; k < L.slice_row[s + 1]; ++k) {
+                const int lane = k - L.slice_row[s];
+                double t = 0.0;
+                for (int e = 0; e < width; ++e) {
+                    const int j = L.col[(size_t)(p0 + 32LL * e + lane)];
+                    if (j >= 0) t += L.val[(size_t)(p0 + 32LL * e + lane)] * x[j];
+                }
+                y[k] = t;
+            }
+        }
+    } else {
+        for (int k = 0; k < L.nrows; ++k) {
+            double t = 0.0;
+            for (int p = L.rptr[k]; p < L.rptr[k + 1]; ++p) t += L.val[p] * x[L.col[p]];
+            y[k] = t;
+        }
+    }
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,141 @@
+// Reference-named entry points: the symbols the reference's host (SSS_AMG.c:51 and the
+// SSS_cycle.h / SSS_smooth.h prototypes) binds.  Each one mirrors its host arguments to the
+// device, runs the resident-hierarchy kernels and copies the results back into the host
+// structures the reference's callers read.  No CPU arithmetic on the data path.
+#include <sys/time.h>
+
+#include <cassert>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/amg_b200.h"
+
+namespace {
+
+double wall() {
+    struct timeval tv;
+    gettimeofday(&tv, nullptr);
+    return tv.tv_sec + tv.tv_usec * 1e-6;
+}
+
+// a one-level hierarchy around a bare matrix, for the function-level entry points
+struct MiniHier {
+    amgb200_amg mg;
+    std::vector<amgb200_comp> comp;
+    amgb200_hier *h = nullptr;
+    MiniHier(const amgb200_mat *A, int *cfmark, int levels) : comp(2) {
+        memset(&mg, 0, sizeof(mg));
+        memset(comp.data(), 0, 2 * sizeof(amgb200_comp));
+        amgb200_default_pars(&mg.pars);
+        comp[0].A = *A;
+        comp[0].cfmark.n = A->num_rows;
+        comp[0].cfmark.d = cfmark;
+        mg.cg = comp.data();
+        mg.num_levels = levels;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+// amg/Solve/SSS_SOLVE.c:4-87
+amgb200_rtn SSS_amg_solve(amgb200_amg *mg, amgb200_vec *x, amgb200_vec *b) {
+    assert(mg != NULL);
+    assert(x != NULL);
+    assert(b != NULL);
+    amgb200_options opt;
+    amgb200_default_options(&opt);
+    opt.verbose = 1;
+    if (getenv("AMGB200_VERBOSE")) opt.verbose = atoi(getenv("AMGB200_VERBOSE"));
+    const double t_up = wall();
+    amgb200_hier *h = amgb200_upload(mg, &opt);
+    const double t0 = wall();
+    amgb200_rtn rtn = amgb200_solve(h, x->d, b->d, nullptr, 0);
+    const double t1 = wall();
+    if (rtn.nits > 0 || rtn.ares != 0.0) {          // SSS_SOLVE.c:49-50: level 0 aliases the caller's vectors
+        mg->cg[0].x = *x;
+        mg->cg[0].b = *b;
+    }
+    mg->rtn = rtn;
+    amgb200_free(h);
+    printf("AMG solve time: %g s\n", t1 - t0);
+    if (opt.verbose >= 2) printf("libamgb200: hierarchy analysis + upload %g s\n", t0 - t_up);
+    return rtn;
+}
+
+// amg/Solve/SSS_cycle.cu:848-967: one cycle on the host hierarchy; level-0 x/b are cg[0].x/.b
+void SSS_amg_cycle(amgb200_amg *mg) {
+    amgb200_options opt;
+    amgb200_default_options(&opt);
+    amgb200_hier *h = amgb200_upload(mg, &opt);
+    amgb200_cycle(h, mg->cg[0].x.d, mg->cg[0].b.d);
+    amgb200_free(h);
+}
+
+// amg/Solve/SSS_cycle.cu:819-846
+void SSS_amg_coarest_solve(amgb200_mat *A, amgb200_vec *b, amgb200_vec *x, const double ctol) {
+    MiniHier m(A, nullptr, 1);
+    amgb200_options opt;
+    amgb200_default_options(&opt);
+    m.h = amgb200_upload(&m.mg, &opt);
+    amgb200_coarse_solve(m.h, x->d, b->d, ctol, nullptr);
+    amgb200_free(m.h);
+}
+
+static void smoother_dropin(amgb200_smtr *s) {
+    assert(s != NULL);
+    if (s->smoother != 2) {                          // SSS_smooth.c:216-218
+        printf("### ERROR: Wrong smoother type %d!\n", s->smoother);
+        exit(-12);
+    }
+    if (!(s->cf_order && s->ordering)) {
+        fprintf(stderr, "libamgb200: natural-order Gauss-Seidel (SSS_smooth.c:90-137) is not implemented yet\n");
+        exit(-12);
+    }
+    // two levels so that level 0 is a smoothed level; level 1 is a dummy 1x1 system
+    int one_ptr[2] = {0, 1}, one_col[1] = {0};
+    double one_val[1] = {1.0};
+    MiniHier m(s->A, s->ordering, 2);
+    amgb200_mat dummy = {1, 1, 1, one_ptr, one_col, one_val};
+    m.comp[1].A = dummy;
+    // transfers are never touched by the smoother hook: 1 x n / n x 1 empty operators
+    std::vector<int> zr((size_t)s->A->num_rows + 1, 0);
+    int zc[2] = {0, 0};
+    amgb200_mat P = {s->A->num_rows, 1, 0, zr.data(), one_col, one_val};
+    amgb200_mat R = {1, s->A->num_rows, 0, zc, one_col, one_val};
+    m.comp[0].P = P;
+    m.comp[0].R = R;
+    amgb200_options opt;
+    amgb200_default_options(&opt);
+    m.h = amgb200_upload(&m.mg, &opt);
+    amgb200_level_smooth(m.h, 0, s->nsweeps, s->x->d, s->b->d);
+    amgb200_free(m.h);
+}
+void SSS_amg_smoother_pre(amgb200_smtr *s) { smoother_dropin(s); }    // SSS_smooth.c:138-220
+void SSS_amg_smoother_post(amgb200_smtr *s) { smoother_dropin(s); }   // SSS_smooth.c:223-304 (same F-then-C order)
+
+// amg/SSS_utils.c:182-201 and :161-178
+void amgb200_blas_mv_mxy(const amgb200_mat *A, const amgb200_vec *x, amgb200_vec *y) {
+    MiniHier m(A, nullptr, 1);
+    amgb200_options opt;
+    amgb200_default_options(&opt);
+    if (A->num_rows != A->num_cols) { fprintf(stderr, "libamgb200: amgb200_blas_mv_mxy needs a square matrix (use the hierarchy API for P/R)\n"); exit(-13); }
+    m.h = amgb200_upload(&m.mg, &opt);
+    amgb200_level_spmv(m.h, 0, 0, 1.0, x->d, 0, y->d);
+    amgb200_free(m.h);
+}
+void amgb200_blas_mv_amxpy(double alpha, const amgb200_mat *A, const amgb200_vec *x, amgb200_vec *y) {
+    MiniHier m(A, nullptr, 1);
+    amgb200_options opt;
+    amgb200_default_options(&opt);
+    if (A->num_rows != A->num_cols) { fprintf(stderr, "libamgb200: amgb200_blas_mv_amxpy needs a square matrix (use the hierarchy API for P/R)\n"); exit(-13); }
+    m.h = amgb200_upload(&m.mg, &opt);
+    amgb200_level_spmv(m.h, 0, 0, alpha, x->d, 1, y->d);
+    amgb200_free(m.h);
+}
+
+}  // extern "C"

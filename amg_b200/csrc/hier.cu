@@ -1,0 +1,876 @@
+// Device-resident AMG hierarchy and the solve-phase driver (V-cycle, coarsest-level Krylov
+// solvers, outer iteration) -- the B200 replacement of the reference's
+// amg/Solve/SSS_SOLVE.c, SSS_cycle.cu, SSS_smooth.c and SSS_cuda.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/amg_b200.h"
+#include "analysis.h"
+#include "kernels.cuh"
+
+using namespace amgb200;
+
+namespace {
+
+long long g_launches = 0;
+
+#define CUDA_CHECK(call)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            fprintf(stderr, "libamgb200: CUDA error %s at %s:%d: %s (no CPU fallback exists)\n",      \
+                    cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_));                \
+            exit(70);                                                                                 \
+        }                                                                                             \
+    } while (0)
+
+#define LAUNCH(kern, grid, block, stream, ...)                     \
+    do {                                                           \
+        kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);       \
+        ++g_launches;                                              \
+        CUDA_CHECK(cudaGetLastError());                            \
+    } while (0)
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <class T>
+T *dev_alloc(size_t n) {
+    T *p = nullptr;
+    CUDA_CHECK(cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T)));
+    return p;
+}
+template <class T>
+T *dev_upload(const std::vector<T> &v) {
+    T *p = dev_alloc<T>(v.size());
+    if (!v.empty()) CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+
+struct DevMatOwner {
+    DMat v{};
+    long long nnz = 0, padded = 0;
+    int max_row = 0;
+    bool valid = false;
+    void upload(const DevLayout &L) {
+        v.kind = L.kind; v.nrows = L.nrows; v.ncols = L.ncols; v.nitems = L.nitems();
+        v.slice_row = nullptr; v.slice_ptr = nullptr; v.rptr = nullptr;
+        if (L.kind == KIND_SELL) { v.slice_row = dev_upload(L.slice_row); v.slice_ptr = dev_upload(L.slice_ptr); }
+        else v.rptr = dev_upload(L.rptr);
+        v.col = dev_upload(L.col);
+        v.val = dev_upload(L.val);
+        nnz = L.nnz; padded = (long long)L.col.size(); max_row = L.max_row; valid = true;
+    }
+    void release() {
+        if (!valid) return;
+        cudaFree((void *)v.slice_row); cudaFree((void *)v.slice_ptr); cudaFree((void *)v.rptr);
+        cudaFree((void *)v.col); cudaFree((void *)v.val);
+        valid = false;
+    }
+};
+
+struct Level {
+    int n = 0;
+    DevMatOwner A, P, R;
+    int *d_order = nullptr;            // schedule position -> natural row
+    double *x = nullptr, *b = nullptr, *wp = nullptr;
+    bool smoothed = false, ordered = false;
+    int W = 0, wf_count[2] = {0, 0}, pass_items[2] = {0, 0}, pass_rows[2] = {0, 0}, max_width = 0;
+    int *d_item_wf = nullptr, *d_wf_item_ptr = nullptr;
+    unsigned *d_cnt = nullptr;
+    int cnt_cap = 0;
+    bool pattern_symmetric = true;
+    int strategy = 0;                  // 0 = parallel passes, 1 = ordered across the grid, 2 = ordered inside one CTA
+};
+
+}  // namespace
+
+struct amgb200_hier {
+    int nl = 0;
+    std::vector<Level> L;
+    amgb200_pars pars{};
+    amgb200_options opt{};
+    cudaStream_t stream = nullptr;
+    int num_sms = 0, gs_block = 64, gs_max_blocks[2] = {0, 0};
+    bool exact = true;
+    double *d_partial = nullptr;       // 4 x partial_stride block partials
+    int partial_stride = 0;
+    double *d_scal = nullptr;          // 8 reduced scalars
+    double *h_scal = nullptr;          // pinned mirror
+    double *d_xnat = nullptr, *d_bnat = nullptr;
+    double *kry = nullptr;             // Krylov work space on the coarsest level
+    size_t kry_len = 0;
+    bool profile = false;
+    double phase_ms[8] = {0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double upload_s = 0, analysis_s = 0;
+    double last_sumsq = 0;             // sum r_i^2 of the most recent dev_true_residual
+};
+
+namespace {
+
+// ---- small device helpers -----------------------------------------------------------------
+int grid_for(int n) { return std::max(1, (n + BLOCK - 1) / BLOCK); }
+int red_grid(const amgb200_hier *h, int n) { return std::max(1, std::min(h->partial_stride, (n + BLOCK - 1) / BLOCK)); }
+
+void fetch_scalars(amgb200_hier *h, int count) {
+    CUDA_CHECK(cudaMemcpyAsync(h->h_scal, h->d_scal, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+struct PhaseTimer {                    // only active with AMGB200_PROFILE=1 (adds syncs)
+    amgb200_hier *h; int id;
+    PhaseTimer(amgb200_hier *h_, int id_) : h(h_), id(id_) { if (h->profile) CUDA_CHECK(cudaEventRecord(h->ev0, h->stream)); }
+    ~PhaseTimer() {
+        if (!h->profile) return;
+        CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+        CUDA_CHECK(cudaEventSynchronize(h->ev1));
+        float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->phase_ms[id] += ms;
+    }
+};
+
+template <int KIND, int MODE, int RED, bool EXACT>
+void launch_spmv_t(amgb200_hier *h, const DMat &A, const double *x, double *y, const double *b, double alpha) {
+    const int grid = std::max(1, (A.nitems + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    if (RED != RED_NONE && grid > h->partial_stride) {
+        fprintf(stderr, "libamgb200: internal error: reduction grid %d exceeds partial buffer %d\n", grid, h->partial_stride);
+        exit(71);
+    }
+    LAUNCH((spmv_kernel<KIND, MODE, RED, EXACT>), grid, BLOCK, h->stream, A, x, y, b, alpha, h->d_partial);
+    if (RED != RED_NONE) LAUNCH(reduce_partials_kernel, 1, BLOCK, h->stream, h->d_partial, grid, h->partial_stride, 1, 0, h->d_scal);
+}
+template <int KIND, bool EXACT>
+void spmv_k(amgb200_hier *h, const DMat &A, int mode, int red, const double *x, double *y, const double *b, double alpha) {
+    if (mode == MODE_MXY && red == RED_NONE) launch_spmv_t<KIND, MODE_MXY, RED_NONE, EXACT>(h, A, x, y, b, alpha);
+    else if (mode == MODE_AMXPY && red == RED_NONE) launch_spmv_t<KIND, MODE_AMXPY, RED_NONE, EXACT>(h, A, x, y, b, alpha);
+    else if (mode == MODE_RESID && red == RED_NONE) launch_spmv_t<KIND, MODE_RESID, RED_NONE, EXACT>(h, A, x, y, b, alpha);
+    else if (mode == MODE_RESID && red == RED_SUMSQ) launch_spmv_t<KIND, MODE_RESID, RED_SUMSQ, EXACT>(h, A, x, y, b, alpha);
+    else { fprintf(stderr, "libamgb200: unsupported spmv mode %d/%d\n", mode, red); exit(71); }
+}
+// y = A x | y += alpha A x | y = b - A x ; optional fused tree reduction sum(y^2) into d_scal[0]
+void spmv(amgb200_hier *h, const DMat &A, int mode, int red, const double *x, double *y, const double *b, double alpha) {
+    if (A.kind == KIND_SELL) spmv_k<0, true>(h, A, mode, red, x, y, b, alpha);
+    else if (h->exact) spmv_k<1, true>(h, A, mode, red, x, y, b, alpha);
+    else spmv_k<1, false>(h, A, mode, red, x, y, b, alpha);
+}
+
+// ---- Gauss-Seidel -------------------------------------------------------------------------
+template <int KIND, bool EXACT>
+void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
+    if (lv.strategy == 0) {
+        for (int s = 0; s < nsweeps; ++s) {
+            int first = 0;
+            for (int p = 0; p < 2; ++p) {
+                const int cnt = lv.pass_items[p];
+                if (cnt > 0) LAUNCH((gs_pass_kernel<KIND, EXACT>), (cnt + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, BLOCK, h->stream, lv.A.v, lv.b, lv.x, first, first + cnt);
+                first += cnt;
+            }
+        }
+        return;
+    }
+    if (lv.strategy == 2) {
+        const int nw = std::max(1, std::min(16, lv.max_width));
+        LAUNCH((gs_ordered_cta_kernel<KIND, EXACT>), 1, 32 * nw, h->stream, lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps);
+        return;
+    }
+    const int need = nsweeps * lv.W;
+    if (need > lv.cnt_cap) {
+        if (lv.d_cnt) CUDA_CHECK(cudaFree(lv.d_cnt));
+        lv.d_cnt = dev_alloc<unsigned>(need);
+        lv.cnt_cap = need;
+    }
+    CUDA_CHECK(cudaMemsetAsync(lv.d_cnt, 0, (size_t)need * sizeof(unsigned), h->stream));
+    const int wpb = h->gs_block / 32;
+    int grid = (lv.max_width + wpb - 1) / wpb;
+    grid = std::max(1, std::min(grid, h->gs_max_blocks[KIND]));
+    const int items = lv.pass_items[0] + lv.pass_items[1];
+    DMat A = lv.A.v;
+    const double *b = lv.b; double *x = lv.x;
+    const int *iw = lv.d_item_wf, *wp = lv.d_wf_item_ptr;
+    unsigned *cnt = lv.d_cnt;
+    int W = lv.W, ips = items, ns = nsweeps;
+    void *args[] = {&A, &b, &x, &iw, &wp, &cnt, &W, &ips, &ns};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((void *)gs_ordered_grid_kernel<KIND, EXACT>, dim3(grid), dim3(h->gs_block), args, 0, h->stream));
+    ++g_launches;
+}
+
+void smooth(amgb200_hier *h, int l, int nsweeps) {
+    Level &lv = h->L[l];
+    if (nsweeps <= 0) return;
+    if (lv.A.v.kind == KIND_SELL) smooth_k<0, true>(h, lv, nsweeps);
+    else if (h->exact) smooth_k<1, true>(h, lv, nsweeps);
+    else smooth_k<1, false>(h, lv, nsweeps);
+}
+
+// ---- coarsest-level Krylov solvers (host control flow, device vectors) ---------------------
+constexpr double BIGF = 1e+20, SMALLF = 1e-20, SMALLF2 = 1e-40;
+constexpr int MAX_STAG = 20, MAX_RESTART = 30;
+constexpr int ERR_STAG = -42, ERR_SOLSTAG = -43, ERR_TOLSMALL = -44, ERR_MAXIT = -48;
+
+// (x, y) feeding a Krylov coefficient: summed left to right like SSS_blas_array_dot (EXACT) or by a tree (FAST)
+void launch_dot(amgb200_hier *h, int n, const double *x, const double *y, double *d_out) {
+    LAUNCH(dot_seq_kernel, 1, 1024, h->stream, n, x, y, d_out, h->exact ? 1 : 0);
+}
+double dev_dot(amgb200_hier *h, int n, const double *x, const double *y) {
+    launch_dot(h, n, x, y, h->d_scal);
+    fetch_scalars(h, 1);
+    return h->h_scal[0];
+}
+double dev_norm2(amgb200_hier *h, int n, const double *x) { return sqrt(dev_dot(h, n, x, x)); }
+// tree-reduced ||x||_2 for quantities that never feed back into x (printing, stopping)
+double dev_norm2_tree(amgb200_hier *h, int n, const double *x) {
+    const int g = red_grid(h, n);
+    LAUNCH(dot_tree_kernel, g, BLOCK, h->stream, n, x, x, h->d_partial);
+    LAUNCH(reduce_partials_kernel, 1, BLOCK, h->stream, h->d_partial, g, h->partial_stride, 1, 0, h->d_scal);
+    fetch_scalars(h, 1);
+    return sqrt(h->h_scal[0]);
+}
+void dev_copy(amgb200_hier *h, int n, const double *src, double *dst) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+}
+void dev_zero(amgb200_hier *h, int n, double *x) { CUDA_CHECK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), h->stream)); }
+void dev_axpy(amgb200_hier *h, int n, double a, const double *x, double *y) { LAUNCH(axpy_kernel, std::min(grid_for(n), 1184), BLOCK, h->stream, n, a, x, y); }
+void dev_scale(amgb200_hier *h, int n, double a, double *x) { LAUNCH(scale_kernel, std::min(grid_for(n), 1184), BLOCK, h->stream, n, a, x); }
+// outer loop: r = b - A u, returns ||r||_2 (tree-reduced: it is only printed and compared with tol)
+double dev_true_residual(amgb200_hier *h, const DMat &A, const double *u, const double *b, double *r) {
+    spmv(h, A, MODE_RESID, RED_SUMSQ, u, r, b, -1.0);
+    fetch_scalars(h, 1);
+    h->last_sumsq = h->h_scal[0];
+    return sqrt(h->h_scal[0]);
+}
+// Krylov solvers: r = b - A u and (r, r) summed in index order, because it becomes temp1/temp2 of CG
+double krylov_residual(amgb200_hier *h, const DMat &A, const double *u, const double *b, double *r) {
+    spmv(h, A, MODE_RESID, RED_NONE, u, r, b, -1.0);
+    launch_dot(h, A.nrows, r, r, h->d_scal);
+    fetch_scalars(h, 1);
+    h->last_sumsq = h->h_scal[0];
+    return sqrt(h->h_scal[0]);
+}
+
+void ensure_krylov(amgb200_hier *h, size_t len) {
+    if (h->kry_len >= len) return;
+    if (h->kry) CUDA_CHECK(cudaFree(h->kry));
+    h->kry = dev_alloc<double>(len);
+    h->kry_len = len;
+}
+
+// CG with the reference's safeguards: amg/Solve/SSS_cycle.cu:15-437, stop_type = STOP_REL_RES.
+int coarse_cg(amgb200_hier *h, const DMat &A, const double *b, double *u, double tol, int maxit) {
+    const int m = A.nrows;
+    const double maxdiff = tol * 1e-4;
+    int iter = 0, stag = 1, more_step = 1, iter_best = 0;
+    double absres0, absres = BIGF, relres, normu, normr0, absres_best = BIGF;
+    double alpha, beta, temp1, temp2, reldiff, infnormu;
+    ensure_krylov(h, (size_t)5 * m);
+    double *p = h->kry, *r = p + m, *t = r + m, *u_best = t + m;   // z == r (no preconditioner): not materialised
+    const int ug = red_grid(h, m);
+
+    absres0 = krylov_residual(h, A, u, b, r);
+    normr0 = std::max(SMALLF, absres0);
+    relres = absres0 / normr0;
+    if (relres < tol) goto done;
+    dev_copy(h, m, r, p);
+    temp1 = h->last_sumsq;                                          // (z, r) with z = r
+
+    while (iter++ < maxit) {
+        spmv(h, A, MODE_MXY, RED_NONE, p, t, nullptr, 0.0);          // t = A p
+        temp2 = dev_dot(h, m, t, p);                                 // (t, p)
+        if (fabs(temp2) > SMALLF2) alpha = temp1 / temp2;
+        else goto restore;
+        LAUNCH(cg_update_kernel, ug, BLOCK, h->stream, m, alpha, p, t, u, r, h->d_partial, h->partial_stride);
+        LAUNCH(reduce_partials_kernel, 1, BLOCK, h->stream, h->d_partial, ug, h->partial_stride, 2, 1, h->d_scal + 1);
+        launch_dot(h, m, r, r, h->d_scal);                           // (r, r): absres^2 and the next (z, r)
+        fetch_scalars(h, 4);
+        const double rr = h->h_scal[0], uu = h->h_scal[1], pp = h->h_scal[2];
+        infnormu = h->h_scal[3];
+        absres = sqrt(rr);
+        relres = absres / normr0;
+        if (absres < absres_best - maxdiff) {
+            absres_best = absres;
+            iter_best = iter;
+            dev_copy(h, m, u, u_best);
+        }
+        if (infnormu <= SMALLF) { iter = ERR_SOLSTAG; break; }
+        normu = sqrt(uu);
+        reldiff = fabs(alpha) * sqrt(pp) / normu;
+        bool fresh_r = false;
+        if ((stag <= MAX_STAG) & (reldiff < maxdiff)) {
+            absres = krylov_residual(h, A, u, b, r);
+            relres = absres / normr0;
+            fresh_r = true;
+            if (relres < tol) break;
+            if (stag >= MAX_STAG) { iter = ERR_STAG; break; }
+            dev_zero(h, m, p);
+            ++stag;
+        }
+        if (relres < tol) {
+            absres = krylov_residual(h, A, u, b, r);
+            relres = absres / normr0;
+            fresh_r = true;
+            if (relres < tol) break;
+            if (more_step >= MAX_RESTART) { iter = ERR_TOLSMALL; break; }
+            dev_zero(h, m, p);
+            ++more_step;
+        }
+        absres0 = absres;
+        temp2 = fresh_r ? h->last_sumsq : rr;                        // (z, r) with z = r
+        if (h->opt.coarse_mode == AMGB200_BETA_FIX) { beta = temp2 / temp1; temp1 = temp2; }
+        else beta = temp1 / temp1;
+        LAUNCH(axpby_kernel, std::min(grid_for(m), 1184), BLOCK, h->stream, m, 1.0, r, beta, p);
+    }
+restore:
+    if (iter != iter_best) {
+        absres_best = krylov_residual(h, A, u_best, b, r);
+        if (absres > absres_best + maxdiff) dev_copy(h, m, u_best, u);
+    }
+done:
+    (void)absres0;
+    return iter > maxit ? ERR_MAXIT : iter;
+}
+
+// GMRES(restart) as in amg/Solve/SSS_cycle.cu:440-817 (stop_type = STOP_REL_RES).  Reached only
+// when CG fails (never on the BASELINE matrices in FIX mode; every cycle in AS_COMPILED mode).
+int coarse_gmres(amgb200_hier *h, const DMat &A, const double *b, double *x, double tol, int maxit, int restart) {
+    const int n = A.nrows;
+    const double maxdiff = tol * 1e-4;
+    const int restart1 = restart + 1;
+    int iter = 0, iter_best = 0, i, j, k;
+    double r_norm, gamma, t, normr0, absres = BIGF, relres, absres_best = BIGF;
+    ensure_krylov(h, (size_t)(restart1 + 3) * n + (size_t)5 * n);
+    double *base = h->kry + (size_t)5 * n;               // keep clear of CG's vectors
+    double *r = base, *w = r + n, *x_best = w + n;
+    std::vector<double *> p(restart1);
+    for (i = 0; i < restart1; ++i) p[i] = x_best + n + (size_t)i * n;
+    std::vector<double> rs(restart1, 0.0), c(restart, 0.0), s(restart, 0.0);
+    std::vector<std::vector<double>> hh(restart1, std::vector<double>(restart, 0.0));
+
+    r_norm = krylov_residual(h, A, x, b, p[0]);
+    normr0 = std::max(SMALLF, r_norm);
+    relres = r_norm / normr0;
+    if (relres < tol) goto done;
+
+    while (iter < maxit) {
+        rs[0] = r_norm;
+        t = 1.0 / r_norm;
+        dev_scale(h, n, t, p[0]);
+        i = 0;
+        while (i < restart && iter < maxit) {
+            i++; iter++;
+            spmv(h, A, MODE_MXY, RED_NONE, p[i - 1], p[i], nullptr, 0.0);
+            for (j = 0; j < i; j++) {
+                hh[j][i - 1] = dev_dot(h, n, p[j], p[i]);
+                dev_axpy(h, n, -hh[j][i - 1], p[j], p[i]);
+            }
+            t = dev_norm2(h, n, p[i]);
+            hh[i][i - 1] = t;
+            if (t != 0.0) { t = 1.0 / t; dev_scale(h, n, t, p[i]); }
+            for (j = 1; j < i; ++j) {
+                t = hh[j - 1][i - 1];
+                hh[j - 1][i - 1] = s[j - 1] * hh[j][i - 1] + c[j - 1] * t;
+                hh[j][i - 1] = -s[j - 1] * t + c[j - 1] * hh[j][i - 1];
+            }
+            t = hh[i][i - 1] * hh[i][i - 1];
+            t += hh[i - 1][i - 1] * hh[i - 1][i - 1];
+            gamma = sqrt(t);
+            if (gamma == 0.0) gamma = SMALLF;
+            c[i - 1] = hh[i - 1][i - 1] / gamma;
+            s[i - 1] = hh[i][i - 1] / gamma;
+            rs[i] = -s[i - 1] * rs[i - 1];
+            rs[i - 1] = c[i - 1] * rs[i - 1];
+            hh[i - 1][i - 1] = s[i - 1] * hh[i][i - 1] + c[i - 1] * hh[i - 1][i - 1];
+            absres = r_norm = fabs(rs[i]);
+            relres = absres / normr0;
+            if (relres <= tol) break;
+        }
+        rs[i - 1] = rs[i - 1] / hh[i - 1][i - 1];
+        for (k = i - 2; k >= 0; k--) {
+            t = 0.0;
+            for (j = k + 1; j < i; j++) t -= hh[k][j] * rs[j];
+            t += rs[k];
+            rs[k] = t / hh[k][k];
+        }
+        dev_copy(h, n, p[i - 1], w);
+        dev_scale(h, n, rs[i - 1], w);
+        for (j = i - 2; j >= 0; j--) dev_axpy(h, n, rs[j], p[j], w);
+        dev_axpy(h, n, 1.0, w, x);
+        if (absres < absres_best - maxdiff) {
+            absres_best = absres;
+            iter_best = iter;
+            dev_copy(h, n, x, x_best);
+        }
+        if (relres <= tol) {
+            r_norm = krylov_residual(h, A, x, b, r);
+            absres = r_norm;
+            relres = absres / normr0;
+            if (relres <= tol) break;
+            dev_copy(h, n, r, p[0]);
+            i = 0;
+        }
+        for (j = i; j > 0; j--) {
+            rs[j - 1] = -s[j - 1] * rs[j];
+            rs[j] = c[j - 1] * rs[j];
+        }
+        if (i) dev_axpy(h, n, rs[i] - 1.0, p[i], p[i]);
+        for (j = i - 1; j > 0; j--) dev_axpy(h, n, rs[j], p[j], p[i]);
+        if (i) {
+            dev_axpy(h, n, rs[0] - 1.0, p[0], p[0]);
+            dev_axpy(h, n, 1.0, p[i], p[0]);
+        }
+    }
+    if (iter != iter_best) {
+        absres_best = krylov_residual(h, A, x_best, b, r);
+        if (absres > absres_best + maxdiff) dev_copy(h, n, x_best, x);
+    }
+done:
+    return iter >= maxit ? ERR_MAXIT : iter;
+}
+
+// amg/Solve/SSS_cycle.cu:819-846
+int coarse_solve(amgb200_hier *h, const DMat &A, const double *b, double *x, double tol, int its[2]) {
+    const long long nn = (long long)A.nrows * A.nrows;
+    const int maxit = (int)std::max<long long>(250, std::min<long long>(nn, 1000));
+    int status = coarse_cg(h, A, b, x, tol, maxit);
+    if (its) { its[0] = status; its[1] = 0; }
+    if (status < 0) {
+        status = coarse_gmres(h, A, b, x, tol, maxit, MAX_RESTART);
+        if (its) its[1] = status;
+    }
+    if (status < 0) printf("### WARNING: Coarse level solver failed to converge!\n");
+    return status;
+}
+
+// ---- V/W-cycle: amg/Solve/SSS_cycle.cu:848-967 ---------------------------------------------
+void cycle(amgb200_hier *h) {
+    const int nl = h->nl;
+    int cycle_type = h->pars.cycle_type;
+    double tol = h->pars.ctol;
+    int visits[64] = {0}, l = 0;
+    if (tol > h->pars.tol) tol = h->pars.tol * 0.1;
+    if (cycle_type <= 0) cycle_type = 1;
+    for (;;) {
+        while (l < nl - 1) {
+            Level &lv = h->L[l];
+            visits[l]++;
+            { PhaseTimer pt(h, 0); smooth(h, l, h->pars.pre_iter); }
+            { PhaseTimer pt(h, 1); spmv(h, lv.A.v, MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0); }
+            { PhaseTimer pt(h, 2); spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[l + 1].b, nullptr, 0.0); }
+            l++;
+            dev_zero(h, h->L[l].n, h->L[l].x);
+        }
+        { PhaseTimer pt(h, 4); coarse_solve(h, h->L[nl - 1].A.v, h->L[nl - 1].b, h->L[nl - 1].x, tol, nullptr); }
+        while (l > 0) {
+            l--;
+            Level &lv = h->L[l];
+            { PhaseTimer pt(h, 3); spmv(h, lv.P.v, MODE_AMXPY, RED_NONE, h->L[l + 1].x, lv.x, nullptr, 1.0); }
+            { PhaseTimer pt(h, 0); smooth(h, l, h->pars.post_iter); }
+            if (visits[l] < cycle_type) break;
+            visits[l] = 0;
+        }
+        if (l <= 0) break;
+    }
+}
+
+void to_schedule(amgb200_hier *h, int l, const double *d_nat, double *d_sched) {
+    LAUNCH(gather_kernel, grid_for(h->L[l].n), BLOCK, h->stream, h->L[l].n, h->L[l].d_order, d_nat, d_sched);
+}
+void to_natural(amgb200_hier *h, int l, const double *d_sched, double *d_nat) {
+    LAUNCH(scatter_kernel, grid_for(h->L[l].n), BLOCK, h->stream, h->L[l].n, h->L[l].d_order, d_sched, d_nat);
+}
+
+void print_itinfo(int iter, double relres, double absres, double factor) {   // amg/SSS_utils.c:104-133
+    if (iter > 0) {
+        printf("%6d | %13.6e   | %13.6e  | %10.4lf\n", iter, relres, absres, factor);
+    } else {
+        printf("-----------------------------------------------------------\n");
+        printf("It Num |   ||r||/||b||   |     ||r||      |  Conv. Factor\n");
+        printf("-----------------------------------------------------------\n");
+        printf("%6d | %13.6e   | %13.6e  |     -.-- \n", iter, relres, absres);
+    }
+}
+
+void check_level(const amgb200_hier *h, int level) {
+    if (level < 0 || level >= h->nl) { fprintf(stderr, "libamgb200: level %d out of range [0,%d)\n", level, h->nl); exit(72); }
+}
+
+}  // namespace
+
+// =============================================================================================
+// public API
+// =============================================================================================
+extern "C" {
+
+void amgb200_default_options(amgb200_options *o) {
+    memset(o, 0, sizeof(*o));
+    o->coarse_mode = AMGB200_BETA_FIX;
+    o->verbose = 0;
+    o->device = -1;
+    o->fast = 0;
+    if (getenv("AMGB200_FAST") && atoi(getenv("AMGB200_FAST")) > 0) o->fast = 1;
+    const char *e = getenv("AMGB200_COARSE_MODE");
+    if (e && (!strcmp(e, "asc") || !strcmp(e, "as_compiled") || !strcmp(e, "1"))) o->coarse_mode = AMGB200_BETA_AS_COMPILED;
+}
+
+const char *amgb200_version(void) { return "amg-b200 0.1 (sm_100a)"; }
+long long amgb200_launch_count(void) { return g_launches; }
+
+amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_in) {
+    amgb200_options opt;
+    if (opt_in) opt = *opt_in; else amgb200_default_options(&opt);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "libamgb200: no usable CUDA device (%s); this library has no CPU fallback\n", cudaGetErrorString(e));
+        exit(70);
+    }
+    if (opt.device >= 0) CUDA_CHECK(cudaSetDevice(opt.device));
+    if (mg->pars.smoother != 2) {
+        printf("### ERROR: Wrong smoother type %d!\n", mg->pars.smoother);   // SSS_smooth.c:216-218
+        exit(-12);
+    }
+    amgb200_hier *h = new amgb200_hier();
+    h->nl = mg->num_levels;
+    h->pars = mg->pars;
+    h->opt = opt;
+    h->profile = getenv("AMGB200_PROFILE") && atoi(getenv("AMGB200_PROFILE")) > 0;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreate(&h->ev0));
+    CUDA_CHECK(cudaEventCreate(&h->ev1));
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    h->num_sms = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) { fprintf(stderr, "libamgb200: device lacks cooperative launch\n"); exit(70); }
+    if (getenv("AMGB200_GS_BLOCK")) h->gs_block = std::max(32, std::min(BLOCK, atoi(getenv("AMGB200_GS_BLOCK")) / 32 * 32));
+    h->exact = !opt.fast;
+    int per_sm = 0;
+    if (h->exact) {
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_ordered_grid_kernel<0, true>, h->gs_block, 0));
+        h->gs_max_blocks[0] = std::max(1, per_sm * h->num_sms);
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_ordered_grid_kernel<1, true>, h->gs_block, 0));
+        h->gs_max_blocks[1] = std::max(1, per_sm * h->num_sms);
+    } else {
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_ordered_grid_kernel<0, true>, h->gs_block, 0));
+        h->gs_max_blocks[0] = std::max(1, per_sm * h->num_sms);
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_ordered_grid_kernel<1, false>, h->gs_block, 0));
+        h->gs_max_blocks[1] = std::max(1, per_sm * h->num_sms);
+    }
+    const double sell_max_mean = getenv("AMGB200_SELL_MAX_MEAN") ? atof(getenv("AMGB200_SELL_MAX_MEAN")) : (h->exact ? 48.0 : 24.0);
+    const double cta_max_avg = getenv("AMGB200_CTA_MAX_AVG") ? atof(getenv("AMGB200_CTA_MAX_AVG")) : 16.0;
+    auto kind_of = [&](const amgb200_mat &M) { return choose_kind(M, sell_max_mean); };
+
+    const double t0 = now_s();
+    const int nl = h->nl;
+    h->L.resize(nl);
+    std::vector<Schedule> sched(nl);
+    int maxn = 0;
+    for (int l = 0; l < nl; ++l) {
+        const amgb200_comp &c = mg->cg[l];
+        if (l < nl - 1) {
+            if (!(mg->pars.cf_order && c.cfmark.d)) {
+                fprintf(stderr, "libamgb200: natural-order Gauss-Seidel (cf_order=0 / no cfmark, SSS_smooth.c:90-137) is not implemented yet\n");
+                exit(-12);
+            }
+            build_schedule(c.A, c.cfmark.d, sched[l]);
+            if (sched[l].rows_without_diag) {
+                fprintf(stderr, "libamgb200: level %d has %d rows without a stored diagonal; the reference's carried-over "
+                                "diagonal (SSS_smooth.c:13,30) cannot be reproduced in parallel\n", l, sched[l].rows_without_diag);
+                exit(-22);
+            }
+        } else {
+            identity_schedule(c.A.num_rows, sched[l]);
+        }
+        maxn = std::max(maxn, c.A.num_rows);
+    }
+    h->analysis_s = now_s() - t0;
+
+    int max_items = 1;
+    for (int l = 0; l < nl; ++l) {
+        const amgb200_comp &c = mg->cg[l];
+        Level &lv = h->L[l];
+        const Schedule &S = sched[l];
+        lv.n = c.A.num_rows;
+        lv.smoothed = l < nl - 1;
+        DevLayout lay;
+        build_layout(c.A, S.order.data(), S.pos.data(), kind_of(c.A), lv.smoothed ? &S.wf_row_ptr : nullptr, lay);
+        lv.A.upload(lay);
+        max_items = std::max(max_items, lay.nitems());
+        lv.d_order = dev_upload(S.order);
+        lv.x = dev_alloc<double>(lv.n);
+        lv.b = dev_alloc<double>(lv.n);
+        lv.wp = dev_alloc<double>(lv.n);
+        CUDA_CHECK(cudaMemset(lv.x, 0, (size_t)lv.n * sizeof(double)));
+        CUDA_CHECK(cudaMemset(lv.b, 0, (size_t)lv.n * sizeof(double)));
+        lv.pattern_symmetric = S.pattern_symmetric;
+        if (lv.smoothed) {
+            lv.W = S.wf_count[0] + S.wf_count[1];
+            lv.wf_count[0] = S.wf_count[0]; lv.wf_count[1] = S.wf_count[1];
+            lv.pass_rows[0] = S.pass_rows[0]; lv.pass_rows[1] = S.pass_rows[1];
+            lv.ordered = S.wf_count[0] > 1 || S.wf_count[1] > 1;
+            const std::vector<int> &wip = lay.wf_item_ptr;
+            lv.pass_items[0] = wip[S.wf_count[0]] - wip[0];
+            lv.pass_items[1] = wip[lv.W] - wip[S.wf_count[0]];
+            std::vector<int> item_wf((size_t)wip[lv.W]);
+            lv.max_width = 1;
+            for (int w = 0; w < lv.W; ++w) {
+                lv.max_width = std::max(lv.max_width, wip[w + 1] - wip[w]);
+                for (int it = wip[w]; it < wip[w + 1]; ++it) item_wf[it] = w;
+            }
+            lv.d_item_wf = dev_upload(item_wf);
+            lv.d_wf_item_ptr = dev_upload(wip);
+            if (!lv.ordered) lv.strategy = 0;
+            else lv.strategy = ((double)wip[lv.W] / lv.W <= cta_max_avg) ? 2 : 1;
+            if (getenv("AMGB200_GS_STRATEGY") && lv.ordered) lv.strategy = std::max(1, std::min(2, atoi(getenv("AMGB200_GS_STRATEGY"))));
+            // transfers: P_l rows in this level's schedule, columns in the next level's; R_l the other way round
+            DevLayout lp, lr;
+            build_layout(c.P, S.order.data(), sched[l + 1].pos.data(), kind_of(c.P), nullptr, lp);
+            lv.P.upload(lp);
+            max_items = std::max(max_items, lp.nitems());
+            build_layout(c.R, sched[l + 1].order.data(), S.pos.data(), kind_of(c.R), nullptr, lr);
+            lv.R.upload(lr);
+            max_items = std::max(max_items, lr.nitems());
+        }
+    }
+    h->partial_stride = std::max(1184, (max_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    h->d_partial = dev_alloc<double>((size_t)4 * h->partial_stride);
+    h->d_scal = dev_alloc<double>(8);
+    CUDA_CHECK(cudaMallocHost((void **)&h->h_scal, 8 * sizeof(double)));
+    h->d_xnat = dev_alloc<double>(maxn);
+    h->d_bnat = dev_alloc<double>(maxn);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    h->upload_s = now_s() - t0;
+    if (opt.verbose >= 2) {
+        printf("libamgb200: %d levels resident; analysis %.3f s, analysis+upload %.3f s\n", nl, h->analysis_s, h->upload_s);
+        printf("  mode %s; lvl       rows         nnz  kind  F-rows  wavefronts F/C   P nnz      R nnz   sym strat\n", h->exact ? "EXACT" : "FAST");
+        for (int l = 0; l < nl; ++l) {
+            const Level &lv = h->L[l];
+            printf("  %3d %10d %11lld  %s %8d  %6d/%-6d %9lld %9lld  %d\n", l, lv.n, lv.A.nnz, lv.A.v.kind == KIND_SELL ? "SELL" : "CSR ",
+                   lv.pass_rows[0], lv.wf_count[0], lv.wf_count[1], lv.P.valid ? lv.P.nnz : 0LL, lv.R.valid ? lv.R.nnz : 0LL, (int)lv.pattern_symmetric);
+            printf("      strategy %d  max wavefront width %d items\n", lv.strategy, lv.max_width);
+        }
+    }
+    return h;
+}
+
+void amgb200_free(amgb200_hier *h) {
+    if (!h) return;
+    cudaStreamSynchronize(h->stream);
+    for (Level &lv : h->L) {
+        lv.A.release(); lv.P.release(); lv.R.release();
+        cudaFree(lv.d_order); cudaFree(lv.x); cudaFree(lv.b); cudaFree(lv.wp);
+        cudaFree(lv.d_item_wf); cudaFree(lv.d_wf_item_ptr); cudaFree(lv.d_cnt);
+    }
+    cudaFree(h->d_partial); cudaFree(h->d_scal); cudaFreeHost(h->h_scal);
+    cudaFree(h->d_xnat); cudaFree(h->d_bnat); cudaFree(h->kry);
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int amgb200_num_levels(const amgb200_hier *h) { return h->nl; }
+
+void amgb200_level_info(const amgb200_hier *h, int level, long long info[8]) {
+    check_level(h, level);
+    const Level &lv = h->L[level];
+    info[0] = lv.n; info[1] = lv.A.nnz; info[2] = lv.wf_count[0]; info[3] = lv.wf_count[1];
+    info[4] = lv.A.v.kind; info[5] = lv.pass_rows[0];
+    info[6] = lv.P.valid ? lv.P.nnz : 0; info[7] = lv.R.valid ? lv.R.nnz : 0;
+}
+
+double amgb200_algorithmic_bytes(const amgb200_hier *h, int level, int op) {
+    auto S = [](long long z, long long n) { return 12.0 * z + 4.0 * (n + 1); };
+    auto lvl = [&](int l, int o) -> double {
+        const Level &lv = h->L[l];
+        const double n = lv.n, SA = S(lv.A.nnz, lv.n);
+        const double nc = l + 1 < h->nl ? h->L[l + 1].n : 0;
+        switch (o) {
+            case 0: return SA + 4 * n + 8 * n + 16 * n;                       // one GS sweep (both passes)
+            case 1: return SA + 24 * n;                                       // r = b - A x
+            case 2: return lv.R.valid ? S(lv.R.nnz, (long long)nc) + 8 * n + 8 * nc : 0;   // b_c = R r
+            case 3: return lv.P.valid ? S(lv.P.nnz, lv.n) + 8 * nc + 16 * n : 0;           // x += P e
+            case 4: return SA + 16 * n;                                       // y = A x
+            default: return 0;
+        }
+    };
+    if (op != 5) { check_level(h, level); return lvl(level, op); }
+    double tot = 0;                                                           // fused op sequence of one V-cycle
+    for (int l = 0; l + 1 < h->nl; ++l) {
+        const Level &lv = h->L[l];
+        const double n = lv.n, nc = h->L[l + 1].n;
+        tot += (h->pars.pre_iter + h->pars.post_iter) * lvl(l, 0);
+        tot += S(lv.A.nnz, lv.n) + 16 * n + S(lv.R.nnz, (long long)nc) + 8 * nc;   // residual (+) restrict, r not materialised
+        tot += 8 * nc;                                                        // x_c = 0
+        tot += lvl(l, 3);
+    }
+    tot += S(h->L[0].A.nnz, h->L[0].n) + 16.0 * h->L[0].n;                    // outer residual (+) norm
+    return tot;
+}
+
+void amgb200_last_phase_ms(const amgb200_hier *h, double ms[8]) { for (int i = 0; i < 8; ++i) ms[i] = h->phase_ms[i]; }
+
+amgb200_rtn amgb200_solve_device(amgb200_hier *h, double *d_x, const double *d_b, double *res_hist, int hist_cap) {
+    amgb200_rtn rtn = {0, 0, 0};
+    Level &l0 = h->L[0];
+    for (int i = 0; i < 8; ++i) h->phase_ms[i] = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (h->profile) { CUDA_CHECK(cudaEventCreate(&t0)); CUDA_CHECK(cudaEventCreate(&t1)); CUDA_CHECK(cudaEventRecord(t0, h->stream)); }
+    to_schedule(h, 0, d_b, l0.b);
+    to_schedule(h, 0, d_x, l0.x);
+    const double sumb = dev_norm2_tree(h, l0.n, l0.b);
+    double absres0 = sumb;
+    if (h->opt.verbose >= 1) print_itinfo(0, 1.0, sumb, 0.0);
+    if (fabs(sumb) == 0.) {                                                   // SSS_SOLVE.c:41-46
+        CUDA_CHECK(cudaMemsetAsync(d_x, 0, (size_t)l0.n * sizeof(double), h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        return rtn;
+    }
+    int iter = 0;
+    while (++iter <= h->pars.max_it) {
+        cycle(h);
+        double absres;
+        { PhaseTimer pt(h, 5); absres = dev_true_residual(h, l0.A.v, l0.x, l0.b, l0.wp); }
+        const double relres = absres / sumb;
+        if (h->opt.verbose >= 1) print_itinfo(iter, relres, absres, absres / absres0);
+        absres0 = absres;
+        if (res_hist && iter <= hist_cap) res_hist[iter - 1] = absres;
+        rtn.ares = absres; rtn.rres = relres; rtn.nits = iter;
+        if (relres < h->pars.tol) break;
+    }
+    to_natural(h, 0, l0.x, d_x);
+    if (h->profile) {
+        CUDA_CHECK(cudaEventRecord(t1, h->stream)); CUDA_CHECK(cudaEventSynchronize(t1));
+        float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, t0, t1)); h->phase_ms[6] = ms;
+        cudaEventDestroy(t0); cudaEventDestroy(t1);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return rtn;
+}
+
+amgb200_rtn amgb200_solve(amgb200_hier *h, double *x, const double *b, double *res_hist, int hist_cap) {
+    const int n = h->L[0].n;
+    CUDA_CHECK(cudaMemcpyAsync(h->d_xnat, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h->d_bnat, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    amgb200_rtn rtn = amgb200_solve_device(h, h->d_xnat, h->d_bnat, res_hist, hist_cap);
+    CUDA_CHECK(cudaMemcpyAsync(x, h->d_xnat, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return rtn;
+}
+
+void amgb200_cycle(amgb200_hier *h, double *x, const double *b) {
+    Level &l0 = h->L[0];
+    const int n = l0.n;
+    CUDA_CHECK(cudaMemcpyAsync(h->d_xnat, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h->d_bnat, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    to_schedule(h, 0, h->d_bnat, l0.b);
+    to_schedule(h, 0, h->d_xnat, l0.x);
+    cycle(h);
+    to_natural(h, 0, l0.x, h->d_xnat);
+    CUDA_CHECK(cudaMemcpyAsync(x, h->d_xnat, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+void amgb200_level_spmv(amgb200_hier *h, int level, int which, double alpha, const double *x, int beta, double *y) {
+    check_level(h, level);
+    Level &lv = h->L[level];
+    if (which != 0 && !lv.P.valid) { fprintf(stderr, "libamgb200: level %d has no transfer operators\n", level); exit(72); }
+    const int in_l = which == 1 ? level + 1 : level, out_l = which == 2 ? level + 1 : level;
+    const DMat &M = which == 0 ? lv.A.v : which == 1 ? lv.P.v : lv.R.v;
+    Level &li = h->L[in_l], &lo = h->L[out_l];
+    // scratch: input in li.wp (schedule), output in lo.b ... use level vectors that the hooks own
+    double *din = li.wp, *dout = lo.b;
+    if (in_l == out_l) dout = lo.b;
+    CUDA_CHECK(cudaMemcpyAsync(h->d_xnat, x, (size_t)li.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    to_schedule(h, in_l, h->d_xnat, din);
+    if (beta) {
+        CUDA_CHECK(cudaMemcpyAsync(h->d_bnat, y, (size_t)lo.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        to_schedule(h, out_l, h->d_bnat, dout);
+        spmv(h, M, MODE_AMXPY, RED_NONE, din, dout, nullptr, alpha);
+    } else {
+        spmv(h, M, MODE_MXY, RED_NONE, din, dout, nullptr, 0.0);
+        if (alpha != 1.0) dev_scale(h, lo.n, alpha, dout);
+    }
+    to_natural(h, out_l, dout, h->d_bnat);
+    CUDA_CHECK(cudaMemcpyAsync(y, h->d_bnat, (size_t)lo.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+void amgb200_level_smooth(amgb200_hier *h, int level, int nsweeps, double *x, const double *b) {
+    check_level(h, level);
+    Level &lv = h->L[level];
+    if (!lv.smoothed) { fprintf(stderr, "libamgb200: level %d is the coarsest level (no smoother)\n", level); exit(72); }
+    CUDA_CHECK(cudaMemcpyAsync(h->d_xnat, x, (size_t)lv.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h->d_bnat, b, (size_t)lv.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    to_schedule(h, level, h->d_xnat, lv.x);
+    to_schedule(h, level, h->d_bnat, lv.b);
+    smooth(h, level, nsweeps);
+    to_natural(h, level, lv.x, h->d_xnat);
+    CUDA_CHECK(cudaMemcpyAsync(x, h->d_xnat, (size_t)lv.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+double amgb200_level_residual(amgb200_hier *h, int level, const double *x, const double *b, double *r) {
+    check_level(h, level);
+    Level &lv = h->L[level];
+    CUDA_CHECK(cudaMemcpyAsync(h->d_xnat, x, (size_t)lv.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h->d_bnat, b, (size_t)lv.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    to_schedule(h, level, h->d_xnat, lv.x);
+    to_schedule(h, level, h->d_bnat, lv.b);
+    const double nrm = dev_true_residual(h, lv.A.v, lv.x, lv.b, lv.wp);
+    if (r) {
+        to_natural(h, level, lv.wp, h->d_xnat);
+        CUDA_CHECK(cudaMemcpyAsync(r, h->d_xnat, (size_t)lv.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
+    return nrm;
+}
+
+int amgb200_coarse_solve(amgb200_hier *h, double *x, const double *b, double tol, int its[2]) {
+    Level &lv = h->L[h->nl - 1];
+    CUDA_CHECK(cudaMemcpyAsync(h->d_xnat, x, (size_t)lv.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h->d_bnat, b, (size_t)lv.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    to_schedule(h, h->nl - 1, h->d_xnat, lv.x);
+    to_schedule(h, h->nl - 1, h->d_bnat, lv.b);
+    const int st = coarse_solve(h, lv.A.v, lv.b, lv.x, tol, its);
+    to_natural(h, h->nl - 1, lv.x, h->d_xnat);
+    CUDA_CHECK(cudaMemcpyAsync(x, h->d_xnat, (size_t)lv.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return st;
+}
+
+double amgb200_time_op(amgb200_hier *h, int level, int op, int reps) {
+    check_level(h, level);
+    Level &lv = h->L[level];
+    if (reps < 1) reps = 1;
+    if ((op == 0 && !lv.smoothed) || ((op == 2 || op == 3) && !lv.P.valid)) return 0.0;
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+    auto run = [&]() {
+        switch (op) {
+            case 0: smooth(h, level, 1); break;
+            case 1: spmv(h, lv.A.v, MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0); break;
+            case 2: spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[level + 1].b, nullptr, 0.0); break;
+            case 3: spmv(h, lv.P.v, MODE_AMXPY, RED_NONE, h->L[level + 1].x, lv.x, nullptr, 1.0); break;
+            default: spmv(h, lv.A.v, MODE_MXY, RED_NONE, lv.x, lv.wp, nullptr, 0.0); break;
+        }
+    };
+    run(); run();                                    // warm-up
+    CUDA_CHECK(cudaEventRecord(a, h->stream));
+    for (int i = 0; i < reps; ++i) run();
+    CUDA_CHECK(cudaEventRecord(b, h->stream));
+    CUDA_CHECK(cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return ms / reps;
+}
+
+}  // extern "C"

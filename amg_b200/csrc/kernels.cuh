@@ -1,0 +1,504 @@
+// sm_100a kernels of the AMG solve phase.  All vectors and matrices are in the level's
+// schedule numbering (analysis.h); fp64 values, int32 indices.
+//
+// Arithmetic contract (EXACT mode, the default).  A 1-ulp difference in x is amplified by
+// |x|/|r| in the residual, so the north-star bar "residual history within 1e-10 relative" can
+// only be met when every operation that feeds x is rounded exactly like the reference's CPU code
+// (gcc, baseline x86-64: no FMA, strictly sequential sums in CSR storage order).  Therefore:
+//   * every product a_k*x_j is rounded on its own (__dmul_rn, never contracted),
+//   * every row sum is accumulated in storage order by one dependent chain of __dadd_rn/__dsub_rn
+//     -- thread-per-row for short rows (SELL layout, coalesced across rows), warp-per-row for long
+//     rows, where the 32 lanes fetch and multiply 32 entries in parallel and the chain consumes the
+//     products in order through warp shuffles (adding +0.0 for padding is exact),
+//   * dot products that feed the Krylov coefficients are summed left to right by one thread.
+// Norms that only steer printing / stopping use deterministic tree reductions.
+// FAST mode (opt-in) replaces the in-order chain of the warp-per-row kernels by a shuffle tree:
+// ~1e-16 relative per row, which the |x|/|r| amplification turns into ~1e-7 at the last V-cycle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace amgb200 {
+
+struct DMat {                      // device view of a DevLayout
+    int kind, nrows, ncols, nitems;
+    const int *slice_row;          // SELL
+    const long long *slice_ptr;    // SELL
+    const int *rptr;               // CSR
+    const int *col;
+    const double *val;
+};
+
+enum { MODE_MXY = 0, MODE_AMXPY = 1, MODE_RESID = 2 };   // y = Ax | y += alpha*Ax | y = b - Ax
+enum { RED_NONE = 0, RED_SUMSQ = 1 };                    // fused tree reduction over the output rows
+
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int BLOCK = 32 * WARPS_PER_BLOCK;
+constexpr double GS_TINY = 1e-20;                         // SMALLFLOAT, amg/SSS_main.h:34
+constexpr unsigned FULL = 0xffffffffu;
+
+// COH: x is being updated by other SMs during this launch -> read it at L2 (L1 is not coherent)
+template <bool COH>
+__device__ __forceinline__ double ld_x(const double *p) { return COH ? __ldcg(p) : *p; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+// block-level deterministic tree sum of one value per thread; result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double *smem /* >= 32 doubles */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = lane < (int)(blockDim.x >> 5) ? smem[lane] : 0.0;
+        v = warp_sum(v);
+    }
+    return v;
+}
+__device__ __forceinline__ double block_max(double v, double *smem) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = lane < (int)(blockDim.x >> 5) ? smem[lane] : 0.0;
+        v = warp_max(v);
+    }
+    return v;
+}
+
+// ==========================================================================================
+// Thread-per-row work item: one SELL slice (<= 32 rows), lane r owns row slice_row[s]+r.
+// prologue() only touches the (static) matrix, so it may run before a dependency wait.
+// ==========================================================================================
+template <int SCH>
+struct SellItem {
+    const int *cp;
+    const double *vp;
+    int width, k, r1;
+    int j[SCH];
+    double a[SCH];
+    __device__ __forceinline__ void load_chunk(int e0) {
+#pragma unroll
+        for (int u = 0; u < SCH; ++u) {
+            if (e0 + u < width) { j[u] = cp[(size_t)(e0 + u) * 32]; a[u] = vp[(size_t)(e0 + u) * 32]; }
+            else { j[u] = -1; a[u] = 0.0; }
+        }
+    }
+    __device__ __forceinline__ void prologue(const DMat &A, int s, int lane) {
+        const int r0 = A.slice_row[s];
+        r1 = A.slice_row[s + 1];
+        const long long p0 = A.slice_ptr[s];
+        width = (int)((A.slice_ptr[s + 1] - p0) >> 5);
+        k = r0 + lane;
+        cp = A.col + p0 + lane;
+        vp = A.val + p0 + lane;
+        load_chunk(0);
+    }
+};
+
+// Gauss-Seidel row update (amg/Solve/SSS_smooth.c:18-33): t = b_i - sum_{j != i} a_ij x_j in storage
+// order; x_i = t / a_ii when |a_ii| > 1e-20
+template <bool COH, int SCH>
+__device__ __forceinline__ void gs_finish_sell(SellItem<SCH> &it, const double *__restrict__ b, double *x) {
+    const bool active = it.k < it.r1;
+    double t = active ? b[it.k] : 0.0, d = 0.0;
+    for (int e0 = 0; e0 < it.width; e0 += SCH) {
+        double xv[SCH];
+#pragma unroll
+        for (int u = 0; u < SCH; ++u) xv[u] = (it.j[u] >= 0 && it.j[u] != it.k) ? ld_x<COH>(x + it.j[u]) : 0.0;
+        int jn[SCH];
+        double an[SCH];
+        const bool more = e0 + SCH < it.width;
+        if (more) {                                   // next chunk's matrix entries fly during this chunk's chain
+#pragma unroll
+            for (int u = 0; u < SCH; ++u) {
+                if (e0 + SCH + u < it.width) { jn[u] = it.cp[(size_t)(e0 + SCH + u) * 32]; an[u] = it.vp[(size_t)(e0 + SCH + u) * 32]; }
+                else { jn[u] = -1; an[u] = 0.0; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SCH; ++u) {
+            if (it.j[u] == it.k) d = it.a[u];
+            else if (it.j[u] >= 0) t = __dsub_rn(t, __dmul_rn(it.a[u], xv[u]));
+        }
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < SCH; ++u) { it.j[u] = jn[u]; it.a[u] = an[u]; }
+        }
+    }
+    if (active && fabs(d) > GS_TINY) x[it.k] = __ddiv_rn(t, d);
+}
+
+// row sum t = sum_k a_k x_{j_k} from 0.0 in storage order (amg/SSS_utils.c:169-177, :190-200)
+template <int SCH>
+__device__ __forceinline__ double spmv_finish_sell(SellItem<SCH> &it, const double *__restrict__ x) {
+    double t = 0.0;
+    for (int e0 = 0; e0 < it.width; e0 += SCH) {
+        double xv[SCH];
+#pragma unroll
+        for (int u = 0; u < SCH; ++u) xv[u] = it.j[u] >= 0 ? x[it.j[u]] : 0.0;
+        int jn[SCH];
+        double an[SCH];
+        const bool more = e0 + SCH < it.width;
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < SCH; ++u) {
+                if (e0 + SCH + u < it.width) { jn[u] = it.cp[(size_t)(e0 + SCH + u) * 32]; an[u] = it.vp[(size_t)(e0 + SCH + u) * 32]; }
+                else { jn[u] = -1; an[u] = 0.0; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SCH; ++u)
+            if (it.j[u] >= 0) t = __dadd_rn(t, __dmul_rn(it.a[u], xv[u]));
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < SCH; ++u) { it.j[u] = jn[u]; it.a[u] = an[u]; }
+        }
+    }
+    return t;
+}
+
+// ==========================================================================================
+// Warp-per-row work item (CSR): lanes fetch/multiply 32 entries at a time; the products are folded
+// into the accumulator in storage order through shuffles (EXACT) or by a shuffle tree (FAST).
+// Three-stage software pipeline: [col/val load] -> [x gather] -> [chain].
+// ==========================================================================================
+struct CsrItem {
+    int k, p0, p1;
+    int jA, jB;        // B = chunk being consumed next, A = the one after
+    double aA, aB;
+    __device__ __forceinline__ void prologue(const DMat &A, int row, int lane) {
+        k = row;
+        p0 = A.rptr[row];
+        p1 = A.rptr[row + 1];
+        int p = p0 + lane;
+        if (p < p1) { jB = A.col[p]; aB = A.val[p]; } else { jB = -1; aB = 0.0; }
+        p += 32;
+        if (p < p1) { jA = A.col[p]; aA = A.val[p]; } else { jA = -1; aA = 0.0; }
+    }
+};
+
+// SUB: accumulate t - prod (Gauss-Seidel) else t + prod (SpMV).  GS: the diagonal entry is skipped and
+// returned through d (valid in all lanes).  Result valid in all lanes.
+template <bool COH, bool EXACT, bool GS>
+__device__ __forceinline__ double csr_row_chain(const DMat &A, CsrItem &it, const double *x, double t, double &d, int lane) {
+    double dl = 0.0, tree = 0.0;
+    double xB = 0.0;
+    {
+        const bool use = it.jB >= 0 && !(GS && it.jB == it.k);
+        if (use) xB = ld_x<COH>(x + it.jB);
+    }
+    for (int base = it.p0; base < it.p1; base += 32) {
+        // stage 2 for the next chunk: gather x (its column indices were loaded one iteration ago)
+        double xA = 0.0;
+        {
+            const bool use = it.jA >= 0 && !(GS && it.jA == it.k);
+            if (use) xA = ld_x<COH>(x + it.jA);
+        }
+        // stage 1 for the chunk after that
+        int jN = -1;
+        double aN = 0.0;
+        {
+            const int p = base + 64 + lane;
+            if (p < it.p1) { jN = A.col[p]; aN = A.val[p]; }
+        }
+        // stage 3: consume chunk B
+        double prod = 0.0;
+        if (it.jB >= 0) {
+            if (GS && it.jB == it.k) dl = it.aB;
+            else prod = __dmul_rn(it.aB, xB);
+        }
+        if (EXACT) {
+            const int cnt = min(32, it.p1 - base);
+            int q = 0;
+            for (; q + 8 <= cnt; q += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double pq = __shfl_sync(FULL, prod, q + u);
+                    t = GS ? __dsub_rn(t, pq) : __dadd_rn(t, pq);
+                }
+            }
+            for (; q < cnt; ++q) {
+                const double pq = __shfl_sync(FULL, prod, q);
+                t = GS ? __dsub_rn(t, pq) : __dadd_rn(t, pq);
+            }
+        } else {
+            tree = __dadd_rn(tree, prod);
+        }
+        it.jB = it.jA; it.aB = it.aA; xB = xA;
+        it.jA = jN; it.aA = aN;
+    }
+    if (!EXACT) {
+        tree = warp_sum(tree);
+        t = GS ? __dsub_rn(t, tree) : __dadd_rn(t, tree);
+    }
+    d = warp_sum(dl);          // exactly one lane holds the diagonal; adding zeros is exact
+    return t;
+}
+
+template <bool COH, bool EXACT>
+__device__ __forceinline__ void gs_finish_csr(const DMat &A, CsrItem &it, const double *__restrict__ b, double *x, int lane) {
+    double d;
+    const double t = csr_row_chain<COH, EXACT, true>(A, it, x, b[it.k], d, lane);
+    if (lane == 0 && fabs(d) > GS_TINY) x[it.k] = __ddiv_rn(t, d);
+}
+
+// ------------------------------------------------------------------------------------------
+// Gauss-Seidel kernels
+// ------------------------------------------------------------------------------------------
+// one fully parallel pass (a pass whose dependency DAG has depth 1): items [item0, item1)
+template <int KIND, bool EXACT>
+__global__ void __launch_bounds__(BLOCK) gs_pass_kernel(DMat A, const double *__restrict__ b, double *x, int item0, int item1) {
+    const int lane = threadIdx.x & 31;
+    const int it = item0 + blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (it >= item1) return;
+    if constexpr (KIND == 0) {
+        SellItem<8> w;
+        w.prologue(A, it, lane);
+        gs_finish_sell<false>(w, b, x);
+    } else {
+        CsrItem w;
+        w.prologue(A, it, lane);
+        gs_finish_csr<false, EXACT>(A, w, b, x, lane);
+    }
+}
+
+// Ordered sweeps across the grid: persistent warps walk the item list of nsweeps x (F pass, C pass)
+// in schedule order; an item of (global) wavefront g starts when the completion counter of
+// wavefront g-1 has reached that wavefront's item count.  All warps must be co-resident
+// (cooperative launch).  cnt[] holds nsweeps*W zero-initialised counters.  The matrix entries of an
+// item are fetched before the wait.
+template <int KIND, bool EXACT>
+__global__ void __launch_bounds__(BLOCK) gs_ordered_grid_kernel(DMat A, const double *__restrict__ b, double *x,
+                                                                const int *__restrict__ item_wf, const int *__restrict__ wf_item_ptr,
+                                                                unsigned *cnt, int W, int items_per_sweep, int nsweeps) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const long long total = (long long)items_per_sweep * nsweeps;
+    int known = -1;                               // highest global wavefront known to be complete
+    for (long long t = warp; t < total; t += nwarps) {
+        const int sweep = (int)(t / items_per_sweep);
+        const int it = (int)(t - (long long)sweep * items_per_sweep);
+        const int wl = item_wf[it];
+        const int g = sweep * W + wl;
+        SellItem<16> ws;
+        CsrItem wc;
+        if constexpr (KIND == 0) ws.prologue(A, it, lane); else wc.prologue(A, it, lane);
+        if (g - 1 > known) {
+            if (lane == 0) {
+                const int pw = wl == 0 ? W - 1 : wl - 1;
+                const unsigned need = (unsigned)(wf_item_ptr[pw + 1] - wf_item_ptr[pw]);
+                const volatile unsigned *c = cnt + (g - 1);
+                while (*c < need) { }
+            }
+            __syncwarp();
+            __threadfence();
+            known = g - 1;
+        }
+        if constexpr (KIND == 0) gs_finish_sell<true>(ws, b, x);
+        else gs_finish_csr<true, EXACT>(A, wc, b, x, lane);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(cnt + g, 1u);
+    }
+}
+
+// Ordered sweeps inside ONE thread block (levels whose wavefronts are narrow): warps take the items
+// of a wavefront round-robin, wavefronts are separated by __syncthreads.  No inter-SM traffic on the
+// dependency path; x is read through L1 (block-level visibility after the barrier).
+template <int KIND, bool EXACT>
+__global__ void __launch_bounds__(512) gs_ordered_cta_kernel(DMat A, const double *__restrict__ b, double *x,
+                                                              const int *__restrict__ wf_item_ptr, int W, int nsweeps) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int totalw = W * nsweeps;
+    SellItem<8> ws;
+    CsrItem wc;
+    int i0 = wf_item_ptr[0], i1 = wf_item_ptr[1];
+    bool have = i0 + warp < i1;
+    if (have) { if constexpr (KIND == 0) ws.prologue(A, i0 + warp, lane); else wc.prologue(A, i0 + warp, lane); }
+    for (int g = 0; g < totalw; ++g) {
+        if (have) {
+            if constexpr (KIND == 0) gs_finish_sell<false>(ws, b, x); else gs_finish_csr<false, EXACT>(A, wc, b, x, lane);
+            for (int it = i0 + warp + nw; it < i1; it += nw) {         // wavefront wider than the block
+                if constexpr (KIND == 0) { ws.prologue(A, it, lane); gs_finish_sell<false>(ws, b, x); }
+                else { wc.prologue(A, it, lane); gs_finish_csr<false, EXACT>(A, wc, b, x, lane); }
+            }
+        }
+        if (g + 1 < totalw) {                                         // fetch the next wavefront's matrix entries before the barrier
+            const int wl = (g + 1) % W;
+            i0 = wf_item_ptr[wl]; i1 = wf_item_ptr[wl + 1];
+            have = i0 + warp < i1;
+            if (have) { if constexpr (KIND == 0) ws.prologue(A, i0 + warp, lane); else wc.prologue(A, i0 + warp, lane); }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// SpMV family (amg/SSS_utils.c:161-201)
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ double spmv_store(double t, double alpha, const double *__restrict__ b, double *y, int k) {
+    double out;
+    if (MODE == MODE_MXY) out = t;
+    else if (MODE == MODE_AMXPY) out = __dadd_rn(y[k], __dmul_rn(t, alpha));
+    else out = __dadd_rn(b[k], __dmul_rn(t, -1.0));
+    y[k] = out;
+    return out;
+}
+
+template <int KIND, int MODE, int RED, bool EXACT>
+__global__ void __launch_bounds__(BLOCK) spmv_kernel(DMat A, const double *__restrict__ x, double *y, const double *__restrict__ b,
+                                                     double alpha, double *partial) {
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31;
+    const int it = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    double contrib = 0.0;
+    if (it < A.nitems) {
+        if constexpr (KIND == 0) {
+            SellItem<8> w;
+            w.prologue(A, it, lane);
+            const double t = spmv_finish_sell(w, x);
+            if (w.k < w.r1) {
+                const double out = spmv_store<MODE>(t, alpha, b, y, w.k);
+                if (RED == RED_SUMSQ) contrib = __dmul_rn(out, out);
+            }
+        } else {
+            CsrItem w;
+            w.prologue(A, it, lane);
+            double d;
+            const double t = csr_row_chain<false, EXACT, false>(A, w, x, 0.0, d, lane);
+            if (lane == 0) {
+                const double out = spmv_store<MODE>(t, alpha, b, y, it);
+                if (RED == RED_SUMSQ) contrib = __dmul_rn(out, out);
+            }
+        }
+    }
+    if (RED != RED_NONE) {
+        const double s = block_sum(contrib, red);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+}
+
+// out[q] = sum_{i<nparts} partial[q*stride + i] for q < nsum ; out[q] = max(...) for nsum <= q < nsum+nmax
+__global__ void __launch_bounds__(BLOCK) reduce_partials_kernel(const double *__restrict__ partial, int nparts, int stride,
+                                                                int nsum, int nmax, double *out) {
+    __shared__ double red[32];
+    for (int q = 0; q < nsum + nmax; ++q) {
+        const double *p = partial + (size_t)q * stride;
+        double v = 0.0;
+        if (q < nsum) {
+            for (int i = threadIdx.x; i < nparts; i += blockDim.x) v = __dadd_rn(v, p[i]);
+            v = block_sum(v, red);
+        } else {
+            for (int i = threadIdx.x; i < nparts; i += blockDim.x) v = fmax(v, p[i]);
+            v = block_max(v, red);
+        }
+        if (threadIdx.x == 0) out[q] = v;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// BLAS-1 pieces of the coarsest-level Krylov solvers (amg/SSS_utils.c:138-260)
+// ------------------------------------------------------------------------------------------
+// out[0] = sum_i x_i*y_i accumulated strictly left to right from 0.0 (SSS_blas_array_dot, :206-214),
+// bit-identical to the CPU loop.  One block: all threads stage the separately rounded products of a
+// tile in shared memory, thread 0 folds them in index order.  seq == 0 -> tree sum instead (FAST).
+constexpr int DOT_TILE = 4096;
+__global__ void __launch_bounds__(1024) dot_seq_kernel(int n, const double *__restrict__ x, const double *__restrict__ y, double *out, int seq) {
+    __shared__ double prod[DOT_TILE];
+    __shared__ double red[32];
+    double acc = 0.0;
+    if (!seq) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) acc = __dadd_rn(acc, __dmul_rn(x[i], y[i]));
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) out[0] = acc;
+        return;
+    }
+    for (int base = 0; base < n; base += DOT_TILE) {
+        const int m = min(DOT_TILE, n - base);
+        for (int i = threadIdx.x; i < m; i += blockDim.x) prod[i] = __dmul_rn(x[base + i], y[base + i]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int i = 0;
+            for (; i + 8 <= m; i += 8) {
+                double p0 = prod[i], p1 = prod[i + 1], p2 = prod[i + 2], p3 = prod[i + 3];
+                double p4 = prod[i + 4], p5 = prod[i + 5], p6 = prod[i + 6], p7 = prod[i + 7];
+                acc = __dadd_rn(acc, p0); acc = __dadd_rn(acc, p1); acc = __dadd_rn(acc, p2); acc = __dadd_rn(acc, p3);
+                acc = __dadd_rn(acc, p4); acc = __dadd_rn(acc, p5); acc = __dadd_rn(acc, p6); acc = __dadd_rn(acc, p7);
+            }
+            for (; i < m; ++i) acc = __dadd_rn(acc, prod[i]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = acc;
+}
+
+// CG update (amg/Solve/SSS_cycle.cu:196-250): u += alpha p ; r += (-alpha) t ; tree partials of
+// u.u, p.p and max|u| (they only steer the safeguards) -> partial[q*stride + block], q = 0..2
+__global__ void __launch_bounds__(BLOCK) cg_update_kernel(int n, double alpha, const double *__restrict__ p, const double *__restrict__ t,
+                                                          double *u, double *r, double *partial, int stride) {
+    __shared__ double red[32];
+    double uu = 0.0, pp = 0.0, um = 0.0;
+    const double nalpha = -alpha;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double pi = p[i];
+        const double ui = __dadd_rn(u[i], __dmul_rn(alpha, pi));
+        r[i] = __dadd_rn(r[i], __dmul_rn(nalpha, t[i]));
+        u[i] = ui;
+        uu = __dadd_rn(uu, __dmul_rn(ui, ui));
+        pp = __dadd_rn(pp, __dmul_rn(pi, pi));
+        um = fmax(um, fabs(ui));
+    }
+    uu = block_sum(uu, red); if (threadIdx.x == 0) partial[0 * stride + blockIdx.x] = uu;
+    pp = block_sum(pp, red); if (threadIdx.x == 0) partial[1 * stride + blockIdx.x] = pp;
+    um = block_max(um, red); if (threadIdx.x == 0) partial[2 * stride + blockIdx.x] = um;
+}
+
+// y = a*x + b*y   (SSS_blas_array_axpby, SSS_utils.c:248-253)
+__global__ void __launch_bounds__(BLOCK) axpby_kernel(int n, double a, const double *__restrict__ x, double b, double *y) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        y[i] = __dadd_rn(__dmul_rn(a, x[i]), __dmul_rn(b, y[i]));
+}
+// y += a*x   (SSS_blas_array_axpy, :217-222); x may alias y
+__global__ void __launch_bounds__(BLOCK) axpy_kernel(int n, double a, const double *x, double *y) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        y[i] = __dadd_rn(y[i], __dmul_rn(a, x[i]));
+}
+// x *= a   (SSS_blas_array_ax, :255-260)
+__global__ void __launch_bounds__(BLOCK) scale_kernel(int n, double a, double *x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = __dmul_rn(x[i], a);
+}
+// partial[block] = tree sum of x_i*y_i (norms that do not feed back into x)
+__global__ void __launch_bounds__(BLOCK) dot_tree_kernel(int n, const double *__restrict__ x, const double *__restrict__ y, double *partial) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s = __dadd_rn(s, __dmul_rn(x[i], y[i]));
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// permutations between natural and schedule numbering
+__global__ void __launch_bounds__(BLOCK) gather_kernel(int n, const int *__restrict__ order, const double *__restrict__ in, double *out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = in[order[k]];
+}
+__global__ void __launch_bounds__(BLOCK) scatter_kernel(int n, const int *__restrict__ order, const double *__restrict__ in, double *out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[order[k]] = in[k];
+}
+
+}  // namespace amgb200

@@ -133,7 +133,12 @@ typedef struct amgb200_options_ {
     int coarse_mode;             /* AMGB200_BETA_* (default FIX; env AMGB200_COARSE_MODE=asc overrides) */
     int verbose;                 /* 0 quiet, 1 reference's iteration table, 2 + level/kernel table */
     int device;                  /* CUDA device ordinal, -1 = current */
-    int reserved[5];
+    int fast;                    /* 0 (default): EXACT arithmetic -- every sum that feeds x is accumulated in the
+                                    reference's order, results bit-identical to the reference's CPU path;
+                                    1: FAST -- long rows and Krylov dot products use tree reductions (~1e-16 per
+                                    operation, amplified by |x|/|r| to ~1e-7 in the last residuals).
+                                    env AMGB200_FAST=1 overrides */
+    int reserved[4];
 } amgb200_options;
 
 void amgb200_default_options(amgb200_options *o);
