@@ -72,7 +72,8 @@ EXPORTS = [
     "amgb200_level_residual", "amgb200_coarse_solve", "amgb200_num_levels", "amgb200_level_info",
     "amgb200_algorithmic_bytes", "amgb200_time_op", "amgb200_launch_count", "amgb200_last_phase_ms",
     "amgb200_version", "amgb200_generate", "amgb200_mat_free", "amgb200_setup", "amgb200_amg_destroy",
-    "amgb200_default_pars",
+    "amgb200_default_pars", "amgb200_last_level_ms", "amgb200_set_profile", "amgb200_upload_seconds",
+    "amgb200_device_bytes", "amgb200_level_kernel", "amgb200_bench_solve",
 ]
 
 _lib = None
@@ -124,6 +125,15 @@ def lib():
         L.amgb200_setup.argtypes = [C.POINTER(Amg), C.POINTER(Mat), C.POINTER(Pars), C.c_int]
         L.amgb200_amg_destroy.argtypes = [C.POINTER(Amg)]
         L.amgb200_default_pars.argtypes = [C.POINTER(Pars)]
+        L.amgb200_last_level_ms.argtypes = [C.c_void_p, C.c_int, c_double_p]
+        L.amgb200_set_profile.argtypes = [C.c_void_p, C.c_int]
+        L.amgb200_upload_seconds.argtypes = [C.c_void_p, c_double_p]
+        L.amgb200_device_bytes.restype = C.c_longlong
+        L.amgb200_device_bytes.argtypes = [C.c_void_p]
+        L.amgb200_level_kernel.restype = C.c_char_p
+        L.amgb200_level_kernel.argtypes = [C.c_void_p, C.c_int]
+        L.amgb200_bench_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                          c_double_p, C.POINTER(Rtn)]
         _lib = L
     return _lib
 

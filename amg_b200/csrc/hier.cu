@@ -89,6 +89,9 @@ struct Level {
     int cnt_cap = 0;
     bool pattern_symmetric = true;
     int strategy = 0;                  // 0 = parallel passes, 1 = ordered across the grid, 2 = ordered inside one CTA
+    double prof_ms[4] = {0, 0, 0, 0};  // AMGB200_PROFILE: GS, residual, restrict, prolong of the last solve
+    bool x_in_smem = false;            // strategy 2 only: x fits in the CTA's shared memory
+    int cta_G = 1, cta_D = 1;          // strategy 2: D groups of G warps (pipeline depth D)
 };
 
 }  // namespace
@@ -101,6 +104,7 @@ struct amgb200_hier {
     cudaStream_t stream = nullptr;
     int num_sms = 0, gs_block = 64, gs_max_blocks[2] = {0, 0};
     bool exact = true;
+    int max_dyn_smem = 0;
     double *d_partial = nullptr;       // 4 x partial_stride block partials
     int partial_stride = 0;
     double *d_scal = nullptr;          // 8 reduced scalars
@@ -127,14 +131,15 @@ void fetch_scalars(amgb200_hier *h, int count) {
 }
 
 struct PhaseTimer {                    // only active with AMGB200_PROFILE=1 (adds syncs)
-    amgb200_hier *h; int id;
-    PhaseTimer(amgb200_hier *h_, int id_) : h(h_), id(id_) { if (h->profile) CUDA_CHECK(cudaEventRecord(h->ev0, h->stream)); }
+    amgb200_hier *h; int id; int level;
+    PhaseTimer(amgb200_hier *h_, int id_, int level_ = -1) : h(h_), id(id_), level(level_) { if (h->profile) CUDA_CHECK(cudaEventRecord(h->ev0, h->stream)); }
     ~PhaseTimer() {
         if (!h->profile) return;
         CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
         CUDA_CHECK(cudaEventSynchronize(h->ev1));
         float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         h->phase_ms[id] += ms;
+        if (level >= 0 && id < 4) h->L[level].prof_ms[id] += ms;
     }
 };
 
@@ -178,8 +183,21 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         return;
     }
     if (lv.strategy == 2) {
-        const int nw = std::max(1, std::min(16, lv.max_width));
-        LAUNCH((gs_ordered_cta_kernel<KIND, EXACT>), 1, 32 * nw, h->stream, lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps);
+        const int G = lv.cta_G, D = lv.cta_D, nw = G * D;
+        const size_t stage = (size_t)nw * SUPER * sizeof(double);
+        const size_t xbytes = (size_t)((lv.n + 1) & ~1) * sizeof(double);
+        if (lv.x_in_smem) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cta_kernel<KIND, EXACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+                attr_set = true;
+            }
+            gs_ordered_cta_kernel<KIND, EXACT, true><<<1, 32 * nw, xbytes + stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D);
+        } else {
+            gs_ordered_cta_kernel<KIND, EXACT, false><<<1, 32 * nw, stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D);
+        }
+        ++g_launches;
+        CUDA_CHECK(cudaGetLastError());
         return;
     }
     const int need = nsweeps * lv.W;
@@ -460,9 +478,9 @@ void cycle(amgb200_hier *h) {
         while (l < nl - 1) {
             Level &lv = h->L[l];
             visits[l]++;
-            { PhaseTimer pt(h, 0); smooth(h, l, h->pars.pre_iter); }
-            { PhaseTimer pt(h, 1); spmv(h, lv.A.v, MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0); }
-            { PhaseTimer pt(h, 2); spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[l + 1].b, nullptr, 0.0); }
+            { PhaseTimer pt(h, 0, l); smooth(h, l, h->pars.pre_iter); }
+            { PhaseTimer pt(h, 1, l); spmv(h, lv.A.v, MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0); }
+            { PhaseTimer pt(h, 2, l); spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[l + 1].b, nullptr, 0.0); }
             l++;
             dev_zero(h, h->L[l].n, h->L[l].x);
         }
@@ -470,8 +488,8 @@ void cycle(amgb200_hier *h) {
         while (l > 0) {
             l--;
             Level &lv = h->L[l];
-            { PhaseTimer pt(h, 3); spmv(h, lv.P.v, MODE_AMXPY, RED_NONE, h->L[l + 1].x, lv.x, nullptr, 1.0); }
-            { PhaseTimer pt(h, 0); smooth(h, l, h->pars.post_iter); }
+            { PhaseTimer pt(h, 3, l); spmv(h, lv.P.v, MODE_AMXPY, RED_NONE, h->L[l + 1].x, lv.x, nullptr, 1.0); }
+            { PhaseTimer pt(h, 0, l); smooth(h, l, h->pars.post_iter); }
             if (visits[l] < cycle_type) break;
             visits[l] = 0;
         }
@@ -549,6 +567,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     h->num_sms = prop.multiProcessorCount;
+    h->max_dyn_smem = (int)prop.sharedMemPerBlockOptin - 1024;
     if (!prop.cooperativeLaunch) { fprintf(stderr, "libamgb200: device lacks cooperative launch\n"); exit(70); }
     if (getenv("AMGB200_GS_BLOCK")) h->gs_block = std::max(32, std::min(BLOCK, atoi(getenv("AMGB200_GS_BLOCK")) / 32 * 32));
     h->exact = !opt.fast;
@@ -628,7 +647,19 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             lv.d_item_wf = dev_upload(item_wf);
             lv.d_wf_item_ptr = dev_upload(wip);
             if (!lv.ordered) lv.strategy = 0;
-            else lv.strategy = ((double)wip[lv.W] / lv.W <= cta_max_avg) ? 2 : 1;
+            else lv.strategy = ((double)wip[lv.W] / lv.W <= (lay.kind == KIND_CSR ? 2.0 * cta_max_avg : cta_max_avg)) ? 2 : 1;
+            {
+                const int maxw = lay.kind == KIND_SELL ? CTA_MAX_WARPS_SELL : CTA_MAX_WARPS_CSR;
+                const double avg = (double)wip[lv.W] / lv.W;
+                (void)avg;
+                int G = std::max(1, std::min(lv.max_width, maxw / 2));
+                if (getenv("AMGB200_CTA_G")) G = std::max(1, std::min(maxw, atoi(getenv("AMGB200_CTA_G"))));
+                lv.cta_G = G;
+                lv.cta_D = std::max(1, maxw / G);
+                if (getenv("AMGB200_CTA_D")) lv.cta_D = std::max(1, std::min(maxw / G, atoi(getenv("AMGB200_CTA_D"))));
+                const size_t needb = (size_t)((lv.n + 1) & ~1) * 8 + (size_t)lv.cta_G * lv.cta_D * SUPER * 8;
+                lv.x_in_smem = lv.strategy == 2 && needb <= (size_t)h->max_dyn_smem && !(getenv("AMGB200_NO_SMEM_X") && atoi(getenv("AMGB200_NO_SMEM_X")));
+            }
             if (getenv("AMGB200_GS_STRATEGY") && lv.ordered) lv.strategy = std::max(1, std::min(2, atoi(getenv("AMGB200_GS_STRATEGY"))));
             // transfers: P_l rows in this level's schedule, columns in the next level's; R_l the other way round
             DevLayout lp, lr;
@@ -655,7 +686,8 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             const Level &lv = h->L[l];
             printf("  %3d %10d %11lld  %s %8d  %6d/%-6d %9lld %9lld  %d\n", l, lv.n, lv.A.nnz, lv.A.v.kind == KIND_SELL ? "SELL" : "CSR ",
                    lv.pass_rows[0], lv.wf_count[0], lv.wf_count[1], lv.P.valid ? lv.P.nnz : 0LL, lv.R.valid ? lv.R.nnz : 0LL, (int)lv.pattern_symmetric);
-            printf("      strategy %d  max wavefront width %d items\n", lv.strategy, lv.max_width);
+            printf("      strategy %d%s  max wavefront width %d items\n", lv.strategy, lv.x_in_smem ? " (x in smem)" : "", lv.max_width);
+            if (lv.strategy == 2) printf("      CTA pipeline: %d groups x %d warps\n", lv.cta_D, lv.cta_G);
         }
     }
     return h;
@@ -716,11 +748,60 @@ double amgb200_algorithmic_bytes(const amgb200_hier *h, int level, int op) {
 }
 
 void amgb200_last_phase_ms(const amgb200_hier *h, double ms[8]) { for (int i = 0; i < 8; ++i) ms[i] = h->phase_ms[i]; }
+void amgb200_last_level_ms(const amgb200_hier *h, int level, double ms[4]) {
+    check_level(h, level);
+    for (int i = 0; i < 4; ++i) ms[i] = h->L[level].prof_ms[i];
+}
+void amgb200_set_profile(amgb200_hier *h, int on) { h->profile = on != 0; }
+void amgb200_upload_seconds(const amgb200_hier *h, double s[2]) { s[0] = h->analysis_s; s[1] = h->upload_s; }
+long long amgb200_device_bytes(const amgb200_hier *h) {
+    long long tot = 0;
+    for (const Level &lv : h->L) {
+        for (const DevMatOwner *m : {&lv.A, &lv.P, &lv.R}) if (m->valid) tot += m->padded * 12 + (long long)m->v.nitems * 12;
+        tot += (long long)lv.n * (3 * 8 + 4);
+    }
+    return tot;
+}
+const char *amgb200_level_kernel(const amgb200_hier *h, int level) {
+    check_level(h, level);
+    const Level &lv = h->L[level];
+    if (!lv.smoothed) return "none";
+    static const char *names[3] = {"gs_pass_kernel", "gs_ordered_grid_kernel", "gs_ordered_cta_kernel"};
+    return names[lv.strategy];
+}
+
+// K timed solves from the same initial guess with CUDA events on the library's stream.
+// d_x0, d_b, d_x: device arrays (natural numbering); d_x is overwritten each step.
+void amgb200_bench_solve(amgb200_hier *h, const double *d_x0, const double *d_b, double *d_x, int warmup, int steps,
+                         double *ms_total, amgb200_rtn *last) {
+    const size_t bytes = (size_t)h->L[0].n * sizeof(double);
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+    amgb200_rtn r = {0, 0, 0};
+    for (int i = 0; i < warmup; ++i) {
+        CUDA_CHECK(cudaMemcpyAsync(d_x, d_x0, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        r = amgb200_solve_device(h, d_x, d_b, nullptr, 0);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    CUDA_CHECK(cudaEventRecord(a, h->stream));
+    for (int i = 0; i < steps; ++i) {
+        CUDA_CHECK(cudaMemcpyAsync(d_x, d_x0, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        r = amgb200_solve_device(h, d_x, d_b, nullptr, 0);
+    }
+    CUDA_CHECK(cudaEventRecord(b, h->stream));
+    CUDA_CHECK(cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *ms_total = ms;
+    if (last) *last = r;
+}
 
 amgb200_rtn amgb200_solve_device(amgb200_hier *h, double *d_x, const double *d_b, double *res_hist, int hist_cap) {
     amgb200_rtn rtn = {0, 0, 0};
     Level &l0 = h->L[0];
     for (int i = 0; i < 8; ++i) h->phase_ms[i] = 0;
+    for (Level &lv : h->L) for (int i = 0; i < 4; ++i) lv.prof_ms[i] = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (h->profile) { CUDA_CHECK(cudaEventCreate(&t0)); CUDA_CHECK(cudaEventCreate(&t1)); CUDA_CHECK(cudaEventRecord(t0, h->stream)); }
     to_schedule(h, 0, d_b, l0.b);

@@ -88,6 +88,7 @@ struct SellItem {
     int width, k, r1;
     int j[SCH];
     double a[SCH];
+    double bk;
     __device__ __forceinline__ void load_chunk(int e0) {
 #pragma unroll
         for (int u = 0; u < SCH; ++u) {
@@ -95,7 +96,7 @@ struct SellItem {
             else { j[u] = -1; a[u] = 0.0; }
         }
     }
-    __device__ __forceinline__ void prologue(const DMat &A, int s, int lane) {
+    __device__ __forceinline__ void prologue(const DMat &A, int s, int lane, const double *__restrict__ b = nullptr) {
         const int r0 = A.slice_row[s];
         r1 = A.slice_row[s + 1];
         const long long p0 = A.slice_ptr[s];
@@ -104,15 +105,16 @@ struct SellItem {
         cp = A.col + p0 + lane;
         vp = A.val + p0 + lane;
         load_chunk(0);
+        bk = (b && k < r1) ? b[k] : 0.0;
     }
 };
 
 // Gauss-Seidel row update (amg/Solve/SSS_smooth.c:18-33): t = b_i - sum_{j != i} a_ij x_j in storage
 // order; x_i = t / a_ii when |a_ii| > 1e-20
 template <bool COH, int SCH>
-__device__ __forceinline__ void gs_finish_sell(SellItem<SCH> &it, const double *__restrict__ b, double *x) {
+__device__ __forceinline__ void gs_finish_sell(SellItem<SCH> &it, double *x) {
     const bool active = it.k < it.r1;
-    double t = active ? b[it.k] : 0.0, d = 0.0;
+    double t = it.bk, d = 0.0;
     for (int e0 = 0; e0 < it.width; e0 += SCH) {
         double xv[SCH];
 #pragma unroll
@@ -170,87 +172,116 @@ __device__ __forceinline__ double spmv_finish_sell(SellItem<SCH> &it, const doub
 }
 
 // ==========================================================================================
-// Warp-per-row work item (CSR): lanes fetch/multiply 32 entries at a time; the products are folded
-// into the accumulator in storage order through shuffles (EXACT) or by a shuffle tree (FAST).
-// Three-stage software pipeline: [col/val load] -> [x gather] -> [chain].
+// Warp-per-row work item (CSR).  The 32 lanes fetch and multiply 128 entries per step ("super
+// chunk", 4 per lane, coalesced); the separately rounded products are staged in 1 KB of shared
+// memory per warp and folded into the accumulator IN STORAGE ORDER by a dependent chain of
+// DADD/DSUB fed with broadcast LDS.128 (8.4 cycles per term measured on B200 = the latency of a
+// dependent fp64 add; shuffle-fed chains degrade to 16 cycles when several warps share an SM).
+// Pipeline: col/val of super chunk s+1 and the x gather of s+1 are in flight during the chain of s.
+// prologue() touches only the static matrix (and b) and may run before a dependency wait.
 // ==========================================================================================
+constexpr int SUPER = 128;
 struct CsrItem {
     int k, p0, p1;
-    int jA, jB;        // B = chunk being consumed next, A = the one after
-    double aA, aB;
-    __device__ __forceinline__ void prologue(const DMat &A, int row, int lane) {
+    int j[4];
+    double a[4];
+    double bk;
+    __device__ __forceinline__ void load_super(const DMat &A, int base, int lane, int (&jj)[4], double (&aa)[4]) const {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = base + u * 32 + lane;
+            if (p < p1) { jj[u] = A.col[p]; aa[u] = A.val[p]; } else { jj[u] = -1; aa[u] = 0.0; }
+        }
+    }
+    __device__ __forceinline__ void prologue(const DMat &A, int row, int lane, const double *__restrict__ b) {
         k = row;
         p0 = A.rptr[row];
         p1 = A.rptr[row + 1];
-        int p = p0 + lane;
-        if (p < p1) { jB = A.col[p]; aB = A.val[p]; } else { jB = -1; aB = 0.0; }
-        p += 32;
-        if (p < p1) { jA = A.col[p]; aA = A.val[p]; } else { jA = -1; aA = 0.0; }
+        load_super(A, p0, lane, j, a);
+        bk = b ? b[row] : 0.0;
     }
 };
 
-// SUB: accumulate t - prod (Gauss-Seidel) else t + prod (SpMV).  GS: the diagonal entry is skipped and
-// returned through d (valid in all lanes).  Result valid in all lanes.
-template <bool COH, bool EXACT, bool GS>
-__device__ __forceinline__ double csr_row_chain(const DMat &A, CsrItem &it, const double *x, double t, double &d, int lane) {
-    double dl = 0.0, tree = 0.0;
-    double xB = 0.0;
-    {
-        const bool use = it.jB >= 0 && !(GS && it.jB == it.k);
-        if (use) xB = ld_x<COH>(x + it.jB);
-    }
-    for (int base = it.p0; base < it.p1; base += 32) {
-        // stage 2 for the next chunk: gather x (its column indices were loaded one iteration ago)
-        double xA = 0.0;
-        {
-            const bool use = it.jA >= 0 && !(GS && it.jA == it.k);
-            if (use) xA = ld_x<COH>(x + it.jA);
-        }
-        // stage 1 for the chunk after that
-        int jN = -1;
-        double aN = 0.0;
-        {
-            const int p = base + 64 + lane;
-            if (p < it.p1) { jN = A.col[p]; aN = A.val[p]; }
-        }
-        // stage 3: consume chunk B
-        double prod = 0.0;
-        if (it.jB >= 0) {
-            if (GS && it.jB == it.k) dl = it.aB;
-            else prod = __dmul_rn(it.aB, xB);
-        }
-        if (EXACT) {
-            const int cnt = min(32, it.p1 - base);
-            int q = 0;
-            for (; q + 8 <= cnt; q += 8) {
+// EXACT in-order accumulation.  GS: t starts at b_k, products are subtracted, the diagonal entry is
+// skipped and returned through d.  Otherwise t starts at 0 and products are added.  Padding and the
+// skipped diagonal contribute +0.0, which leaves t bit-unchanged.  Result valid in all lanes.
+template <bool COH, bool GS>
+__device__ __forceinline__ double csr_row_exact(const DMat &A, CsrItem &it, const double *x, double t, double &d, int lane, double *sprod) {
+    double dl = 0.0;
+    double xc[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const double pq = __shfl_sync(FULL, prod, q + u);
-                    t = GS ? __dsub_rn(t, pq) : __dadd_rn(t, pq);
-                }
+    for (int u = 0; u < 4; ++u) xc[u] = (it.j[u] >= 0 && !(GS && it.j[u] == it.k)) ? ld_x<COH>(x + it.j[u]) : 0.0;
+    for (int base = it.p0; base < it.p1; base += SUPER) {
+        int jn[4];
+        double an[4], xn[4];
+        const bool more = base + SUPER < it.p1;
+        if (more) it.load_super(A, base + SUPER, lane, jn, an);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double prod = 0.0;
+            if (it.j[u] >= 0) {
+                if (GS && it.j[u] == it.k) dl = it.a[u];
+                else prod = __dmul_rn(it.a[u], xc[u]);
             }
-            for (; q < cnt; ++q) {
-                const double pq = __shfl_sync(FULL, prod, q);
-                t = GS ? __dsub_rn(t, pq) : __dadd_rn(t, pq);
-            }
-        } else {
-            tree = __dadd_rn(tree, prod);
+            sprod[u * 32 + lane] = prod;
         }
-        it.jB = it.jA; it.aB = it.aA; xB = xA;
-        it.jA = jN; it.aA = aN;
-    }
-    if (!EXACT) {
-        tree = warp_sum(tree);
-        t = GS ? __dsub_rn(t, tree) : __dadd_rn(t, tree);
+        __syncwarp();
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xn[u] = (jn[u] >= 0 && !(GS && jn[u] == it.k)) ? ld_x<COH>(x + jn[u]) : 0.0;
+        }
+        const int cnt = min(SUPER, it.p1 - base);
+        const double2 *sp2 = reinterpret_cast<const double2 *>(sprod);
+        int q = 0;
+        for (; q + 8 <= cnt; q += 8) {
+            const double2 v0 = sp2[(q >> 1)], v1 = sp2[(q >> 1) + 1], v2 = sp2[(q >> 1) + 2], v3 = sp2[(q >> 1) + 3];
+            if (GS) {
+                t = __dsub_rn(t, v0.x); t = __dsub_rn(t, v0.y); t = __dsub_rn(t, v1.x); t = __dsub_rn(t, v1.y);
+                t = __dsub_rn(t, v2.x); t = __dsub_rn(t, v2.y); t = __dsub_rn(t, v3.x); t = __dsub_rn(t, v3.y);
+            } else {
+                t = __dadd_rn(t, v0.x); t = __dadd_rn(t, v0.y); t = __dadd_rn(t, v1.x); t = __dadd_rn(t, v1.y);
+                t = __dadd_rn(t, v2.x); t = __dadd_rn(t, v2.y); t = __dadd_rn(t, v3.x); t = __dadd_rn(t, v3.y);
+            }
+        }
+        for (; q < cnt; q += 2) {                       // slot cnt holds +0.0 when cnt is odd
+            const double2 v = sp2[q >> 1];
+            if (GS) { t = __dsub_rn(t, v.x); t = __dsub_rn(t, v.y); }
+            else { t = __dadd_rn(t, v.x); t = __dadd_rn(t, v.y); }
+        }
+        __syncwarp();
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { it.j[u] = jn[u]; it.a[u] = an[u]; xc[u] = xn[u]; }
+        }
     }
     d = warp_sum(dl);          // exactly one lane holds the diagonal; adding zeros is exact
     return t;
 }
 
+// FAST variant: per-lane partial sums combined by a shuffle tree (not the reference's rounding order)
+template <bool COH, bool GS>
+__device__ __forceinline__ double csr_row_fast(const DMat &A, CsrItem &it, const double *x, double t, double &d, int lane) {
+    double dl = 0.0, acc = 0.0;
+    for (int base = it.p0; base < it.p1; base += SUPER) {
+        if (base != it.p0) it.load_super(A, base, lane, it.j, it.a);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (it.j[u] >= 0) {
+                if (GS && it.j[u] == it.k) dl = it.a[u];
+                else acc = __dadd_rn(acc, __dmul_rn(it.a[u], ld_x<COH>(x + it.j[u])));
+            }
+        }
+    }
+    acc = warp_sum(acc);
+    t = GS ? __dsub_rn(t, acc) : __dadd_rn(t, acc);
+    d = warp_sum(dl);
+    return t;
+}
+
 template <bool COH, bool EXACT>
-__device__ __forceinline__ void gs_finish_csr(const DMat &A, CsrItem &it, const double *__restrict__ b, double *x, int lane) {
+__device__ __forceinline__ void gs_finish_csr(const DMat &A, CsrItem &it, double *x, int lane, double *sprod) {
     double d;
-    const double t = csr_row_chain<COH, EXACT, true>(A, it, x, b[it.k], d, lane);
+    const double t = EXACT ? csr_row_exact<COH, true>(A, it, x, it.bk, d, lane, sprod) : csr_row_fast<COH, true>(A, it, x, it.bk, d, lane);
     if (lane == 0 && fabs(d) > GS_TINY) x[it.k] = __ddiv_rn(t, d);
 }
 
@@ -260,17 +291,18 @@ __device__ __forceinline__ void gs_finish_csr(const DMat &A, CsrItem &it, const 
 // one fully parallel pass (a pass whose dependency DAG has depth 1): items [item0, item1)
 template <int KIND, bool EXACT>
 __global__ void __launch_bounds__(BLOCK) gs_pass_kernel(DMat A, const double *__restrict__ b, double *x, int item0, int item1) {
-    const int lane = threadIdx.x & 31;
-    const int it = item0 + blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * SUPER : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int it = item0 + blockIdx.x * WARPS_PER_BLOCK + warp;
     if (it >= item1) return;
     if constexpr (KIND == 0) {
         SellItem<8> w;
-        w.prologue(A, it, lane);
-        gs_finish_sell<false>(w, b, x);
+        w.prologue(A, it, lane, b);
+        gs_finish_sell<false>(w, x);
     } else {
         CsrItem w;
-        w.prologue(A, it, lane);
-        gs_finish_csr<false, EXACT>(A, w, b, x, lane);
+        w.prologue(A, it, lane, b);
+        gs_finish_csr<false, EXACT>(A, w, x, lane, sprod + warp * SUPER);
     }
 }
 
@@ -283,6 +315,7 @@ template <int KIND, bool EXACT>
 __global__ void __launch_bounds__(BLOCK) gs_ordered_grid_kernel(DMat A, const double *__restrict__ b, double *x,
                                                                 const int *__restrict__ item_wf, const int *__restrict__ wf_item_ptr,
                                                                 unsigned *cnt, int W, int items_per_sweep, int nsweeps) {
+    __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * SUPER : 1];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -293,9 +326,9 @@ __global__ void __launch_bounds__(BLOCK) gs_ordered_grid_kernel(DMat A, const do
         const int it = (int)(t - (long long)sweep * items_per_sweep);
         const int wl = item_wf[it];
         const int g = sweep * W + wl;
-        SellItem<16> ws;
+        SellItem<20> ws;
         CsrItem wc;
-        if constexpr (KIND == 0) ws.prologue(A, it, lane); else wc.prologue(A, it, lane);
+        if constexpr (KIND == 0) ws.prologue(A, it, lane, b); else wc.prologue(A, it, lane, b);
         if (g - 1 > known) {
             if (lane == 0) {
                 const int pw = wl == 0 ? W - 1 : wl - 1;
@@ -307,43 +340,62 @@ __global__ void __launch_bounds__(BLOCK) gs_ordered_grid_kernel(DMat A, const do
             __threadfence();
             known = g - 1;
         }
-        if constexpr (KIND == 0) gs_finish_sell<true>(ws, b, x);
-        else gs_finish_csr<true, EXACT>(A, wc, b, x, lane);
+        if constexpr (KIND == 0) gs_finish_sell<true>(ws, x);
+        else gs_finish_csr<true, EXACT>(A, wc, x, lane, sprod + (threadIdx.x >> 5) * SUPER);
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicAdd(cnt + g, 1u);
     }
 }
 
-// Ordered sweeps inside ONE thread block (levels whose wavefronts are narrow): warps take the items
-// of a wavefront round-robin, wavefronts are separated by __syncthreads.  No inter-SM traffic on the
-// dependency path; x is read through L1 (block-level visibility after the barrier).
-template <int KIND, bool EXACT>
-__global__ void __launch_bounds__(512) gs_ordered_cta_kernel(DMat A, const double *__restrict__ b, double *x,
-                                                              const int *__restrict__ wf_item_ptr, int W, int nsweeps) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+// Ordered sweeps inside ONE thread block (levels whose wavefronts are narrow).  The block's G*D
+// warps form D groups of G warps; group (g mod D) owns wavefront g: its warps take the wavefront's
+// items round-robin.  A group fetches the matrix entries (row pointers, col, val, b) of its next
+// wavefront D steps ahead, so only the x gathers, the in-order chain and one __syncthreads per
+// wavefront sit on the dependency path.  No inter-SM traffic.
+// XS: the whole x vector lives in shared memory for the duration of the launch (levels with
+// n*8 bytes <= ~200 KB): the gathers cost ~30 cycles instead of an L2 round trip.
+// Dynamic shared memory: [x (n doubles, XS only)] [nwarps * 128 doubles of product staging]
+constexpr int CTA_MAX_WARPS_SELL = 8, CTA_MAX_WARPS_CSR = 16;
+template <int KIND, bool EXACT, bool XS>
+__global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA_MAX_WARPS_CSR) gs_ordered_cta_kernel(
+    DMat A, const double *__restrict__ b, double *xg, const int *__restrict__ wf_item_ptr, int W, int nsweeps, int G, int D) {
+    extern __shared__ double dyn_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = warp / G, r = warp - grp * G;
+    const int n = A.nrows;
+    double *x = XS ? dyn_smem : xg;
+    double *sprod = dyn_smem + (XS ? ((n + 1) & ~1) : 0) + warp * SUPER;
+    if (XS) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dyn_smem[i] = xg[i];
+        __syncthreads();
+    }
     const int totalw = W * nsweeps;
-    SellItem<8> ws;
+    SellItem<20> ws;
     CsrItem wc;
-    int i0 = wf_item_ptr[0], i1 = wf_item_ptr[1];
-    bool have = i0 + warp < i1;
-    if (have) { if constexpr (KIND == 0) ws.prologue(A, i0 + warp, lane); else wc.prologue(A, i0 + warp, lane); }
+    int i0 = 0, i1 = 0;
+    bool have = false;
+    auto fetch = [&](int g) {
+        const int wl = g % W;
+        i0 = wf_item_ptr[wl]; i1 = wf_item_ptr[wl + 1];
+        have = i0 + r < i1;
+        if (have) { if constexpr (KIND == 0) ws.prologue(A, i0 + r, lane, b); else wc.prologue(A, i0 + r, lane, b); }
+    };
+    if (grp < totalw) fetch(grp);
     for (int g = 0; g < totalw; ++g) {
-        if (have) {
-            if constexpr (KIND == 0) gs_finish_sell<false>(ws, b, x); else gs_finish_csr<false, EXACT>(A, wc, b, x, lane);
-            for (int it = i0 + warp + nw; it < i1; it += nw) {         // wavefront wider than the block
-                if constexpr (KIND == 0) { ws.prologue(A, it, lane); gs_finish_sell<false>(ws, b, x); }
-                else { wc.prologue(A, it, lane); gs_finish_csr<false, EXACT>(A, wc, b, x, lane); }
+        if (g % D == grp) {
+            if (have) {
+                if constexpr (KIND == 0) gs_finish_sell<false>(ws, x); else gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod);
+                for (int it = i0 + r + G; it < i1; it += G) {          // wavefront wider than the group
+                    if constexpr (KIND == 0) { ws.prologue(A, it, lane, b); gs_finish_sell<false>(ws, x); }
+                    else { wc.prologue(A, it, lane, b); gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod); }
+                }
             }
-        }
-        if (g + 1 < totalw) {                                         // fetch the next wavefront's matrix entries before the barrier
-            const int wl = (g + 1) % W;
-            i0 = wf_item_ptr[wl]; i1 = wf_item_ptr[wl + 1];
-            have = i0 + warp < i1;
-            if (have) { if constexpr (KIND == 0) ws.prologue(A, i0 + warp, lane); else wc.prologue(A, i0 + warp, lane); }
+            if (g + D < totalw) fetch(g + D);
         }
         __syncthreads();
     }
+    if (XS) for (int i = threadIdx.x; i < n; i += blockDim.x) xg[i] = dyn_smem[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -363,8 +415,9 @@ template <int KIND, int MODE, int RED, bool EXACT>
 __global__ void __launch_bounds__(BLOCK) spmv_kernel(DMat A, const double *__restrict__ x, double *y, const double *__restrict__ b,
                                                      double alpha, double *partial) {
     __shared__ double red[32];
-    const int lane = threadIdx.x & 31;
-    const int it = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * SUPER : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int it = blockIdx.x * WARPS_PER_BLOCK + warp;
     double contrib = 0.0;
     if (it < A.nitems) {
         if constexpr (KIND == 0) {
@@ -377,9 +430,10 @@ __global__ void __launch_bounds__(BLOCK) spmv_kernel(DMat A, const double *__res
             }
         } else {
             CsrItem w;
-            w.prologue(A, it, lane);
+            w.prologue(A, it, lane, nullptr);
             double d;
-            const double t = csr_row_chain<false, EXACT, false>(A, w, x, 0.0, d, lane);
+            const double t = EXACT ? csr_row_exact<false, false>(A, w, x, 0.0, d, lane, sprod + warp * SUPER)
+                                   : csr_row_fast<false, false>(A, w, x, 0.0, d, lane);
             if (lane == 0) {
                 const double out = spmv_store<MODE>(t, alpha, b, y, it);
                 if (RED == RED_SUMSQ) contrib = __dmul_rn(out, out);

@@ -237,3 +237,28 @@ class DeviceHierarchy:
         a = (C.c_double * 8)()
         self._lib.amgb200_last_phase_ms(self.h, a)
         return list(a)
+
+    def level_ms(self, l):
+        a = (C.c_double * 4)()
+        self._lib.amgb200_last_level_ms(self.h, l, a)
+        return list(a)
+
+    def set_profile(self, on):
+        self._lib.amgb200_set_profile(self.h, int(on))
+
+    def upload_seconds(self):
+        a = (C.c_double * 2)()
+        self._lib.amgb200_upload_seconds(self.h, a)
+        return a[0], a[1]
+
+    def device_bytes(self):
+        return self._lib.amgb200_device_bytes(self.h)
+
+    def gs_kernel(self, l):
+        return self._lib.amgb200_level_kernel(self.h, l).decode()
+
+    def bench_solve(self, d_x0_ptr, d_b_ptr, d_x_ptr, warmup, steps):
+        ms = C.c_double(0)
+        rtn = capi.Rtn()
+        self._lib.amgb200_bench_solve(self.h, d_x0_ptr, d_b_ptr, d_x_ptr, warmup, steps, C.byref(ms), C.byref(rtn))
+        return ms.value, rtn

@@ -1,0 +1,297 @@
+#!/usr/bin/env python3
+"""bench.py -- V-cycle solve time to 1e-8 of the AMG solve phase on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload p3d128] [--impl amgb200|reference] [--fast]
+
+A "step" is one complete solve of the workload (x0 = 1, b = 1, tol 1e-8, the reference's defaults
+apart from the tolerance) on a hierarchy that is already resident in HBM.  Prints ONE JSON line.
+
+  value / ms_per_step   device-timed (CUDA events on the library's stream) solve time, max over ranks
+  e2e                   the same solve through the reference-facing C ABI call SSS_amg_solve(mg, x, b)
+                        with HOST buffers: hierarchy analysis + H2D upload + solve + D2H inside the timer
+  roofline              the kernel with the largest share of the step (live per-level CUDA-event timing
+                        of one profiled solve) against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline          the reference's own CPU path (oracle/_ref, 1 thread -- it has no live OpenMP
+                        region) timed on this box's host, same workload, one full solve
+--impl reference runs that CPU path as the timed arm (the one place besides cpu_baseline where
+bench.py executes anything under oracle/).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {           # name: (generator kind, N, eps_z, description)
+    "p2d256": ("p2d", 256, 0.0, "2D 5-point Poisson 256x256"),
+    "p3d64": ("p3d", 64, 0.0, "3D 7-point Poisson 64^3"),
+    "p3d128": ("p3d", 128, 0.0, "3D 7-point Poisson 128^3"),
+    "p3d256": ("p3d", 256, 0.0, "3D 7-point Poisson 256^3"),
+    "aniso64": ("aniso3d", 64, 1e-3, "anisotropic 3D diffusion (1,1,1e-3) 64^3"),
+    "v27_32": ("v27", 32, 0.0, "3D 27-point variable-coefficient diffusion 32^3"),
+    "v27_64": ("v27", 64, 0.0, "3D 27-point variable-coefficient diffusion 64^3"),
+}
+METRIC = "vcycle_solve_time_to_1e-8"
+TOL = 1e-8
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_problem(workload):
+    from amg_b200 import HostHierarchy, generate
+    kind, N, eps, desc = WORKLOADS[workload]
+    A = generate(kind, N, eps)
+    hier = HostHierarchy(A, tol=TOL)
+    return A, hier, desc
+
+
+def reference_cpu_solve(A, tol):
+    """the reference's own objects: SSS_amg_setup + SSS_amg_solve on the host CPU (1 thread)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_ffi
+    from amg_b200 import capi
+    import numpy as np
+    n = A.nrows
+    if oracle_ffi.have_ref():
+        ref = oracle_ffi.Reference("fix")
+        mg = ref.setup(A, capi.default_pars(tol))
+        def run():
+            r, x, dt = ref.solve_timed(mg, np.ones(n), np.ones(n), tol)
+            return r, dt
+        return run, "reference", lambda: ref.destroy(mg)
+    from amg_b200 import HostHierarchy
+    orc = oracle_ffi.Oracle()
+    hier = HostHierarchy(A, tol=tol)
+    def run():
+        t0 = time.perf_counter()
+        r, x, h = orc.solve(hier, np.ones(n), np.ones(n), 0)
+        return r, time.perf_counter() - t0
+    return run, "port", lambda: None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="p3d128", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="amgb200", choices=["amgb200", "reference"])
+    ap.add_argument("--fast", action="store_true", help="FAST arithmetic mode (not parity-exact)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world)
+    kind, N, eps, desc = WORKLOADS[args.workload]
+    config = {"workload": f"{desc}, V-cycle solve to 1e-8, fp64, b=1, x0=1", "tolerance": TOL,
+              "l2_policy": "inputs larger than L2 (hierarchy >> 126 MB); no flush" if args.workload in ("p3d128", "p3d256", "v27_64") else "hierarchy smaller than L2: L2-resident between steps"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from amg_b200 import generate
+        A = generate(kind, N, eps)
+        run, how, done = reference_cpu_solve(A, TOL)
+        for _ in range(min(args.warmup, 1)):          # one warm-up solve is enough for a CPU loop (bounded run time)
+            run()
+        times = []
+        rtn = None
+        for _ in range(args.steps):
+            rtn, dt = run()
+            times.append(dt)
+        done()
+        ms = 1e3 * sum(times) / len(times)
+        line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": n_gpus, "steps": args.steps,
+                "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config, "vcycles": rtn.nits, "relres": rtn.rres,
+                "cpu_baseline": {"value": ms, "unit": "ms", "cores": 1, "kind": how,
+                                 "sample": f"full solve ({rtn.nits} V-cycles), mean of {args.steps}", "host_cores_available": os.cpu_count()},
+                "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import numpy as np
+    import torch
+    from amg_b200 import DeviceHierarchy, capi, solve_dropin
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the amgb200 arm has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    A, hier, _ = build_problem(args.workload)
+    n = A.nrows
+    dev = DeviceHierarchy(hier, device=local_rank, fast=1 if args.fast else None)
+    x0 = torch.ones(n, dtype=torch.float64, device="cuda")
+    b = torch.ones(n, dtype=torch.float64, device="cuda")
+    x = torch.empty_like(x0)
+    torch.cuda.synchronize()
+
+    launches0 = capi.lib().amgb200_launch_count()
+    sampler = ClockSampler(local_rank)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ms_total, rtn = dev.bench_solve(x0.data_ptr(), b.data_ptr(), x.data_ptr(), args.warmup, args.steps)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clocks = sampler.stop()
+    launches = capi.lib().amgb200_launch_count() - launches0
+    launches_per_step = launches / (args.warmup + args.steps)
+    ms_step = ms_total / args.steps
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- one profiled solve: per-level kernel shares (adds syncs; not part of the timed number)
+    dev.set_profile(1)
+    r2, _, hist = dev.solve(np.ones(n), np.ones(n))
+    dev.set_profile(0)
+    phase = dev.phase_ms()
+    hbm, hbm_src = load_peaks()
+    kernels = []
+    sweeps = hier.pars.pre_iter + hier.pars.post_iter
+    for l in range(dev.num_levels):
+        info = dev.info(l)
+        lm = dev.level_ms(l)
+        if l < dev.num_levels - 1 and lm[0] > 0:
+            launches_l = r2.nits * 2 * (1 if dev.gs_kernel(l) != "gs_pass_kernel" else 2 * hier.pars.pre_iter)
+            per_cycle_bytes = sweeps * dev.bytes(l, 0)
+            kernels.append({"kernel": dev.gs_kernel(l), "level": l, "rows": info["rows"], "nnz": info["nnz"],
+                            "wavefronts": info["wf_F"] + info["wf_C"], "ms_per_solve": lm[0], "share": lm[0] / phase[6],
+                            "gbs": per_cycle_bytes * r2.nits / lm[0] / 1e6, "launches_per_solve": launches_l})
+    kernels.sort(key=lambda k: -k["ms_per_solve"])
+    top = kernels[0]
+    roofline = {"bound": "hbm", "kernel": f"{top['kernel']} (level {top['level']})", "achieved": top["gbs"], "peak": hbm, "unit": "GB/s",
+                "frac": top["gbs"] / hbm, "traffic": None, "peak_source": hbm_src, "share_of_step": top["share"],
+                "avg_launch_ms": top["ms_per_solve"] / top["launches_per_solve"],
+                "algorithmic_bytes_per_launch": top["gbs"] * 1e6 * top["ms_per_solve"] / top["launches_per_solve"]}
+    # level-0 kernels and SpMV against the HBM roofline (the north-star's >= 70 % target applies to these)
+    l0 = {"gs_sweep_gbs": dev.bytes(0, 0) / dev.time_op(0, 0, 20) / 1e6,
+          "residual_gbs": dev.bytes(0, 1) / dev.time_op(0, 1, 20) / 1e6,
+          "restrict_gbs": dev.bytes(0, 2) / dev.time_op(0, 2, 20) / 1e6,
+          "prolong_gbs": dev.bytes(0, 3) / dev.time_op(0, 3, 20) / 1e6,
+          "spmv_gbs": dev.bytes(0, 4) / dev.time_op(0, 4, 20) / 1e6}
+    l0_frac = {k.replace("_gbs", "_frac_of_hbm"): v / hbm for k, v in l0.items()}
+    vcycle_bytes = dev.bytes(0, 5)
+
+    # ---- e2e through the reference-facing call with host buffers
+    os.environ["AMGB200_VERBOSE"] = "0"
+    t0 = time.perf_counter()
+    with open(os.devnull, "w") as devnull:
+        saved = os.dup(1); sys.stdout.flush(); os.dup2(devnull.fileno(), 1)
+        try:
+            rtn_e2e, x_e2e = solve_dropin(hier, np.ones(n), np.ones(n))
+        finally:
+            os.dup2(saved, 1); os.close(saved)
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    h2d = dev.device_bytes() + 2 * 8 * n
+    d2h = 8 * n + 8 * (rtn_e2e.nits + 1)
+    analysis_s, upload_s = dev.upload_seconds()
+
+    # ---- CPU baseline: the reference's own CPU path on this box, one full solve
+    cpu = None
+    if not args.no_cpu_baseline and n_gpus == 1:
+        run, how, done = reference_cpu_solve(A, TOL)
+        r_cpu, dt = run()
+        done()
+        cpu = {"value": 1e3 * dt, "unit": "ms", "cores": 1, "kind": how,
+               "sample": f"one full solve of the same workload ({r_cpu.nits} V-cycles) on 1 of {os.cpu_count()} host cores",
+               "vcycles": r_cpu.nits, "ares": r_cpu.ares}
+
+    line = {"metric": METRIC, "value": ms_step, "unit": "ms", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict(config, parallelism=("single GPU" if n_gpus == 1 else f"{n_gpus} independent replicas"),
+                                                 arithmetic=("FAST" if args.fast else "EXACT (bit-identical to the reference CPU path)")),
+            "vcycles": rtn.nits, "relres": rtn.rres, "ares": rtn.ares, "ms_per_vcycle": ms_step / max(1, rtn.nits),
+            "vcycle_algorithmic_gb": vcycle_bytes / 1e9, "vcycle_gbs": vcycle_bytes * rtn.nits / ms_step / 1e6,
+            "vcycle_frac_of_hbm": vcycle_bytes * rtn.nits / ms_step / 1e6 / hbm,
+            "level0": dict(l0, **l0_frac),
+            "clocks": clocks,
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "analysis_ms": 1e3 * analysis_s, "analysis_plus_upload_ms": 1e3 * upload_s, "vcycles": rtn_e2e.nits},
+            "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline, "kernels": kernels[:6],
+            "phase_ms_per_solve": {"gs": phase[0], "residual": phase[1], "restrict": phase[2], "prolong": phase[3],
+                                   "coarse_solve": phase[4], "outer_residual": phase[5], "total_profiled": phase[6]},
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -189,6 +189,18 @@ long long amgb200_launch_count(void);
  * [3] prolong, [4] coarse solve, [5] outer residual+norm, [6] total (only when
  * AMGB200_PROFILE=1 in the environment; otherwise zeros) */
 void amgb200_last_phase_ms(const amgb200_hier *h, double ms[8]);
+/* same, per level: [0] GS, [1] residual, [2] restrict, [3] prolong */
+void amgb200_last_level_ms(const amgb200_hier *h, int level, double ms[4]);
+void amgb200_set_profile(amgb200_hier *h, int on);
+/* s[0] = host analysis seconds, s[1] = analysis + upload seconds of amgb200_upload */
+void amgb200_upload_seconds(const amgb200_hier *h, double s[2]);
+long long amgb200_device_bytes(const amgb200_hier *h);
+/* name of the Gauss-Seidel kernel chosen for that level */
+const char *amgb200_level_kernel(const amgb200_hier *h, int level);
+/* `warmup` untimed + `steps` timed solves from d_x0 (device arrays, natural numbering), timed with
+ * CUDA events on the library's stream; *ms_total = milliseconds for the `steps` solves */
+void amgb200_bench_solve(amgb200_hier *h, const double *d_x0, const double *d_b, double *d_x, int warmup, int steps,
+                         double *ms_total, amgb200_rtn *last);
 const char *amgb200_version(void);
 
 /* ---- 3. host-side helpers (pure C++, no device): synthetic operators + RS setup ---------- */
