@@ -117,6 +117,7 @@ struct amgb200_hier {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double upload_s = 0, analysis_s = 0;
     double last_sumsq = 0;             // sum r_i^2 of the most recent dev_true_residual
+    long long *d_dbg = nullptr;        // AMGB200_DEBUG_TIMING: per-warp cycle counters of the CTA kernel
 };
 
 namespace {
@@ -184,7 +185,7 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
     }
     if (lv.strategy == 2) {
         const int G = lv.cta_G, D = lv.cta_D, nw = G * D;
-        const size_t stage = (size_t)nw * SUPER * sizeof(double);
+        const size_t stage = (size_t)nw * STAGE * sizeof(double);
         const size_t xbytes = (size_t)((lv.n + 1) & ~1) * sizeof(double);
         if (lv.x_in_smem) {
             static bool attr_set = false;
@@ -192,11 +193,18 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
                 CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cta_kernel<KIND, EXACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
                 attr_set = true;
             }
-            gs_ordered_cta_kernel<KIND, EXACT, true><<<1, 32 * nw, xbytes + stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D);
+            gs_ordered_cta_kernel<KIND, EXACT, true><<<1, 32 * nw, xbytes + stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D, h->d_dbg);
         } else {
-            gs_ordered_cta_kernel<KIND, EXACT, false><<<1, 32 * nw, stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D);
+            gs_ordered_cta_kernel<KIND, EXACT, false><<<1, 32 * nw, stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D, h->d_dbg);
         }
         ++g_launches;
+        if (h->d_dbg) {
+            long long hd[16 * 8];
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            CUDA_CHECK(cudaMemcpy(hd, h->d_dbg, sizeof(hd), cudaMemcpyDeviceToHost));
+            printf("[dbg] CTA kernel level n=%d G=%d D=%d W=%d sweeps=%d\n", lv.n, G, D, lv.W, nsweeps);
+            for (int w = 0; w < nw; ++w) printf("   warp %2d: wait %9lld  finish %9lld  fetch %9lld  items %6lld  total %9lld | gather %9lld prod %9lld chain %9lld\n", w, hd[w*8], hd[w*8+1], hd[w*8+2], hd[w*8+3], hd[w*8+4], hd[w*8+5], hd[w*8+6], hd[w*8+7]);
+        }
         CUDA_CHECK(cudaGetLastError());
         return;
     }
@@ -654,10 +662,11 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                 (void)avg;
                 int G = std::max(1, std::min(lv.max_width, maxw / 2));
                 if (getenv("AMGB200_CTA_G")) G = std::max(1, std::min(maxw, atoi(getenv("AMGB200_CTA_G"))));
+                G = std::min(G, maxw / 2);                 // the producer/consumer barrier scheme needs >= 2 groups
                 lv.cta_G = G;
-                lv.cta_D = std::max(1, maxw / G);
-                if (getenv("AMGB200_CTA_D")) lv.cta_D = std::max(1, std::min(maxw / G, atoi(getenv("AMGB200_CTA_D"))));
-                const size_t needb = (size_t)((lv.n + 1) & ~1) * 8 + (size_t)lv.cta_G * lv.cta_D * SUPER * 8;
+                lv.cta_D = std::max(2, maxw / G);
+                if (getenv("AMGB200_CTA_D")) lv.cta_D = std::max(2, std::min(maxw / G, atoi(getenv("AMGB200_CTA_D"))));
+                const size_t needb = (size_t)((lv.n + 1) & ~1) * 8 + (size_t)lv.cta_G * lv.cta_D * STAGE * 8;
                 lv.x_in_smem = lv.strategy == 2 && needb <= (size_t)h->max_dyn_smem && !(getenv("AMGB200_NO_SMEM_X") && atoi(getenv("AMGB200_NO_SMEM_X")));
             }
             if (getenv("AMGB200_GS_STRATEGY") && lv.ordered) lv.strategy = std::max(1, std::min(2, atoi(getenv("AMGB200_GS_STRATEGY"))));
@@ -675,6 +684,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     h->d_partial = dev_alloc<double>((size_t)4 * h->partial_stride);
     h->d_scal = dev_alloc<double>(8);
     CUDA_CHECK(cudaMallocHost((void **)&h->h_scal, 8 * sizeof(double)));
+    if (getenv("AMGB200_DEBUG_TIMING")) h->d_dbg = dev_alloc<long long>(16 * 8);
     h->d_xnat = dev_alloc<double>(maxn);
     h->d_bnat = dev_alloc<double>(maxn);
     CUDA_CHECK(cudaDeviceSynchronize());

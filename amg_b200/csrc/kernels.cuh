@@ -181,11 +181,15 @@ __device__ __forceinline__ double spmv_finish_sell(SellItem<SCH> &it, const doub
 // prologue() touches only the static matrix (and b) and may run before a dependency wait.
 // ==========================================================================================
 constexpr int SUPER = 128;
+constexpr int STAGE = SUPER + 16;   // per-warp product staging area (the chain reads up to 16 slots ahead)
 struct CsrItem {
     int k, p0, p1;
-    int j[4];
-    double a[4];
+    int j[4], j1[4];           // super chunk 0 and 1
+    double a[4], a1[4];
     double bk;
+#ifdef AMGB200_TIMING
+    long long tg = 0, tp = 0, tc = 0, te = 0;
+#endif
     __device__ __forceinline__ void load_super(const DMat &A, int base, int lane, int (&jj)[4], double (&aa)[4]) const {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -198,6 +202,7 @@ struct CsrItem {
         p0 = A.rptr[row];
         p1 = A.rptr[row + 1];
         load_super(A, p0, lane, j, a);
+        load_super(A, p0 + SUPER, lane, j1, a1);
         bk = b ? b[row] : 0.0;
     }
 };
@@ -209,13 +214,32 @@ template <bool COH, bool GS>
 __device__ __forceinline__ double csr_row_exact(const DMat &A, CsrItem &it, const double *x, double t, double &d, int lane, double *sprod) {
     double dl = 0.0;
     double xc[4];
+#ifdef AMGB200_TIMING
+    long long k0 = clock64();
+#endif
 #pragma unroll
     for (int u = 0; u < 4; ++u) xc[u] = (it.j[u] >= 0 && !(GS && it.j[u] == it.k)) ? ld_x<COH>(x + it.j[u]) : 0.0;
+#ifdef AMGB200_TIMING
+    { double sink = xc[0] + xc[1] + xc[2] + xc[3]; if (sink == 1.2345e300) it.k = -1; long long k1 = clock64(); it.tg += k1 - k0; }
+#endif
     for (int base = it.p0; base < it.p1; base += SUPER) {
+#ifdef AMGB200_TIMING
+        long long k2 = clock64();
+#endif
+        // stage 1: col/val of super chunk s+2 ; stage 2: x gather of s+1 (its col arrived an iteration ago)
         int jn[4];
         double an[4], xn[4];
         const bool more = base + SUPER < it.p1;
-        if (more) it.load_super(A, base + SUPER, lane, jn, an);
+        if (base + 2 * SUPER < it.p1) it.load_super(A, base + 2 * SUPER, lane, jn, an);
+        else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { jn[u] = -1; an[u] = 0.0; }
+        }
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xn[u] = (it.j1[u] >= 0 && !(GS && it.j1[u] == it.k)) ? ld_x<COH>(x + it.j1[u]) : 0.0;
+        }
+        // stage 3: products of super chunk s into the staging buffer, then the in-order chain
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             double prod = 0.0;
@@ -226,35 +250,56 @@ __device__ __forceinline__ double csr_row_exact(const DMat &A, CsrItem &it, cons
             sprod[u * 32 + lane] = prod;
         }
         __syncwarp();
-        if (more) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) xn[u] = (jn[u] >= 0 && !(GS && jn[u] == it.k)) ? ld_x<COH>(x + jn[u]) : 0.0;
-        }
+#ifdef AMGB200_TIMING
+        long long k3 = clock64(); it.tp += k3 - k2;
+#endif
         const int cnt = min(SUPER, it.p1 - base);
         const double2 *sp2 = reinterpret_cast<const double2 *>(sprod);
-        int q = 0;
-        for (; q + 8 <= cnt; q += 8) {
-            const double2 v0 = sp2[(q >> 1)], v1 = sp2[(q >> 1) + 1], v2 = sp2[(q >> 1) + 2], v3 = sp2[(q >> 1) + 3];
-            if (GS) {
-                t = __dsub_rn(t, v0.x); t = __dsub_rn(t, v0.y); t = __dsub_rn(t, v1.x); t = __dsub_rn(t, v1.y);
-                t = __dsub_rn(t, v2.x); t = __dsub_rn(t, v2.y); t = __dsub_rn(t, v3.x); t = __dsub_rn(t, v3.y);
-            } else {
-                t = __dadd_rn(t, v0.x); t = __dadd_rn(t, v0.y); t = __dadd_rn(t, v1.x); t = __dadd_rn(t, v1.y);
-                t = __dadd_rn(t, v2.x); t = __dadd_rn(t, v2.y); t = __dadd_rn(t, v3.x); t = __dadd_rn(t, v3.y);
+        // 8-term half blocks, ping-pong: the LDS.128 of the next half block are issued before the chain
+        // of the current one.  The __syncwarp between them keeps ptxas from sinking the loads next to
+        // their uses (which would expose ~30 cycles of shared-memory latency every few terms).
+        // Slots >= cnt hold +0.0 (exact no-ops); reads run up to 16 slots past the staged chunk (STAGE pad).
+        {
+            double2 va[4], vb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) va[u] = sp2[u];
+            int q = 0;
+            while (true) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) vb[u] = sp2[(q >> 1) + 4 + u];
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (GS) { t = __dsub_rn(t, va[u].x); t = __dsub_rn(t, va[u].y); }
+                    else { t = __dadd_rn(t, va[u].x); t = __dadd_rn(t, va[u].y); }
+                }
+                q += 8;
+                if (q >= cnt) break;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) va[u] = sp2[(q >> 1) + 4 + u];
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (GS) { t = __dsub_rn(t, vb[u].x); t = __dsub_rn(t, vb[u].y); }
+                    else { t = __dadd_rn(t, vb[u].x); t = __dadd_rn(t, vb[u].y); }
+                }
+                q += 8;
+                if (q >= cnt) break;
             }
         }
-        for (; q < cnt; q += 2) {                       // slot cnt holds +0.0 when cnt is odd
-            const double2 v = sp2[q >> 1];
-            if (GS) { t = __dsub_rn(t, v.x); t = __dsub_rn(t, v.y); }
-            else { t = __dadd_rn(t, v.x); t = __dadd_rn(t, v.y); }
-        }
+#ifdef AMGB200_TIMING
+        { if (t == 1.2345e300) it.k = -1; long long k4 = clock64(); it.tc += k4 - k3; }
+#endif
         __syncwarp();
         if (more) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { it.j[u] = jn[u]; it.a[u] = an[u]; xc[u] = xn[u]; }
+            for (int u = 0; u < 4; ++u) { it.j[u] = it.j1[u]; it.a[u] = it.a1[u]; xc[u] = xn[u]; it.j1[u] = jn[u]; it.a1[u] = an[u]; }
         }
     }
-    d = warp_sum(dl);          // exactly one lane holds the diagonal; adding zeros is exact
+    {                          // exactly one lane saw the diagonal entry: broadcast it
+        const unsigned m = __ballot_sync(FULL, dl != 0.0);
+        d = m ? __shfl_sync(FULL, dl, __ffs(m) - 1) : 0.0;
+    }
     return t;
 }
 
@@ -291,7 +336,7 @@ __device__ __forceinline__ void gs_finish_csr(const DMat &A, CsrItem &it, double
 // one fully parallel pass (a pass whose dependency DAG has depth 1): items [item0, item1)
 template <int KIND, bool EXACT>
 __global__ void __launch_bounds__(BLOCK) gs_pass_kernel(DMat A, const double *__restrict__ b, double *x, int item0, int item1) {
-    __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * SUPER : 1];
+    __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * STAGE : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int it = item0 + blockIdx.x * WARPS_PER_BLOCK + warp;
     if (it >= item1) return;
@@ -302,7 +347,7 @@ __global__ void __launch_bounds__(BLOCK) gs_pass_kernel(DMat A, const double *__
     } else {
         CsrItem w;
         w.prologue(A, it, lane, b);
-        gs_finish_csr<false, EXACT>(A, w, x, lane, sprod + warp * SUPER);
+        gs_finish_csr<false, EXACT>(A, w, x, lane, sprod + warp * STAGE);
     }
 }
 
@@ -315,15 +360,15 @@ template <int KIND, bool EXACT>
 __global__ void __launch_bounds__(BLOCK) gs_ordered_grid_kernel(DMat A, const double *__restrict__ b, double *x,
                                                                 const int *__restrict__ item_wf, const int *__restrict__ wf_item_ptr,
                                                                 unsigned *cnt, int W, int items_per_sweep, int nsweeps) {
-    __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * SUPER : 1];
+    __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * STAGE : 1];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const long long total = (long long)items_per_sweep * nsweeps;
     int known = -1;                               // highest global wavefront known to be complete
+    int sweep = 0, it = warp;                     // (sweep, item) of work unit t, tracked without divisions
+    while (it >= items_per_sweep) { it -= items_per_sweep; ++sweep; }
     for (long long t = warp; t < total; t += nwarps) {
-        const int sweep = (int)(t / items_per_sweep);
-        const int it = (int)(t - (long long)sweep * items_per_sweep);
         const int wl = item_wf[it];
         const int g = sweep * W + wl;
         SellItem<20> ws;
@@ -341,10 +386,12 @@ __global__ void __launch_bounds__(BLOCK) gs_ordered_grid_kernel(DMat A, const do
             known = g - 1;
         }
         if constexpr (KIND == 0) gs_finish_sell<true>(ws, x);
-        else gs_finish_csr<true, EXACT>(A, wc, x, lane, sprod + (threadIdx.x >> 5) * SUPER);
+        else gs_finish_csr<true, EXACT>(A, wc, x, lane, sprod + (threadIdx.x >> 5) * STAGE);
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicAdd(cnt + g, 1u);
+        it += nwarps;
+        while (it >= items_per_sweep) { it -= items_per_sweep; ++sweep; }
     }
 }
 
@@ -359,13 +406,15 @@ __global__ void __launch_bounds__(BLOCK) gs_ordered_grid_kernel(DMat A, const do
 constexpr int CTA_MAX_WARPS_SELL = 8, CTA_MAX_WARPS_CSR = 16;
 template <int KIND, bool EXACT, bool XS>
 __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA_MAX_WARPS_CSR) gs_ordered_cta_kernel(
-    DMat A, const double *__restrict__ b, double *xg, const int *__restrict__ wf_item_ptr, int W, int nsweeps, int G, int D) {
+    DMat A, const double *__restrict__ b, double *xg, const int *__restrict__ wf_item_ptr, int W, int nsweeps, int G, int D,
+    long long *dbg) {
     extern __shared__ double dyn_smem[];
+    long long t_wait = 0, t_fin = 0, t_fetch = 0, n_items = 0, t_begin = clock64();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = warp / G, r = warp - grp * G;
     const int n = A.nrows;
     double *x = XS ? dyn_smem : xg;
-    double *sprod = dyn_smem + (XS ? ((n + 1) & ~1) : 0) + warp * SUPER;
+    double *sprod = dyn_smem + (XS ? ((n + 1) & ~1) : 0) + warp * STAGE;
     if (XS) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) dyn_smem[i] = xg[i];
         __syncthreads();
@@ -375,26 +424,51 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
     CsrItem wc;
     int i0 = 0, i1 = 0;
     bool have = false;
-    auto fetch = [&](int g) {
-        const int wl = g % W;
-        i0 = wf_item_ptr[wl]; i1 = wf_item_ptr[wl + 1];
+    int my_g = grp, my_wl = grp;                  // next wavefront of this warp's group (global index, index within a sweep)
+    while (my_wl >= W) my_wl -= W;
+    auto fetch = [&]() {
+        i0 = wf_item_ptr[my_wl]; i1 = wf_item_ptr[my_wl + 1];
         have = i0 + r < i1;
         if (have) { if constexpr (KIND == 0) ws.prologue(A, i0 + r, lane, b); else wc.prologue(A, i0 + r, lane, b); }
     };
-    if (grp < totalw) fetch(grp);
-    for (int g = 0; g < totalw; ++g) {
-        if (g % D == grp) {
-            if (have) {
-                if constexpr (KIND == 0) gs_finish_sell<false>(ws, x); else gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod);
-                for (int it = i0 + r + G; it < i1; it += G) {          // wavefront wider than the group
-                    if constexpr (KIND == 0) { ws.prologue(A, it, lane, b); gs_finish_sell<false>(ws, x); }
-                    else { wc.prologue(A, it, lane, b); gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod); }
-                }
+    // Wavefront g is produced by group g mod D and consumed (waited for) by group (g+1) mod D through the
+    // named barrier 1 + (g mod 8): the producers only *arrive* (non-blocking) and go on to prefetch their
+    // next wavefront, so the prefetch latency never delays the consumers.  D >= 2.
+    const int pair_threads = 2 * G * 32;
+    if (my_g < totalw) fetch();
+    for (; my_g < totalw; my_g += D) {
+        long long c0 = clock64();
+        if (my_g > 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + ((my_g - 1) & 7)), "r"(pair_threads) : "memory");
+#ifdef AMGB200_TIMING
+        { volatile double *vs = sprod; if (vs[0] == 1.2345e300) ++n_items; }
+#endif
+        long long c1 = clock64();
+        t_wait += c1 - c0;
+        if (have) {
+            ++n_items;
+            if constexpr (KIND == 0) gs_finish_sell<false>(ws, x); else gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod);
+            for (int it = i0 + r + G; it < i1; it += G) {              // wavefront wider than the group
+                if constexpr (KIND == 0) { ws.prologue(A, it, lane, b); gs_finish_sell<false>(ws, x); }
+                else { wc.prologue(A, it, lane, b); gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod); }
             }
-            if (g + D < totalw) fetch(g + D);
         }
-        __syncthreads();
+        __threadfence_block();
+        if (my_g + 1 < totalw) asm volatile("bar.arrive %0, %1;" ::"r"(1 + (my_g & 7)), "r"(pair_threads) : "memory");
+        long long c2 = clock64();
+        t_fin += c2 - c1;
+        my_wl += D;
+        while (my_wl >= W) my_wl -= W;
+        if (my_g + D < totalw) fetch();
+        t_fetch += clock64() - c2;
     }
+#ifdef AMGB200_TIMING
+    if (dbg && lane == 0) { dbg[warp * 8 + 5] = wc.tg; dbg[warp * 8 + 6] = wc.tp; dbg[warp * 8 + 7] = wc.tc; }
+#endif
+    if (dbg && lane == 0) {
+        dbg[warp * 8 + 0] = t_wait; dbg[warp * 8 + 1] = t_fin; dbg[warp * 8 + 2] = t_fetch; dbg[warp * 8 + 3] = n_items;
+        dbg[warp * 8 + 4] = clock64() - t_begin;
+    }
+    __syncthreads();
     if (XS) for (int i = threadIdx.x; i < n; i += blockDim.x) xg[i] = dyn_smem[i];
 }
 
@@ -415,7 +489,7 @@ template <int KIND, int MODE, int RED, bool EXACT>
 __global__ void __launch_bounds__(BLOCK) spmv_kernel(DMat A, const double *__restrict__ x, double *y, const double *__restrict__ b,
                                                      double alpha, double *partial) {
     __shared__ double red[32];
-    __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * SUPER : 1];
+    __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * STAGE : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int it = blockIdx.x * WARPS_PER_BLOCK + warp;
     double contrib = 0.0;
@@ -432,7 +506,7 @@ __global__ void __launch_bounds__(BLOCK) spmv_kernel(DMat A, const double *__res
             CsrItem w;
             w.prologue(A, it, lane, nullptr);
             double d;
-            const double t = EXACT ? csr_row_exact<false, false>(A, w, x, 0.0, d, lane, sprod + warp * SUPER)
+            const double t = EXACT ? csr_row_exact<false, false>(A, w, x, 0.0, d, lane, sprod + warp * STAGE)
                                    : csr_row_fast<false, false>(A, w, x, 0.0, d, lane);
             if (lane == 0) {
                 const double out = spmv_store<MODE>(t, alpha, b, y, it);

@@ -117,7 +117,19 @@ def compile_mode(mode, tmp):
             os.remove(lib)
         run(["ar", "rcs", lib] + host, d)
         shutil.copy(os.path.join(d, "SSS_main.o"), os.path.join(OUT, "sss_main.o"))
-        shutil.copy(os.path.join(REF, "Matrix/1138_bus.mtx"), os.path.join(OUT, "1138_bus.mtx"))
+        bus = os.path.join(OUT, "1138_bus.mtx")
+        if os.path.exists(bus):
+            os.chmod(bus, 0o644)
+        shutil.copy(os.path.join(REF, "Matrix/1138_bus.mtx"), bus)
+        os.chmod(bus, 0o644)
+        # the drop-in demo: the reference's own main + host objects linked against libamgb200.so
+        # (INTEGRATION.md section 1); only possible once the product library has been built
+        prod = os.path.join(os.path.dirname(HERE), "amg_b200", "libamgb200.so")
+        if os.path.exists(prod):
+            exe = os.path.join(OUT, "amg_dropin")
+            run(["nvcc", "-Xcompiler", "-fopenmp", "-o", exe, "SSS_main.o"] + host +
+                ["-L" + os.path.dirname(prod), "-lamgb200", "-Xlinker", "-rpath=$ORIGIN/../../amg_b200", "-lm"], d)
+            print(f"[oracle/_ref] built {os.path.relpath(exe, HERE)} (reference host + libamgb200.so)")
     return so
 
 

@@ -1,0 +1,69 @@
+"""The reference's own host -- main(), MatrixMarket loader, SSS_solver_amg, the whole setup phase --
+linked against libamgb200.so instead of its four solve-phase objects.
+oracle/_ref/amg_dropin is built by oracle/build_ref.py where /root/reference exists and travels to
+the GPU box as a prebuilt binary."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from amg_b200 import HostHierarchy, generate, read_mtx
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "oracle", "_ref", "amg_dropin")
+pytestmark = pytest.mark.gpu
+
+
+def write_mtx(path, A):
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n")
+        f.write(f"{A.nrows} {A.ncols} {A.nnz}\n")
+        rows = np.repeat(np.arange(A.nrows), np.diff(A.row_ptr))
+        for r, c, v in zip(rows, A.col_idx, A.val):
+            f.write(f"{r + 1} {c + 1} {v:.17g}\n")
+
+
+def run_dropin(path):
+    out = subprocess.run([EXE, path], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, AMGB200_VERBOSE="1"))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    return out.stdout
+
+
+def parse(stdout):
+    its = int(re.search(r"AMG iterations: (\d+)", stdout).group(1))
+    res = float(re.search(r"AMG residual: (\S+)", stdout).group(1))
+    table = [(int(m.group(1)), float(m.group(2)), float(m.group(3)))
+             for m in re.finditer(r"^\s*(\d+) \|\s+(\S+)\s+\|\s+(\S+)\s+\|", stdout, re.M)]
+    levels = [(int(m.group(2)), int(m.group(3))) for m in re.finditer(r"^\s*(\d+)\s+(\d+)\s+(\d+)\s+[\d.]+\s*$", stdout, re.M)]
+    return its, res, table, levels
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/amg_dropin not built (needs /root/reference)")
+def test_reference_host_with_libamgb200_on_generated_poisson(tmp_path, oracle):
+    A = generate("p3d", 20)
+    p = str(tmp_path / "p3d20.mtx")
+    write_mtx(p, A)
+    stdout = run_dropin(p)
+    its, res, table, levels = parse(stdout)
+    hier = HostHierarchy(A, tol=1e-6)                      # the reference's main hard-codes tol = 1e-6 (SSS_main.c:33)
+    rtn, x, hist = oracle.solve(hier, np.ones(A.nrows), np.ones(A.nrows), 0)
+    assert levels == hier.table()                          # the reference's own setup printed this table
+    assert its == rtn.nits
+    assert abs(res - rtn.ares) <= 1e-5 * rtn.ares          # printed with %g (6 digits)
+    assert [t[0] for t in table] == list(range(rtn.nits + 1))
+    for (_, rel, absr), want in zip(table[1:], hist):
+        assert abs(absr - want) <= 1e-6 * want             # printed with %13.6e
+    assert "AMG solve time:" in stdout and "AMG totally time:" in stdout
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/amg_dropin not built (needs /root/reference)")
+def test_reference_host_with_libamgb200_on_1138_bus(oracle):
+    path = os.path.join(ROOT, "oracle", "_ref", "1138_bus.mtx")
+    stdout = run_dropin(path)
+    its, res, table, levels = parse(stdout)
+    assert levels == [(1138, 4054), (511, 2465), (230, 1416), (111, 939), (59, 733)]
+    assert its == 11
+    assert abs(res - 1.49702381972262923e-05) <= 1e-5 * 1.5e-5
