@@ -79,7 +79,9 @@ struct DevMatOwner {
 
 struct Level {
     int n = 0;
-    DevMatOwner A, P, R;
+    DevMatOwner A, P, R;               // A: layout used by the smoother
+    DevMatOwner Asp;                   // A in the layout used by SpMV/residual when it differs from the smoother's
+    const DMat &spmvA() const { return Asp.valid ? Asp.v : A.v; }
     int *d_order = nullptr;            // schedule position -> natural row
     double *x = nullptr, *b = nullptr, *wp = nullptr;
     bool smoothed = false, ordered = false;
@@ -105,6 +107,7 @@ struct amgb200_hier {
     int num_sms = 0, gs_block = 64, gs_max_blocks[2] = {0, 0};
     bool exact = true;
     int max_dyn_smem = 0;
+    int cluster_block = 256;
     double *d_partial = nullptr;       // 4 x partial_stride block partials
     int partial_stride = 0;
     double *d_scal = nullptr;          // 8 reduced scalars
@@ -206,6 +209,38 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
             for (int w = 0; w < nw; ++w) printf("   warp %2d: wait %9lld  finish %9lld  fetch %9lld  items %6lld  total %9lld | gather %9lld prod %9lld chain %9lld\n", w, hd[w*8], hd[w*8+1], hd[w*8+2], hd[w*8+3], hd[w*8+4], hd[w*8+5], hd[w*8+6], hd[w*8+7]);
         }
         CUDA_CHECK(cudaGetLastError());
+        return;
+    }
+    if (lv.strategy == 3) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cluster_kernel<KIND, EXACT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            attr_set = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CLUSTER_CTAS);
+        {
+            // enough warps in the cluster to take the widest wavefront in one round, and no more (barrier cost grows with threads)
+            const int maxw = KIND == 0 ? std::min(h->cluster_block / 32, CLUSTER_WARPS_SELL) : CLUSTER_WARPS_CSR;
+            const int nwc = std::max(1, std::min(maxw, (lv.max_width + CLUSTER_CTAS - 1) / CLUSTER_CTAS));
+            cfg.blockDim = dim3(32 * nwc);
+        }
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CLUSTER_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, gs_ordered_cluster_kernel<KIND, EXACT>, lv.A.v, (const double *)lv.b, lv.x, (const int *)lv.d_wf_item_ptr, lv.W, nsweeps, h->d_dbg));
+        ++g_launches;
+        if (h->d_dbg) {
+            long long hd[5 * 8];
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            CUDA_CHECK(cudaMemcpy(hd, h->d_dbg, sizeof(hd), cudaMemcpyDeviceToHost));
+            printf("[dbg] cluster kernel n=%d W=%d sweeps=%d\n", lv.n, lv.W, nsweeps);
+            for (int w = 0; w < 5; ++w) printf("   warp slot %d: finish(first) %9lld  finish(extra rounds) %9lld  arrive %9lld  prefetch %9lld  wait %9lld  items %6lld\n", w, hd[w*8], hd[w*8+1], hd[w*8+2], hd[w*8+3], hd[w*8+4], hd[w*8+5]);
+        }
         return;
     }
     const int need = nsweeps * lv.W;
@@ -487,7 +522,7 @@ void cycle(amgb200_hier *h) {
             Level &lv = h->L[l];
             visits[l]++;
             { PhaseTimer pt(h, 0, l); smooth(h, l, h->pars.pre_iter); }
-            { PhaseTimer pt(h, 1, l); spmv(h, lv.A.v, MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0); }
+            { PhaseTimer pt(h, 1, l); spmv(h, lv.spmvA(), MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0); }
             { PhaseTimer pt(h, 2, l); spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[l + 1].b, nullptr, 0.0); }
             l++;
             dev_zero(h, h->L[l].n, h->L[l].x);
@@ -592,8 +627,10 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         h->gs_max_blocks[1] = std::max(1, per_sm * h->num_sms);
     }
     const double sell_max_mean = getenv("AMGB200_SELL_MAX_MEAN") ? atof(getenv("AMGB200_SELL_MAX_MEAN")) : (h->exact ? 48.0 : 24.0);
-    const double cta_max_avg = getenv("AMGB200_CTA_MAX_AVG") ? atof(getenv("AMGB200_CTA_MAX_AVG")) : 16.0;
+    const double cta_max_avg = getenv("AMGB200_CTA_MAX_AVG") ? atof(getenv("AMGB200_CTA_MAX_AVG")) : 6.0;
+    if (getenv("AMGB200_CLUSTER_BLOCK")) h->cluster_block = std::max(32, std::min(BLOCK, atoi(getenv("AMGB200_CLUSTER_BLOCK")) / 32 * 32));
     auto kind_of = [&](const amgb200_mat &M) { return choose_kind(M, sell_max_mean); };
+    const double ordered_csr_min = getenv("AMGB200_ORDERED_CSR_MIN") ? atof(getenv("AMGB200_ORDERED_CSR_MIN")) : 24.0;
 
     const double t0 = now_s();
     const int nl = h->nl;
@@ -628,9 +665,22 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         lv.n = c.A.num_rows;
         lv.smoothed = l < nl - 1;
         DevLayout lay;
-        build_layout(c.A, S.order.data(), S.pos.data(), kind_of(c.A), lv.smoothed ? &S.wf_row_ptr : nullptr, lay);
+        const bool is_ordered = l < nl - 1 && (S.wf_count[0] > 1 || S.wf_count[1] > 1);
+        // ordered (latency-bound) sweeps: a warp per row keeps the scattered x gathers of one dependency step
+        // at ~len L1 wavefronts instead of 32*len for a 32-row slice, so rows longer than ordered_csr_min
+        // use the warp-per-row layout there; SpMV/residual (throughput-bound) keep the coalesced SELL layout
+        int gs_kind = kind_of(c.A);
+        const double mean_len = (double)c.A.num_nnzs / std::max(1, c.A.num_rows);
+        if (is_ordered && h->exact && mean_len > ordered_csr_min) gs_kind = KIND_CSR;
+        build_layout(c.A, S.order.data(), S.pos.data(), gs_kind, lv.smoothed ? &S.wf_row_ptr : nullptr, lay);
         lv.A.upload(lay);
         max_items = std::max(max_items, lay.nitems());
+        if (gs_kind != kind_of(c.A)) {
+            DevLayout lsp;
+            build_layout(c.A, S.order.data(), S.pos.data(), kind_of(c.A), nullptr, lsp);
+            lv.Asp.upload(lsp);
+            max_items = std::max(max_items, lsp.nitems());
+        }
         lv.d_order = dev_upload(S.order);
         lv.x = dev_alloc<double>(lv.n);
         lv.b = dev_alloc<double>(lv.n);
@@ -654,8 +704,9 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             }
             lv.d_item_wf = dev_upload(item_wf);
             lv.d_wf_item_ptr = dev_upload(wip);
+            // 0 parallel passes | 2 one CTA (narrow wavefronts) | 3 one 16-CTA cluster | 1 cooperative grid (fallback)
             if (!lv.ordered) lv.strategy = 0;
-            else lv.strategy = ((double)wip[lv.W] / lv.W <= (lay.kind == KIND_CSR ? 2.0 * cta_max_avg : cta_max_avg)) ? 2 : 1;
+            else lv.strategy = ((double)wip[lv.W] / lv.W <= cta_max_avg) ? 2 : 3;
             {
                 const int maxw = lay.kind == KIND_SELL ? CTA_MAX_WARPS_SELL : CTA_MAX_WARPS_CSR;
                 const double avg = (double)wip[lv.W] / lv.W;
@@ -669,7 +720,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                 const size_t needb = (size_t)((lv.n + 1) & ~1) * 8 + (size_t)lv.cta_G * lv.cta_D * STAGE * 8;
                 lv.x_in_smem = lv.strategy == 2 && needb <= (size_t)h->max_dyn_smem && !(getenv("AMGB200_NO_SMEM_X") && atoi(getenv("AMGB200_NO_SMEM_X")));
             }
-            if (getenv("AMGB200_GS_STRATEGY") && lv.ordered) lv.strategy = std::max(1, std::min(2, atoi(getenv("AMGB200_GS_STRATEGY"))));
+            if (getenv("AMGB200_GS_STRATEGY") && lv.ordered) lv.strategy = std::max(1, std::min(3, atoi(getenv("AMGB200_GS_STRATEGY"))));
             // transfers: P_l rows in this level's schedule, columns in the next level's; R_l the other way round
             DevLayout lp, lr;
             build_layout(c.P, S.order.data(), sched[l + 1].pos.data(), kind_of(c.P), nullptr, lp);
@@ -707,7 +758,7 @@ void amgb200_free(amgb200_hier *h) {
     if (!h) return;
     cudaStreamSynchronize(h->stream);
     for (Level &lv : h->L) {
-        lv.A.release(); lv.P.release(); lv.R.release();
+        lv.A.release(); lv.Asp.release(); lv.P.release(); lv.R.release();
         cudaFree(lv.d_order); cudaFree(lv.x); cudaFree(lv.b); cudaFree(lv.wp);
         cudaFree(lv.d_item_wf); cudaFree(lv.d_wf_item_ptr); cudaFree(lv.d_cnt);
     }
@@ -767,7 +818,7 @@ void amgb200_upload_seconds(const amgb200_hier *h, double s[2]) { s[0] = h->anal
 long long amgb200_device_bytes(const amgb200_hier *h) {
     long long tot = 0;
     for (const Level &lv : h->L) {
-        for (const DevMatOwner *m : {&lv.A, &lv.P, &lv.R}) if (m->valid) tot += m->padded * 12 + (long long)m->v.nitems * 12;
+        for (const DevMatOwner *m : {&lv.A, &lv.Asp, &lv.P, &lv.R}) if (m->valid) tot += m->padded * 12 + (long long)m->v.nitems * 12;
         tot += (long long)lv.n * (3 * 8 + 4);
     }
     return tot;
@@ -776,7 +827,7 @@ const char *amgb200_level_kernel(const amgb200_hier *h, int level) {
     check_level(h, level);
     const Level &lv = h->L[level];
     if (!lv.smoothed) return "none";
-    static const char *names[3] = {"gs_pass_kernel", "gs_ordered_grid_kernel", "gs_ordered_cta_kernel"};
+    static const char *names[4] = {"gs_pass_kernel", "gs_ordered_grid_kernel", "gs_ordered_cta_kernel", "gs_ordered_cluster_kernel"};
     return names[lv.strategy];
 }
 
@@ -828,7 +879,7 @@ amgb200_rtn amgb200_solve_device(amgb200_hier *h, double *d_x, const double *d_b
     while (++iter <= h->pars.max_it) {
         cycle(h);
         double absres;
-        { PhaseTimer pt(h, 5); absres = dev_true_residual(h, l0.A.v, l0.x, l0.b, l0.wp); }
+        { PhaseTimer pt(h, 5); absres = dev_true_residual(h, l0.spmvA(), l0.x, l0.b, l0.wp); }
         const double relres = absres / sumb;
         if (h->opt.verbose >= 1) print_itinfo(iter, relres, absres, absres / absres0);
         absres0 = absres;
@@ -874,7 +925,7 @@ void amgb200_level_spmv(amgb200_hier *h, int level, int which, double alpha, con
     Level &lv = h->L[level];
     if (which != 0 && !lv.P.valid) { fprintf(stderr, "libamgb200: level %d has no transfer operators\n", level); exit(72); }
     const int in_l = which == 1 ? level + 1 : level, out_l = which == 2 ? level + 1 : level;
-    const DMat &M = which == 0 ? lv.A.v : which == 1 ? lv.P.v : lv.R.v;
+    const DMat &M = which == 0 ? lv.spmvA() : which == 1 ? lv.P.v : lv.R.v;
     Level &li = h->L[in_l], &lo = h->L[out_l];
     // scratch: input in li.wp (schedule), output in lo.b ... use level vectors that the hooks own
     double *din = li.wp, *dout = lo.b;
@@ -915,7 +966,7 @@ double amgb200_level_residual(amgb200_hier *h, int level, const double *x, const
     CUDA_CHECK(cudaMemcpyAsync(h->d_bnat, b, (size_t)lv.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     to_schedule(h, level, h->d_xnat, lv.x);
     to_schedule(h, level, h->d_bnat, lv.b);
-    const double nrm = dev_true_residual(h, lv.A.v, lv.x, lv.b, lv.wp);
+    const double nrm = dev_true_residual(h, lv.spmvA(), lv.x, lv.b, lv.wp);
     if (r) {
         to_natural(h, level, lv.wp, h->d_xnat);
         CUDA_CHECK(cudaMemcpyAsync(r, h->d_xnat, (size_t)lv.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -947,10 +998,10 @@ double amgb200_time_op(amgb200_hier *h, int level, int op, int reps) {
     auto run = [&]() {
         switch (op) {
             case 0: smooth(h, level, 1); break;
-            case 1: spmv(h, lv.A.v, MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0); break;
+            case 1: spmv(h, lv.spmvA(), MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0); break;
             case 2: spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[level + 1].b, nullptr, 0.0); break;
             case 3: spmv(h, lv.P.v, MODE_AMXPY, RED_NONE, h->L[level + 1].x, lv.x, nullptr, 1.0); break;
-            default: spmv(h, lv.A.v, MODE_MXY, RED_NONE, lv.x, lv.wp, nullptr, 0.0); break;
+            default: spmv(h, lv.spmvA(), MODE_MXY, RED_NONE, lv.x, lv.wp, nullptr, 0.0); break;
         }
     };
     run(); run();                                    // warm-up

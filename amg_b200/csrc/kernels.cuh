@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace amgb200 {
 
@@ -96,16 +97,26 @@ struct SellItem {
             else { j[u] = -1; a[u] = 0.0; }
         }
     }
-    __device__ __forceinline__ void prologue(const DMat &A, int s, int lane, const double *__restrict__ b = nullptr) {
-        const int r0 = A.slice_row[s];
-        r1 = A.slice_row[s + 1];
-        const long long p0 = A.slice_ptr[s];
-        width = (int)((A.slice_ptr[s + 1] - p0) >> 5);
-        k = r0 + lane;
-        cp = A.col + p0 + lane;
-        vp = A.val + p0 + lane;
+    // stage 1: the slice descriptor (two dependent-load levels below the wavefront table)
+    struct Desc { int r0, r1; long long p0, p1; };
+    __device__ __forceinline__ static Desc load_desc(const DMat &A, int s) {
+        Desc d;
+        d.r0 = A.slice_row[s]; d.r1 = A.slice_row[s + 1];
+        d.p0 = A.slice_ptr[s]; d.p1 = A.slice_ptr[s + 1];
+        return d;
+    }
+    // stage 2: first chunk of matrix entries and the right-hand side
+    __device__ __forceinline__ void load_entries(const DMat &A, const Desc &d, int lane, const double *__restrict__ b) {
+        r1 = d.r1;
+        width = (int)((d.p1 - d.p0) >> 5);
+        k = d.r0 + lane;
+        cp = A.col + d.p0 + lane;
+        vp = A.val + d.p0 + lane;
         load_chunk(0);
         bk = (b && k < r1) ? b[k] : 0.0;
+    }
+    __device__ __forceinline__ void prologue(const DMat &A, int s, int lane, const double *__restrict__ b = nullptr) {
+        load_entries(A, load_desc(A, s), lane, b);
     }
 };
 
@@ -197,13 +208,20 @@ struct CsrItem {
             if (p < p1) { jj[u] = A.col[p]; aa[u] = A.val[p]; } else { jj[u] = -1; aa[u] = 0.0; }
         }
     }
-    __device__ __forceinline__ void prologue(const DMat &A, int row, int lane, const double *__restrict__ b) {
-        k = row;
-        p0 = A.rptr[row];
-        p1 = A.rptr[row + 1];
+    struct Desc { int row, p0, p1; };
+    __device__ __forceinline__ static Desc load_desc(const DMat &A, int row) {
+        Desc d;
+        d.row = row; d.p0 = A.rptr[row]; d.p1 = A.rptr[row + 1];
+        return d;
+    }
+    __device__ __forceinline__ void load_entries(const DMat &A, const Desc &d, int lane, const double *__restrict__ b) {
+        k = d.row; p0 = d.p0; p1 = d.p1;
         load_super(A, p0, lane, j, a);
         load_super(A, p0 + SUPER, lane, j1, a1);
-        bk = b ? b[row] : 0.0;
+        bk = b ? b[d.row] : 0.0;
+    }
+    __device__ __forceinline__ void prologue(const DMat &A, int row, int lane, const double *__restrict__ b) {
+        load_entries(A, load_desc(A, row), lane, b);
     }
 };
 
@@ -470,6 +488,92 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
     }
     __syncthreads();
     if (XS) for (int i = threadIdx.x; i < n; i += blockDim.x) xg[i] = dyn_smem[i];
+}
+
+// Ordered sweeps inside ONE thread-block cluster (16 CTAs = 16 SMs on one die): the wavefronts of the
+// level are walked in order, the items of a wavefront are spread over all warps of the cluster, and
+// consecutive wavefronts are separated by the hardware cluster barrier (barrier.cluster, ~0.2 us)
+// instead of a round trip through L2 atomics (~2-5 us for a grid-wide counter).  The barrier is split:
+// after its last store a warp *arrives*, then prefetches the matrix entries of its next item, then
+// *waits*.  x lives in global memory and is read at L2 (ld.cg) after the acquire.
+constexpr int CLUSTER_CTAS = 16;
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+constexpr int CLUSTER_WARPS_SELL = 8, CLUSTER_WARPS_CSR = 16;
+template <int KIND, bool EXACT>
+__global__ void __launch_bounds__(KIND == 0 ? 32 * CLUSTER_WARPS_SELL : 32 * CLUSTER_WARPS_CSR) gs_ordered_cluster_kernel(
+    DMat A, const double *__restrict__ b, double *x, const int *__restrict__ wf_item_ptr, int W, int nsweeps, long long *dbg) {
+    __shared__ double sprod[KIND == 1 ? CLUSTER_WARPS_CSR * STAGE : 1];
+    using Item = typename std::conditional<KIND == 0, SellItem<20>, CsrItem>::type;
+    using Desc = typename Item::Desc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    const int gw = (int)cluster_ctarank() * nw + warp;        // warp index within the cluster
+    const int TW = CLUSTER_CTAS * nw;
+    const int totalw = W * nsweeps;
+    double *sp = sprod + (KIND == 1 ? warp * STAGE : 0);
+    auto finish = [&](Item &w) {
+        if constexpr (KIND == 0) gs_finish_sell<true>(w, x); else gs_finish_csr<true, EXACT>(A, w, x, lane, sp);
+    };
+    // Look-ahead pipeline over the (static) schedule, one stage per wavefront step, so that no dependent
+    // load chain (wavefront table -> item descriptor -> matrix entries) is exposed between two barriers:
+    //   (a0,a1) item range of wavefront g     cur : entries of my item in g     (loaded during step g-1)
+    //   (b0,b1) item range of wavefront g+1   dn  : descriptor of my item in g+1 (loaded during step g-1)
+    //   (c0,c1) item range of wavefront g+2
+    int wl2 = 2 % W;
+    int a0 = wf_item_ptr[0], a1 = wf_item_ptr[1];
+    int b0 = wf_item_ptr[1 % W], b1 = wf_item_ptr[1 % W + 1];
+    int c0 = wf_item_ptr[wl2], c1 = wf_item_ptr[wl2 + 1];
+    Item cur;
+    Desc dn = {};
+    bool have = a0 + gw < a1, have_n = b0 + gw < b1;
+    if (have) cur.prologue(A, a0 + gw, lane, b);
+    if (have_n) dn = Item::load_desc(A, b0 + gw);
+#ifdef AMGB200_TIMING
+    long long tf = 0, tf2 = 0, ta = 0, tpre = 0, tw = 0, nit = 0;
+#endif
+    for (int g = 0; g < totalw; ++g) {
+#ifdef AMGB200_TIMING
+        long long k0 = clock64(), k1 = k0;
+#endif
+        if (have) {
+            finish(cur);
+#ifdef AMGB200_TIMING
+            ++nit; k1 = clock64();
+#endif
+            for (int it = a0 + gw + TW; it < a1; it += TW) { cur.prologue(A, it, lane, b); finish(cur); }   // wider than the cluster
+        }
+#ifdef AMGB200_TIMING
+        long long k2 = clock64(); tf += k1 - k0; tf2 += k2 - k1;
+#endif
+        if (g + 1 < totalw) {
+            cluster_arrive();
+#ifdef AMGB200_TIMING
+            long long k3 = clock64(); ta += k3 - k2;
+#endif
+            a0 = b0; a1 = b1; have = have_n;
+            if (have) cur.load_entries(A, dn, lane, b);                 // descriptor arrived during the previous step
+            b0 = c0; b1 = c1; have_n = b0 + gw < b1;
+            if (have_n) dn = Item::load_desc(A, b0 + gw);
+            if (++wl2 == W) wl2 = 0;
+            c0 = wf_item_ptr[wl2]; c1 = wf_item_ptr[wl2 + 1];
+#ifdef AMGB200_TIMING
+            long long k4 = clock64(); tpre += k4 - k3;
+#endif
+            cluster_wait();
+#ifdef AMGB200_TIMING
+            tw += clock64() - k4;
+#endif
+        }
+    }
+#ifdef AMGB200_TIMING
+    if (dbg && lane == 0 && (gw < 4 || gw == TW - 1)) {
+        const int s = gw < 4 ? gw : 4;
+        dbg[s * 8 + 0] = tf; dbg[s * 8 + 1] = tf2; dbg[s * 8 + 2] = ta; dbg[s * 8 + 3] = tpre; dbg[s * 8 + 4] = tw; dbg[s * 8 + 5] = nit;
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
