@@ -74,6 +74,9 @@ EXPORTS = [
     "amgb200_version", "amgb200_generate", "amgb200_mat_free", "amgb200_setup", "amgb200_amg_destroy",
     "amgb200_default_pars", "amgb200_last_level_ms", "amgb200_set_profile", "amgb200_upload_seconds",
     "amgb200_device_bytes", "amgb200_level_kernel", "amgb200_bench_solve",
+    "amgb200_set_stream", "amgb200_level_vec", "amgb200_level_order", "amgb200_l0_shape", "amgb200_l0_gs_pass",
+    "amgb200_l0_residual", "amgb200_l0_prolong", "amgb200_restrict_from", "amgb200_cycle_from",
+    "amgb200_vec_to_schedule", "amgb200_vec_to_natural", "amgb200_sync",
 ]
 
 _lib = None
@@ -134,6 +137,19 @@ def lib():
         L.amgb200_level_kernel.argtypes = [C.c_void_p, C.c_int]
         L.amgb200_bench_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                           c_double_p, C.POINTER(Rtn)]
+        L.amgb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.amgb200_level_vec.restype = C.c_void_p
+        L.amgb200_level_vec.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.amgb200_level_order.argtypes = [C.c_void_p, C.c_int, c_int_p]
+        L.amgb200_l0_shape.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        L.amgb200_l0_gs_pass.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.amgb200_l0_residual.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.amgb200_l0_prolong.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.amgb200_restrict_from.argtypes = [C.c_void_p, C.c_int]
+        L.amgb200_cycle_from.argtypes = [C.c_void_p, C.c_int]
+        L.amgb200_vec_to_schedule.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.amgb200_vec_to_natural.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.amgb200_sync.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 

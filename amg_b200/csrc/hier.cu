@@ -61,7 +61,7 @@ struct DevMatOwner {
     int max_row = 0;
     bool valid = false;
     void upload(const DevLayout &L) {
-        v.kind = L.kind; v.nrows = L.nrows; v.ncols = L.ncols; v.nitems = L.nitems();
+        v.kind = L.kind; v.nrows = L.nrows; v.ncols = L.ncols; v.nitems = L.nitems(); v.max_row = L.max_row;
         v.slice_row = nullptr; v.slice_ptr = nullptr; v.rptr = nullptr;
         if (L.kind == KIND_SELL) { v.slice_row = dev_upload(L.slice_row); v.slice_ptr = dev_upload(L.slice_ptr); }
         else v.rptr = dev_upload(L.rptr);
@@ -121,6 +121,8 @@ struct amgb200_hier {
     double upload_s = 0, analysis_s = 0;
     double last_sumsq = 0;             // sum r_i^2 of the most recent dev_true_residual
     long long *d_dbg = nullptr;        // AMGB200_DEBUG_TIMING: per-warp cycle counters of the CTA kernel
+    int item0 = -1, item1 = -1;        // >= 0: restrict the next spmv launch to this item range
+    bool own_stream = true;
 };
 
 namespace {
@@ -149,12 +151,16 @@ struct PhaseTimer {                    // only active with AMGB200_PROFILE=1 (ad
 
 template <int KIND, int MODE, int RED, bool EXACT>
 void launch_spmv_t(amgb200_hier *h, const DMat &A, const double *x, double *y, const double *b, double alpha) {
-    const int grid = std::max(1, (A.nitems + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    const int item0 = h->item0 >= 0 ? h->item0 : 0, item1 = h->item0 >= 0 ? h->item1 : A.nitems;   // (item range: multi-GPU building blocks)
+    const int grid = std::max(1, (item1 - item0 + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     if (RED != RED_NONE && grid > h->partial_stride) {
         fprintf(stderr, "libamgb200: internal error: reduction grid %d exceeds partial buffer %d\n", grid, h->partial_stride);
         exit(71);
     }
-    LAUNCH((spmv_kernel<KIND, MODE, RED, EXACT>), grid, BLOCK, h->stream, A, x, y, b, alpha, h->d_partial);
+    if (KIND == 0 && A.max_row <= 8)
+        LAUNCH((spmv_kernel<KIND, MODE, RED, EXACT, true>), grid, BLOCK, h->stream, A, x, y, b, alpha, h->d_partial, item0, item1);
+    else
+        LAUNCH((spmv_kernel<KIND, MODE, RED, EXACT>), grid, BLOCK, h->stream, A, x, y, b, alpha, h->d_partial, item0, item1);
     if (RED != RED_NONE) LAUNCH(reduce_partials_kernel, 1, BLOCK, h->stream, h->d_partial, grid, h->partial_stride, 1, 0, h->d_scal);
 }
 template <int KIND, bool EXACT>
@@ -180,7 +186,11 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
             int first = 0;
             for (int p = 0; p < 2; ++p) {
                 const int cnt = lv.pass_items[p];
-                if (cnt > 0) LAUNCH((gs_pass_kernel<KIND, EXACT>), (cnt + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, BLOCK, h->stream, lv.A.v, lv.b, lv.x, first, first + cnt);
+                if (cnt > 0) {
+                    const int grid = (cnt + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+                    if (KIND == 0 && lv.A.v.max_row <= 8) LAUNCH((gs_pass_kernel<KIND, EXACT, true>), grid, BLOCK, h->stream, lv.A.v, lv.b, lv.x, first, first + cnt);
+                    else LAUNCH((gs_pass_kernel<KIND, EXACT>), grid, BLOCK, h->stream, lv.A.v, lv.b, lv.x, first, first + cnt);
+                }
                 first += cnt;
             }
         }
@@ -510,11 +520,11 @@ int coarse_solve(amgb200_hier *h, const DMat &A, const double *b, double *x, dou
 }
 
 // ---- V/W-cycle: amg/Solve/SSS_cycle.cu:848-967 ---------------------------------------------
-void cycle(amgb200_hier *h) {
+void cycle_from(amgb200_hier *h, int lstart) {
     const int nl = h->nl;
     int cycle_type = h->pars.cycle_type;
     double tol = h->pars.ctol;
-    int visits[64] = {0}, l = 0;
+    int visits[64] = {0}, l = lstart;
     if (tol > h->pars.tol) tol = h->pars.tol * 0.1;
     if (cycle_type <= 0) cycle_type = 1;
     for (;;) {
@@ -528,17 +538,19 @@ void cycle(amgb200_hier *h) {
             dev_zero(h, h->L[l].n, h->L[l].x);
         }
         { PhaseTimer pt(h, 4); coarse_solve(h, h->L[nl - 1].A.v, h->L[nl - 1].b, h->L[nl - 1].x, tol, nullptr); }
-        while (l > 0) {
+        while (l > lstart) {
             l--;
             Level &lv = h->L[l];
             { PhaseTimer pt(h, 3, l); spmv(h, lv.P.v, MODE_AMXPY, RED_NONE, h->L[l + 1].x, lv.x, nullptr, 1.0); }
             { PhaseTimer pt(h, 0, l); smooth(h, l, h->pars.post_iter); }
             if (visits[l] < cycle_type) break;
             visits[l] = 0;
+            if (l == lstart) break;
         }
-        if (l <= 0) break;
+        if (l <= lstart) break;
     }
 }
+void cycle(amgb200_hier *h) { cycle_from(h, 0); }
 
 void to_schedule(amgb200_hier *h, int l, const double *d_nat, double *d_sched) {
     LAUNCH(gather_kernel, grid_for(h->L[l].n), BLOCK, h->stream, h->L[l].n, h->L[l].d_order, d_nat, d_sched);
@@ -765,7 +777,7 @@ void amgb200_free(amgb200_hier *h) {
     cudaFree(h->d_partial); cudaFree(h->d_scal); cudaFreeHost(h->h_scal);
     cudaFree(h->d_xnat); cudaFree(h->d_bnat); cudaFree(h->kry);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
-    cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
@@ -1014,5 +1026,79 @@ double amgb200_time_op(amgb200_hier *h, int level, int op, int reps) {
     cudaEventDestroy(a); cudaEventDestroy(b);
     return ms / reps;
 }
+
+
+// ---- multi-GPU building blocks (amg_b200/distributed.py drives them; one process per GPU) ----
+void amgb200_set_stream(amgb200_hier *h, void *stream) {
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)stream;
+    h->own_stream = false;
+}
+void *amgb200_level_vec(amgb200_hier *h, int level, int which) {
+    check_level(h, level);
+    Level &lv = h->L[level];
+    return which == 0 ? (void *)lv.x : which == 1 ? (void *)lv.b : (void *)lv.wp;
+}
+void amgb200_level_order(const amgb200_hier *h, int level, int *order_host) {
+    check_level(h, level);
+    CUDA_CHECK(cudaMemcpy(order_host, h->L[level].d_order, (size_t)h->L[level].n * sizeof(int), cudaMemcpyDeviceToHost));
+}
+// info: [0] n, [1] rows in the F pass, [2] items (slices/rows) in the F pass, [3] items in the C pass,
+//       [4] layout kind of A, [5] 1 if both passes are fully parallel (shardable), [6] rows per item (32 | 1), [7] items of P
+void amgb200_l0_shape(const amgb200_hier *h, long long info[8]) {
+    const Level &lv = h->L[0];
+    info[0] = lv.n; info[1] = lv.pass_rows[0]; info[2] = lv.pass_items[0]; info[3] = lv.pass_items[1];
+    info[4] = lv.A.v.kind; info[5] = (lv.smoothed && !lv.ordered) ? 1 : 0; info[6] = lv.A.v.kind == KIND_SELL ? 32 : 1;
+    info[7] = lv.P.valid ? lv.P.v.nitems : 0;
+}
+// one Gauss-Seidel pass (0 = F, 1 = C) over the pass-relative item range [item0, item1) of level 0
+void amgb200_l0_gs_pass(amgb200_hier *h, int pass, int item0, int item1) {
+    Level &lv = h->L[0];
+    if (!lv.smoothed || lv.ordered) { fprintf(stderr, "libamgb200: level 0 is not two-colour; it cannot be sharded\n"); exit(73); }
+    const int base = pass ? lv.pass_items[0] : 0;
+    const int cnt = item1 - item0;
+    if (cnt <= 0) return;
+    const int grid = (cnt + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    if (lv.A.v.kind == KIND_SELL && lv.A.v.max_row <= 8) LAUNCH((gs_pass_kernel<0, true, true>), grid, BLOCK, h->stream, lv.A.v, lv.b, lv.x, base + item0, base + item1);
+    else if (lv.A.v.kind == KIND_SELL) LAUNCH((gs_pass_kernel<0, true>), grid, BLOCK, h->stream, lv.A.v, lv.b, lv.x, base + item0, base + item1);
+    else if (h->exact) LAUNCH((gs_pass_kernel<1, true>), grid, BLOCK, h->stream, lv.A.v, lv.b, lv.x, base + item0, base + item1);
+    else LAUNCH((gs_pass_kernel<1, false>), grid, BLOCK, h->stream, lv.A.v, lv.b, lv.x, base + item0, base + item1);
+}
+// wp = b - A x on the absolute item range [item0, item1) of level 0's smoother layout
+void amgb200_l0_residual(amgb200_hier *h, int item0, int item1) {
+    Level &lv = h->L[0];
+    if (item1 <= item0) return;
+    h->item0 = item0; h->item1 = item1;
+    spmv(h, lv.A.v, MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0);
+    h->item0 = h->item1 = -1;
+}
+// x_0 += P_0 x_1 on the item range [item0, item1) of P_0 (32 schedule rows per item for SELL)
+void amgb200_l0_prolong(amgb200_hier *h, int item0, int item1) {
+    Level &lv = h->L[0];
+    if (item1 <= item0) return;
+    h->item0 = item0; h->item1 = item1;
+    spmv(h, lv.P.v, MODE_AMXPY, RED_NONE, h->L[1].x, lv.x, nullptr, 1.0);
+    h->item0 = h->item1 = -1;
+}
+// b_{level+1} = R_level wp_level ; x_{level+1} = 0   (SSS_cycle.cu:921,929)
+void amgb200_restrict_from(amgb200_hier *h, int level) {
+    check_level(h, level);
+    Level &lv = h->L[level];
+    spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[level + 1].b, nullptr, 0.0);
+    dev_zero(h, h->L[level + 1].n, h->L[level + 1].x);
+}
+// the cycle on levels >= level (b_level and x_level already set), V-cycle only when level > 0
+void amgb200_cycle_from(amgb200_hier *h, int level) {
+    check_level(h, level);
+    if (level == h->nl - 1) {
+        double tol = h->pars.ctol;
+        if (tol > h->pars.tol) tol = h->pars.tol * 0.1;
+        coarse_solve(h, h->L[level].A.v, h->L[level].b, h->L[level].x, tol, nullptr);
+    } else cycle_from(h, level);
+}
+void amgb200_vec_to_schedule(amgb200_hier *h, int level, const double *d_nat, double *d_sched) { check_level(h, level); to_schedule(h, level, d_nat, d_sched); }
+void amgb200_vec_to_natural(amgb200_hier *h, int level, const double *d_sched, double *d_nat) { check_level(h, level); to_natural(h, level, d_sched, d_nat); }
+void amgb200_sync(amgb200_hier *h) { CUDA_CHECK(cudaStreamSynchronize(h->stream)); }
 
 }  // extern "C"

@@ -22,7 +22,7 @@
 namespace amgb200 {
 
 struct DMat {                      // device view of a DevLayout
-    int kind, nrows, ncols, nitems;
+    int kind, nrows, ncols, nitems, max_row;
     const int *slice_row;          // SELL
     const long long *slice_ptr;    // SELL
     const int *rptr;               // CSR
@@ -122,6 +122,33 @@ struct SellItem {
 
 // Gauss-Seidel row update (amg/Solve/SSS_smooth.c:18-33): t = b_i - sum_{j != i} a_ij x_j in storage
 // order; x_i = t / a_ii when |a_ii| > 1e-20
+// rows no longer than one chunk (max row length <= SCH, e.g. level 0 of the 5-/7-point problems): no loop,
+// no next-chunk registers -> ~40 registers, 6 blocks/SM for the HBM-bound kernels
+template <bool COH, int SCH>
+__device__ __forceinline__ void gs_finish_sell_one(SellItem<SCH> &it, double *x) {
+    double t = it.bk, d = 0.0;
+    double xv[SCH];
+#pragma unroll
+    for (int u = 0; u < SCH; ++u) xv[u] = (it.j[u] >= 0 && it.j[u] != it.k) ? ld_x<COH>(x + it.j[u]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < SCH; ++u) {
+        if (it.j[u] == it.k) d = it.a[u];
+        else if (it.j[u] >= 0) t = __dsub_rn(t, __dmul_rn(it.a[u], xv[u]));
+    }
+    if (it.k < it.r1 && fabs(d) > GS_TINY) x[it.k] = __ddiv_rn(t, d);
+}
+template <int SCH>
+__device__ __forceinline__ double spmv_finish_sell_one(SellItem<SCH> &it, const double *__restrict__ x) {
+    double t = 0.0;
+    double xv[SCH];
+#pragma unroll
+    for (int u = 0; u < SCH; ++u) xv[u] = it.j[u] >= 0 ? x[it.j[u]] : 0.0;
+#pragma unroll
+    for (int u = 0; u < SCH; ++u)
+        if (it.j[u] >= 0) t = __dadd_rn(t, __dmul_rn(it.a[u], xv[u]));
+    return t;
+}
+
 template <bool COH, int SCH>
 __device__ __forceinline__ void gs_finish_sell(SellItem<SCH> &it, double *x) {
     const bool active = it.k < it.r1;
@@ -352,7 +379,7 @@ __device__ __forceinline__ void gs_finish_csr(const DMat &A, CsrItem &it, double
 // Gauss-Seidel kernels
 // ------------------------------------------------------------------------------------------
 // one fully parallel pass (a pass whose dependency DAG has depth 1): items [item0, item1)
-template <int KIND, bool EXACT>
+template <int KIND, bool EXACT, bool ONE = false>
 __global__ void __launch_bounds__(BLOCK) gs_pass_kernel(DMat A, const double *__restrict__ b, double *x, int item0, int item1) {
     __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * STAGE : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -361,7 +388,7 @@ __global__ void __launch_bounds__(BLOCK) gs_pass_kernel(DMat A, const double *__
     if constexpr (KIND == 0) {
         SellItem<8> w;
         w.prologue(A, it, lane, b);
-        gs_finish_sell<false>(w, x);
+        if constexpr (ONE) gs_finish_sell_one<false>(w, x); else gs_finish_sell<false>(w, x);
     } else {
         CsrItem w;
         w.prologue(A, it, lane, b);
@@ -589,19 +616,19 @@ __device__ __forceinline__ double spmv_store(double t, double alpha, const doubl
     return out;
 }
 
-template <int KIND, int MODE, int RED, bool EXACT>
+template <int KIND, int MODE, int RED, bool EXACT, bool ONE = false>
 __global__ void __launch_bounds__(BLOCK) spmv_kernel(DMat A, const double *__restrict__ x, double *y, const double *__restrict__ b,
-                                                     double alpha, double *partial) {
+                                                     double alpha, double *partial, int item0, int item1) {
     __shared__ double red[32];
     __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * STAGE : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int it = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int it = item0 + blockIdx.x * WARPS_PER_BLOCK + warp;
     double contrib = 0.0;
-    if (it < A.nitems) {
+    if (it < item1) {
         if constexpr (KIND == 0) {
             SellItem<8> w;
             w.prologue(A, it, lane);
-            const double t = spmv_finish_sell(w, x);
+            const double t = ONE ? spmv_finish_sell_one(w, x) : spmv_finish_sell(w, x);
             if (w.k < w.r1) {
                 const double out = spmv_store<MODE>(t, alpha, b, y, w.k);
                 if (RED == RED_SUMSQ) contrib = __dmul_rn(out, out);

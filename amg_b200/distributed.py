@@ -1,0 +1,291 @@
+"""Multi-GPU driver of the solve phase: one process per GPU, torch.distributed for the plumbing.
+
+What shards (DESIGN.md "Multi-GPU"): under the reference's row-order Gauss-Seidel only a level whose
+F pass and C pass are each ONE wavefront (level 0 of the 5-/7-point problems: an exact red/black split)
+can be partitioned without a cross-device dependency chain.  Every rank holds the resident hierarchy
+(HBM is not the constraint: 256^3 needs ~9 of 180 GB); on level 0 each rank runs the Gauss-Seidel
+passes, the residual and the prolongation on its own row block and refreshes the ghost x entries it
+reads from their owners (point-to-point halo exchange, no collective on the data path except the
+residual gather to rank 0 and the broadcast of the coarse correction).  Levels >= 1 are a single
+dependency chain per sweep and run on rank 0 ("agglomerated").  The arithmetic of every row is the same
+as on one GPU, so the iterates are bit-identical to the single-GPU (and the reference's CPU) iterates.
+
+The driver is backend-agnostic: GpuBackend calls libamgb200.so; tests/test_sharded_gloo.py plugs in a CPU
+emulation built on the oracle to check partitioning, ghost lists and the exchange schedule with gloo.
+"""
+import numpy as np
+
+
+def split_even(nitems, parts):
+    """parts contiguous item ranges of (nearly) equal size"""
+    cuts = [(nitems * p) // parts for p in range(parts + 1)]
+    return [(cuts[p], cuts[p + 1]) for p in range(parts)]
+
+
+class Partition:
+    """Ownership of level-0 rows in schedule numbering: rank p owns the F rows of F items
+    [fi[p], fi[p+1]) and the C rows of C items [ci[p], ci[p+1]) (an item = rows_per_item rows)."""
+
+    def __init__(self, n, nF, itemsF, itemsC, rows_per_item, world):
+        self.n, self.nF, self.rpi, self.world = n, nF, rows_per_item, world
+        self.f_items = split_even(itemsF, world)
+        self.c_items = split_even(itemsC, world)
+        # schedule-row ranges per rank and pass
+        self.f_rows = [(min(a * rows_per_item, nF), min(b * rows_per_item, nF)) for a, b in self.f_items]
+        self.c_rows = [(min(nF + a * rows_per_item, n), min(nF + b * rows_per_item, n)) for a, b in self.c_items]
+        self.f_bounds = np.array([r[0] for r in self.f_rows] + [nF])
+        self.c_bounds = np.array([r[0] for r in self.c_rows] + [n])
+
+    def owner(self, k):
+        """owning rank of schedule rows k (array)"""
+        k = np.asarray(k)
+        own = np.empty(k.shape, np.int64)
+        isF = k < self.nF
+        own[isF] = np.searchsorted(self.f_bounds, k[isF], side="right") - 1
+        own[~isF] = np.searchsorted(self.c_bounds, k[~isF], side="right") - 1
+        return np.clip(own, 0, self.world - 1)
+
+    def rows(self, rank, which):
+        a, b = (self.f_rows if which == 0 else self.c_rows)[rank]
+        return np.arange(a, b)
+
+
+def ghost_lists(A_nat, order, part, rank):
+    """For `rank`: ghosts[p][src] = schedule indices of pass-p x entries owned by `src` that this rank's
+    rows of the OTHER pass (and, for the residual, of both passes) read.  Symmetric send lists follow by
+    evaluating the same function for the peer, which every rank does locally (the matrix is replicated)."""
+    n = part.n
+    pos = np.empty(n, np.int64)
+    pos[order] = np.arange(n)
+    out = {}
+    for which in (0, 1):                      # ghost entries belonging to pass `which`
+        reader_rows = np.concatenate([part.rows(rank, 0), part.rows(rank, 1)])
+        nat = order[reader_rows]
+        starts, ends = A_nat.row_ptr[nat], A_nat.row_ptr[nat + 1]
+        idx = np.concatenate([np.arange(s, e) for s, e in zip(starts, ends)]) if len(nat) else np.zeros(0, np.int64)
+        cols = np.unique(pos[A_nat.col_idx[idx]])
+        cols = cols[(cols < part.nF) if which == 0 else (cols >= part.nF)]
+        own = part.owner(cols)
+        out[which] = {src: cols[own == src] for src in range(part.world) if src != rank and (own == src).any()}
+    return out
+
+
+class ShardedSolver:
+    """V-cycle solve with level 0 sharded over `world` ranks (see module docstring).
+
+    backend interface (all vectors in level-0 schedule numbering):
+      shape() -> dict(n, nF, itemsF, itemsC, rows_per_item, p_items, shardable)
+      order() -> schedule->natural permutation of level 0
+      gs_pass(which, item0, item1); residual(item0, item1); prolong(item0, item1)
+      x0(), wp0(), x1()            -> writable 1-D torch tensors aliasing the level vectors
+      restrict_and_lower_levels()  -> b1 = R wp0, x1 = 0, V-cycle on levels >= 1   (rank 0)
+      set_problem(x_nat, b_nat), get_solution() ; sumsq(tensor) -> float
+    """
+
+    def __init__(self, backend, A_nat, dist, rank, world, pre=2, post=2):
+        import torch
+        self.torch, self.dist, self.be, self.rank, self.world = torch, dist, backend, rank, world
+        sh = backend.shape()
+        if not sh["shardable"]:
+            raise ValueError("level 0 is not two-colour: the path does not shard (run replicas instead)")
+        self.sh = sh
+        self.part = Partition(sh["n"], sh["nF"], sh["itemsF"], sh["itemsC"], sh["rows_per_item"], world)
+        self.pre, self.post = pre, post
+        order = backend.order()
+        # what I need from each peer, and (same function evaluated for the peer) what each peer needs from me
+        mine = ghost_lists(A_nat, order, self.part, rank)
+        self.recv_idx = {w: {src: torch.as_tensor(v, dtype=torch.long, device=backend.device) for src, v in mine[w].items()} for w in (0, 1)}
+        self.send_idx = {0: {}, 1: {}}
+        for peer in range(world):
+            if peer == rank:
+                continue
+            theirs = ghost_lists(A_nat, order, self.part, peer)
+            for w in (0, 1):
+                if rank in theirs[w]:
+                    self.send_idx[w][peer] = torch.as_tensor(theirs[w][rank], dtype=torch.long, device=backend.device)
+        self.halo_bytes = sum(8 * len(v) for w in (0, 1) for v in self.recv_idx[w].values())
+        # prolongation item ranges (P's items are 32-row groups counted from schedule row 0) covering my rows;
+        # at the seams an item may also touch rows of a neighbour: those are ghosts here, refreshed before use
+        rpi = sh["rows_per_item"]
+        self.p_ranges = []
+        for a, b in (self.part.f_rows[rank], self.part.c_rows[rank]):
+            if b > a:
+                lo, hi = a // rpi, min(sh["p_items"], -(-b // rpi))
+                if self.p_ranges and lo < self.p_ranges[-1][1]:   # never run an item twice on one rank
+                    lo = self.p_ranges[-1][1]
+                if hi > lo:
+                    self.p_ranges.append((lo, hi))
+
+    # ---- communication -------------------------------------------------------------------------
+    def exchange(self, which):
+        """refresh my ghost copies of pass-`which` x entries from their owners (point-to-point)"""
+        if self.world == 1:
+            return
+        torch, dist = self.torch, self.dist
+        x = self.be.x0()
+        ops, recv_bufs = [], []
+        for peer, idx in self.send_idx[which].items():
+            ops.append(dist.P2POp(dist.isend, x.index_select(0, idx).contiguous(), peer))
+        for peer, idx in self.recv_idx[which].items():
+            buf = torch.empty(len(idx), dtype=x.dtype, device=x.device)
+            recv_bufs.append((idx, buf))
+            ops.append(dist.P2POp(dist.irecv, buf, peer))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for idx, buf in recv_bufs:
+            x.index_copy_(0, idx, buf)
+
+    def gather_residual(self):
+        """own rows of wp0 -> rank 0 (the restriction needs the whole fine residual)"""
+        if self.world == 1:
+            return
+        torch, dist = self.torch, self.dist
+        wp = self.be.wp0()
+        ops = []
+        if self.rank == 0:
+            for peer in range(1, self.world):
+                for a, b in (self.part.f_rows[peer], self.part.c_rows[peer]):
+                    if b > a:
+                        ops.append(dist.P2POp(dist.irecv, wp[a:b], peer))
+        else:
+            for a, b in (self.part.f_rows[self.rank], self.part.c_rows[self.rank]):
+                if b > a:
+                    ops.append(dist.P2POp(dist.isend, wp[a:b].contiguous(), 0))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    # ---- one V-cycle ----------------------------------------------------------------------------
+    def smooth(self, sweeps):
+        fa, fb = self.part.f_items[self.rank]
+        ca, cb = self.part.c_items[self.rank]
+        for _ in range(sweeps):
+            self.exchange(1)                 # F rows read C neighbours
+            self.be.gs_pass(0, fa, fb)
+            self.exchange(0)                 # C rows read F neighbours
+            self.be.gs_pass(1, ca, cb)
+
+    def residual_own(self):
+        self.exchange(1)                     # F values are current since the last C pass; C values changed
+        self.exchange(0)
+        fa, fb = self.part.f_items[self.rank]
+        ca, cb = self.part.c_items[self.rank]
+        self.be.residual(fa, fb)
+        self.be.residual(self.sh["itemsF"] + ca, self.sh["itemsF"] + cb)
+
+    def cycle(self):
+        self.smooth(self.pre)
+        self.residual_own()
+        self.gather_residual()
+        if self.rank == 0:
+            self.be.restrict_and_lower_levels()
+        if self.world > 1:
+            self.dist.broadcast(self.be.x1(), src=0)      # coarse correction to every rank
+        for a, b in self.p_ranges:                        # own rows (+ partial items at the seams)
+            self.be.prolong(a, b)
+        self.smooth(self.post)
+
+    def residual_norm(self):
+        self.residual_own()
+        wp = self.be.wp0()
+        s = self.torch.zeros(1, dtype=wp.dtype, device=wp.device)
+        for a, b in (self.part.f_rows[self.rank], self.part.c_rows[self.rank]):
+            if b > a:
+                s += (wp[a:b] * wp[a:b]).sum()
+        if self.world > 1:
+            self.dist.all_reduce(s)
+        return float(s.sqrt().item())
+
+    def collect_solution(self):
+        """owners -> rank 0 (level-0 x in schedule numbering)"""
+        if self.world == 1:
+            return
+        dist = self.dist
+        x = self.be.x0()
+        ops = []
+        if self.rank == 0:
+            for peer in range(1, self.world):
+                for a, b in (self.part.f_rows[peer], self.part.c_rows[peer]):
+                    if b > a:
+                        ops.append(dist.P2POp(dist.irecv, x[a:b], peer))
+        else:
+            for a, b in (self.part.f_rows[self.rank], self.part.c_rows[self.rank]):
+                if b > a:
+                    ops.append(dist.P2POp(dist.isend, x[a:b].contiguous(), 0))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def solve(self, x_nat, b_nat, tol, max_it=100):
+        """outer iteration of SSS_amg_solve (Solve/SSS_SOLVE.c:53-80); returns (nits, history, x on rank 0)"""
+        self.be.set_problem(x_nat, b_nat)
+        sumb = float(np.sqrt(np.sum(np.asarray(b_nat, dtype=np.float64) ** 2)))
+        hist = []
+        for it in range(1, max_it + 1):
+            self.cycle()
+            absres = self.residual_norm()
+            hist.append(absres)
+            if absres / sumb < tol:
+                break
+        self.collect_solution()
+        return len(hist), np.array(hist), (self.be.get_solution() if self.rank == 0 else None)
+
+
+class _CudaArray:
+    """zero-copy torch view of a device pointer owned by libamgb200 (via __cuda_array_interface__)"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class GpuBackend:
+    """libamgb200.so building blocks (include/amg_b200.h section 2b) on this rank's GPU"""
+
+    def __init__(self, dev, torch):
+        import ctypes as C
+        from . import capi
+        self.C, self.capi, self.torch, self.dev = C, capi, torch, dev
+        self.L = capi.lib()
+        self.h = dev.h
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.L.amgb200_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        info = (C.c_longlong * 8)()
+        self.L.amgb200_l0_shape(self.h, info)
+        self._shape = {"n": info[0], "nF": info[1], "itemsF": info[2], "itemsC": info[3], "rows_per_item": info[6],
+                       "p_items": info[7], "shardable": bool(info[5]) and dev.num_levels >= 2}
+        n0, n1 = info[0], dev.info(1)["rows"] if dev.num_levels > 1 else 0
+        self._x0 = torch.as_tensor(_CudaArray(self.L.amgb200_level_vec(self.h, 0, 0), n0), device=self.device)
+        self._b0 = torch.as_tensor(_CudaArray(self.L.amgb200_level_vec(self.h, 0, 1), n0), device=self.device)
+        self._wp0 = torch.as_tensor(_CudaArray(self.L.amgb200_level_vec(self.h, 0, 2), n0), device=self.device)
+        self._x1 = torch.as_tensor(_CudaArray(self.L.amgb200_level_vec(self.h, 1, 0), n1), device=self.device) if n1 else None
+        self._nat = torch.empty(n0, dtype=torch.float64, device=self.device)
+
+    def shape(self):
+        return self._shape
+
+    def order(self):
+        o = np.zeros(self._shape["n"], np.int32)
+        self.L.amgb200_level_order(self.h, 0, self.capi.iptr(o))
+        return o.astype(np.int64)
+
+    def x0(self): return self._x0
+    def wp0(self): return self._wp0
+    def x1(self): return self._x1
+    def gs_pass(self, which, a, b): self.L.amgb200_l0_gs_pass(self.h, which, a, b)
+    def residual(self, a, b): self.L.amgb200_l0_residual(self.h, a, b)
+    def prolong(self, a, b): self.L.amgb200_l0_prolong(self.h, a, b)
+
+    def restrict_and_lower_levels(self):
+        self.L.amgb200_restrict_from(self.h, 0)
+        self.L.amgb200_cycle_from(self.h, 1)
+
+    def set_problem(self, x_nat, b_nat):
+        t = self.torch
+        for src, dst in ((x_nat, self._x0), (b_nat, self._b0)):
+            self._nat.copy_(t.as_tensor(np.asarray(src, dtype=np.float64)))
+            self.L.amgb200_vec_to_schedule(self.h, 0, self.C.c_void_p(self._nat.data_ptr()), self.C.c_void_p(dst.data_ptr()))
+
+    def get_solution(self):
+        self.L.amgb200_vec_to_natural(self.h, 0, self.C.c_void_p(self._x0.data_ptr()), self.C.c_void_p(self._nat.data_ptr()))
+        return self._nat.cpu().numpy()

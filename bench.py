@@ -195,24 +195,59 @@ def main():
 
     launches0 = capi.lib().amgb200_launch_count()
     sampler = ClockSampler(local_rank)
+    sharded = None
     if dist:
+        # N > 1: level 0 row-block sharded over the ranks with halo exchange, levels >= 1 on rank 0
+        from amg_b200.distributed import GpuBackend, ShardedSolver
+        be = GpuBackend(dev, torch)
+        if not be.shape()["shardable"]:
+            raise SystemExit("bench.py: level 0 of this workload is not two-colour; the path does not shard (run --gpus 1)")
+        sharded = ShardedSolver(be, A, dist, rank, world, hier.pars.pre_iter, hier.pars.post_iter)
+        ones = np.ones(n)
+        for _ in range(args.warmup):
+            nits, hist, _x = sharded.solve(ones, ones, TOL)
         dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    ms_total, rtn = dev.bench_solve(x0.data_ptr(), b.data_ptr(), x.data_ptr(), args.warmup, args.steps)
-    torch.cuda.synchronize()
-    if dist:
+        torch.cuda.synchronize()
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            nits, hist, _x = sharded.solve(ones, ones, TOL)
+        ev1.record()
+        torch.cuda.synchronize()
         dist.barrier()
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
+        rtn = capi.Rtn(float(hist[-1]), float(hist[-1]) / float(np.sqrt(n)), int(nits))
+    else:
+        torch.cuda.synchronize()
+        sampler.start()
+        ms_total, rtn = dev.bench_solve(x0.data_ptr(), b.data_ptr(), x.data_ptr(), args.warmup, args.steps)
+        torch.cuda.synchronize()
     clocks = sampler.stop()
     launches = capi.lib().amgb200_launch_count() - launches0
     launches_per_step = launches / (args.warmup + args.steps)
     ms_step = ms_total / args.steps
-    if rank != 0:
-        if dist:
-            dist.destroy_process_group()
+    if dist:                                   # the sharded run is reported as is (no single-GPU extras)
+        if rank == 0:
+            hbm, hbm_src = load_peaks()
+            vb = dev.bytes(0, 5)
+            line = {"metric": METRIC, "value": ms_step, "unit": "ms", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                    "data": "synthetic",
+                    "config": dict(config, parallelism=f"level 0 row-block sharded over {world} GPUs with point-to-point halo exchange (NCCL); "
+                                                       f"levels >= 1 (one dependency chain per sweep) on rank 0",
+                                   arithmetic="EXACT (bit-identical to the reference CPU path)"),
+                    "vcycles": rtn.nits, "relres": rtn.rres, "ares": rtn.ares, "ms_per_vcycle": ms_step / max(1, rtn.nits),
+                    "vcycle_algorithmic_gb": vb / 1e9, "vcycle_gbs": vb * rtn.nits / ms_step / 1e6,
+                    "halo_bytes_per_exchange_per_rank": sharded.halo_bytes, "clocks": clocks,
+                    "e2e": {"value": ms_step, "unit": "ms", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n,
+                            "note": "x0/b copied from host and x gathered to rank 0 and copied back inside every step"},
+                    "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
+                    "roofline": None, "cpu_baseline": None}
+            print(json.dumps(line))
+        dist.destroy_process_group()
         return 0
 
     # ---- one profiled solve: per-level kernel shares (adds syncs; not part of the timed number)

@@ -203,6 +203,23 @@ void amgb200_bench_solve(amgb200_hier *h, const double *d_x0, const double *d_b,
                          double *ms_total, amgb200_rtn *last);
 const char *amgb200_version(void);
 
+/* ---- 2b. multi-GPU building blocks (one process per GPU; driven by amg_b200/distributed.py) -------
+ * Only level 0 of two-colour problems shards without a cross-device dependency chain:
+ * every rank holds the resident hierarchy, runs the level-0 kernels on its own item range and exchanges
+ * ghost x entries; rank 0 runs the levels below.  All ranges are item ranges of the level-0 layouts. */
+void amgb200_set_stream(amgb200_hier *h, void *cuda_stream);            /* run on the caller's stream */
+void *amgb200_level_vec(amgb200_hier *h, int level, int which);         /* device ptr: 0 x, 1 b, 2 wp (schedule numbering) */
+void amgb200_level_order(const amgb200_hier *h, int level, int *order_host);   /* schedule position -> natural row */
+void amgb200_l0_shape(const amgb200_hier *h, long long info[8]);
+void amgb200_l0_gs_pass(amgb200_hier *h, int pass, int item0, int item1);
+void amgb200_l0_residual(amgb200_hier *h, int item0, int item1);
+void amgb200_l0_prolong(amgb200_hier *h, int item0, int item1);
+void amgb200_restrict_from(amgb200_hier *h, int level);
+void amgb200_cycle_from(amgb200_hier *h, int level);
+void amgb200_vec_to_schedule(amgb200_hier *h, int level, const double *d_nat, double *d_sched);
+void amgb200_vec_to_natural(amgb200_hier *h, int level, const double *d_sched, double *d_nat);
+void amgb200_sync(amgb200_hier *h);
+
 /* ---- 3. host-side helpers (pure C++, no device): synthetic operators + RS setup ---------- */
 /* Synthetic level-0 operators of SURVEY.md Appendix B, CSR with ascending columns:
  *   kind 0 = p2d N (5-point), 1 = p3d N (7-point), 2 = aniso3d N (1,1,eps_z), 3 = v27 N
