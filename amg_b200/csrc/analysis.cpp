@@ -107,7 +107,24 @@ void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos
                 L.val[w] = M.val[q];
             }
         }
-        if (breaks) L.wf_item_ptr = *breaks;
+        if (breaks) {
+            L.wf_item_ptr = *breaks;
+            // wavefront of every schedule row, then the prefix/suffix split of every row
+            const int W = (int)breaks->size() - 1;
+            std::vector<int> wf_of((size_t)n);
+            for (int w = 0; w < W; ++w) for (int k = (*breaks)[w]; k < (*breaks)[w + 1]; ++k) wf_of[k] = w;
+            L.split.resize((size_t)n);
+#pragma omp parallel for schedule(static)
+            for (int k = 0; k < n; ++k) {
+                const int prev = wf_of[k] == 0 ? W - 1 : wf_of[k] - 1;
+                int sp = L.rptr[k + 1] - L.rptr[k];
+                for (int q = L.rptr[k]; q < L.rptr[k + 1]; ++q) {
+                    const int c = L.col[q];
+                    if (c != k && c < n && wf_of[c] == prev) { sp = q - L.rptr[k]; break; }
+                }
+                L.split[k] = sp;
+            }
+        }
         return;
     }
 

@@ -62,16 +62,16 @@ struct DevMatOwner {
     bool valid = false;
     void upload(const DevLayout &L) {
         v.kind = L.kind; v.nrows = L.nrows; v.ncols = L.ncols; v.nitems = L.nitems(); v.max_row = L.max_row;
-        v.slice_row = nullptr; v.slice_ptr = nullptr; v.rptr = nullptr;
+        v.slice_row = nullptr; v.slice_ptr = nullptr; v.rptr = nullptr; v.split = nullptr;
         if (L.kind == KIND_SELL) { v.slice_row = dev_upload(L.slice_row); v.slice_ptr = dev_upload(L.slice_ptr); }
-        else v.rptr = dev_upload(L.rptr);
+        else { v.rptr = dev_upload(L.rptr); if (!L.split.empty()) v.split = dev_upload(L.split); }
         v.col = dev_upload(L.col);
         v.val = dev_upload(L.val);
         nnz = L.nnz; padded = (long long)L.col.size(); max_row = L.max_row; valid = true;
     }
     void release() {
         if (!valid) return;
-        cudaFree((void *)v.slice_row); cudaFree((void *)v.slice_ptr); cudaFree((void *)v.rptr);
+        cudaFree((void *)v.slice_row); cudaFree((void *)v.slice_ptr); cudaFree((void *)v.rptr); cudaFree((void *)v.split);
         cudaFree((void *)v.col); cudaFree((void *)v.val);
         valid = false;
     }
@@ -729,6 +729,9 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                 lv.cta_G = G;
                 lv.cta_D = std::max(2, maxw / G);
                 if (getenv("AMGB200_CTA_D")) lv.cta_D = std::max(2, std::min(maxw / G, atoi(getenv("AMGB200_CTA_D"))));
+                // the prefix/suffix scheme of the warp-per-row EXACT kernel folds a row's prefix while exactly ONE earlier
+                // wavefront is still in flight: two alternating groups
+                if (lay.kind == KIND_CSR && h->exact) lv.cta_D = 2;
                 const size_t needb = (size_t)((lv.n + 1) & ~1) * 8 + (size_t)lv.cta_G * lv.cta_D * STAGE * 8;
                 lv.x_in_smem = lv.strategy == 2 && needb <= (size_t)h->max_dyn_smem && !(getenv("AMGB200_NO_SMEM_X") && atoi(getenv("AMGB200_NO_SMEM_X")));
             }

@@ -26,6 +26,7 @@ struct DMat {                      // device view of a DevLayout
     const int *slice_row;          // SELL
     const long long *slice_ptr;    // SELL
     const int *rptr;               // CSR
+    const int *split;              // CSR, ordered levels: per row, index of the first entry that reads the previous wavefront (or NULL)
     const int *col;
     const double *val;
 };
@@ -221,30 +222,34 @@ __device__ __forceinline__ double spmv_finish_sell(SellItem<SCH> &it, const doub
 constexpr int SUPER = 128;
 constexpr int STAGE = SUPER + 16;   // per-warp product staging area (the chain reads up to 16 slots ahead)
 struct CsrItem {
-    int k, p0, p1;
-    int j[4], j1[4];           // super chunk 0 and 1
+    int k, p0, p1, ps;         // row, its entry range, and the first entry that reads the previous wavefront (p0 <= ps <= p1)
+    int pb, pe;                // range currently being streamed
+    int j[4], j1[4];           // super chunks 0 and 1 of that range
     double a[4], a1[4];
-    double bk;
-#ifdef AMGB200_TIMING
-    long long tg = 0, tp = 0, tc = 0, te = 0;
-#endif
+    double bk, dl;             // right-hand side; diagonal entry if this lane has seen it
     __device__ __forceinline__ void load_super(const DMat &A, int base, int lane, int (&jj)[4], double (&aa)[4]) const {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int p = base + u * 32 + lane;
-            if (p < p1) { jj[u] = A.col[p]; aa[u] = A.val[p]; } else { jj[u] = -1; aa[u] = 0.0; }
+            if (p < pe) { jj[u] = A.col[p]; aa[u] = A.val[p]; } else { jj[u] = -1; aa[u] = 0.0; }
         }
     }
-    struct Desc { int row, p0, p1; };
+    struct Desc { int row, p0, p1, ps; };
     __device__ __forceinline__ static Desc load_desc(const DMat &A, int row) {
         Desc d;
         d.row = row; d.p0 = A.rptr[row]; d.p1 = A.rptr[row + 1];
+        d.ps = A.split ? d.p0 + A.split[row] : d.p0;
         return d;
     }
-    __device__ __forceinline__ void load_entries(const DMat &A, const Desc &d, int lane, const double *__restrict__ b) {
-        k = d.row; p0 = d.p0; p1 = d.p1;
-        load_super(A, p0, lane, j, a);
-        load_super(A, p0 + SUPER, lane, j1, a1);
+    // start streaming the entries [beg, end): the first two super chunks of col/val
+    __device__ __forceinline__ void begin_range(const DMat &A, int beg, int end, int lane) {
+        pb = beg; pe = end;
+        load_super(A, beg, lane, j, a);
+        load_super(A, beg + SUPER, lane, j1, a1);
+    }
+    __device__ __forceinline__ void load_entries(const DMat &A, const Desc &d, int lane, const double *__restrict__ b, bool prefix_only = false) {
+        k = d.row; p0 = d.p0; p1 = d.p1; ps = d.ps; dl = 0.0;
+        begin_range(A, p0, prefix_only ? ps : p1, lane);
         bk = b ? b[d.row] : 0.0;
     }
     __device__ __forceinline__ void prologue(const DMat &A, int row, int lane, const double *__restrict__ b) {
@@ -252,30 +257,57 @@ struct CsrItem {
     }
 };
 
-// EXACT in-order accumulation.  GS: t starts at b_k, products are subtracted, the diagonal entry is
-// skipped and returned through d.  Otherwise t starts at 0 and products are added.  Padding and the
-// skipped diagonal contribute +0.0, which leaves t bit-unchanged.  Result valid in all lanes.
+// fold `cnt` staged products into t in order: 8-term blocks, ping-pong registers; the LDS.128 of the next
+// block are issued before the chain of the current one, and the __syncwarp between them keeps ptxas from
+// sinking the loads next to their uses (which would expose ~30 cycles of shared-memory latency every few
+// terms).  Four blocks per loop trip: one taken branch per 32 terms.  Slots >= cnt hold +0.0 (exact no-ops);
+// reads run up to 16 slots past the staged chunk (STAGE pad).
+template <bool GS>
+__device__ __forceinline__ double chain_fold(double t, const double2 *sp2, int cnt) {
+#define AMGB200_FOLD(v)                                                        \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                            \
+        if (GS) { t = __dsub_rn(t, v[u].x); t = __dsub_rn(t, v[u].y); }        \
+        else { t = __dadd_rn(t, v[u].x); t = __dadd_rn(t, v[u].y); }           \
+    }
+#define AMGB200_LOAD(v, q)                                                     \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) v[u] = sp2[((q) >> 1) + u];  \
+    __syncwarp();
+    double2 va[4], vb[4];
+    int q = 0;
+    AMGB200_LOAD(va, 0)
+#pragma unroll 1
+    for (; q + 32 <= cnt; q += 32) {
+        AMGB200_LOAD(vb, q + 8)  AMGB200_FOLD(va)
+        AMGB200_LOAD(va, q + 16) AMGB200_FOLD(vb)
+        AMGB200_LOAD(vb, q + 24) AMGB200_FOLD(va)
+        AMGB200_LOAD(va, q + 32) AMGB200_FOLD(vb)
+    }
+#pragma unroll 1
+    for (; q < cnt; q += 8) {
+        AMGB200_LOAD(vb, q + 8)  AMGB200_FOLD(va)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) va[u] = vb[u];
+    }
+#undef AMGB200_FOLD
+#undef AMGB200_LOAD
+    return t;
+}
+
+// EXACT in-order accumulation over the range begun with begin_range().  GS: products are subtracted and the
+// diagonal entry is skipped (remembered in it.dl); otherwise products are added.  Padding and the skipped
+// diagonal contribute +0.0, which leaves t bit-unchanged.  Result valid in all lanes.
 template <bool COH, bool GS>
-__device__ __forceinline__ double csr_row_exact(const DMat &A, CsrItem &it, const double *x, double t, double &d, int lane, double *sprod) {
-    double dl = 0.0;
+__device__ __forceinline__ double csr_chain_run(const DMat &A, CsrItem &it, const double *x, double t, int lane, double *sprod) {
+    if (it.pb >= it.pe) return t;
     double xc[4];
-#ifdef AMGB200_TIMING
-    long long k0 = clock64();
-#endif
 #pragma unroll
     for (int u = 0; u < 4; ++u) xc[u] = (it.j[u] >= 0 && !(GS && it.j[u] == it.k)) ? ld_x<COH>(x + it.j[u]) : 0.0;
-#ifdef AMGB200_TIMING
-    { double sink = xc[0] + xc[1] + xc[2] + xc[3]; if (sink == 1.2345e300) it.k = -1; long long k1 = clock64(); it.tg += k1 - k0; }
-#endif
-    for (int base = it.p0; base < it.p1; base += SUPER) {
-#ifdef AMGB200_TIMING
-        long long k2 = clock64();
-#endif
+    for (int base = it.pb; base < it.pe; base += SUPER) {
         // stage 1: col/val of super chunk s+2 ; stage 2: x gather of s+1 (its col arrived an iteration ago)
         int jn[4];
         double an[4], xn[4];
-        const bool more = base + SUPER < it.p1;
-        if (base + 2 * SUPER < it.p1) it.load_super(A, base + 2 * SUPER, lane, jn, an);
+        const bool more = base + SUPER < it.pe;
+        if (base + 2 * SUPER < it.pe) it.load_super(A, base + 2 * SUPER, lane, jn, an);
         else {
 #pragma unroll
             for (int u = 0; u < 4; ++u) { jn[u] = -1; an[u] = 0.0; }
@@ -289,62 +321,29 @@ __device__ __forceinline__ double csr_row_exact(const DMat &A, CsrItem &it, cons
         for (int u = 0; u < 4; ++u) {
             double prod = 0.0;
             if (it.j[u] >= 0) {
-                if (GS && it.j[u] == it.k) dl = it.a[u];
+                if (GS && it.j[u] == it.k) it.dl = it.a[u];
                 else prod = __dmul_rn(it.a[u], xc[u]);
             }
             sprod[u * 32 + lane] = prod;
         }
         __syncwarp();
-#ifdef AMGB200_TIMING
-        long long k3 = clock64(); it.tp += k3 - k2;
-#endif
-        const int cnt = min(SUPER, it.p1 - base);
-        const double2 *sp2 = reinterpret_cast<const double2 *>(sprod);
-        // 8-term half blocks, ping-pong: the LDS.128 of the next half block are issued before the chain
-        // of the current one.  The __syncwarp between them keeps ptxas from sinking the loads next to
-        // their uses (which would expose ~30 cycles of shared-memory latency every few terms).
-        // Slots >= cnt hold +0.0 (exact no-ops); reads run up to 16 slots past the staged chunk (STAGE pad).
-        {
-            double2 va[4], vb[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) va[u] = sp2[u];
-            int q = 0;
-            while (true) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) vb[u] = sp2[(q >> 1) + 4 + u];
-                __syncwarp();
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (GS) { t = __dsub_rn(t, va[u].x); t = __dsub_rn(t, va[u].y); }
-                    else { t = __dadd_rn(t, va[u].x); t = __dadd_rn(t, va[u].y); }
-                }
-                q += 8;
-                if (q >= cnt) break;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) va[u] = sp2[(q >> 1) + 4 + u];
-                __syncwarp();
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (GS) { t = __dsub_rn(t, vb[u].x); t = __dsub_rn(t, vb[u].y); }
-                    else { t = __dadd_rn(t, vb[u].x); t = __dadd_rn(t, vb[u].y); }
-                }
-                q += 8;
-                if (q >= cnt) break;
-            }
-        }
-#ifdef AMGB200_TIMING
-        { if (t == 1.2345e300) it.k = -1; long long k4 = clock64(); it.tc += k4 - k3; }
-#endif
+        t = chain_fold<GS>(t, reinterpret_cast<const double2 *>(sprod), min(SUPER, it.pe - base));
         __syncwarp();
         if (more) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) { it.j[u] = it.j1[u]; it.a[u] = it.a1[u]; xc[u] = xn[u]; it.j1[u] = jn[u]; it.a1[u] = an[u]; }
         }
     }
-    {                          // exactly one lane saw the diagonal entry: broadcast it
-        const unsigned m = __ballot_sync(FULL, dl != 0.0);
-        d = m ? __shfl_sync(FULL, dl, __ffs(m) - 1) : 0.0;
-    }
+    return t;
+}
+__device__ __forceinline__ double csr_diag(const CsrItem &it) {   // exactly one lane saw the diagonal entry: broadcast it
+    const unsigned m = __ballot_sync(FULL, it.dl != 0.0);
+    return m ? __shfl_sync(FULL, it.dl, __ffs(m) - 1) : 0.0;
+}
+template <bool COH, bool GS>
+__device__ __forceinline__ double csr_row_exact(const DMat &A, CsrItem &it, const double *x, double t, double &d, int lane, double *sprod) {
+    t = csr_chain_run<COH, GS>(A, it, x, t, lane, sprod);
+    d = csr_diag(it);
     return t;
 }
 
@@ -352,8 +351,8 @@ __device__ __forceinline__ double csr_row_exact(const DMat &A, CsrItem &it, cons
 template <bool COH, bool GS>
 __device__ __forceinline__ double csr_row_fast(const DMat &A, CsrItem &it, const double *x, double t, double &d, int lane) {
     double dl = 0.0, acc = 0.0;
-    for (int base = it.p0; base < it.p1; base += SUPER) {
-        if (base != it.p0) it.load_super(A, base, lane, it.j, it.a);
+    for (int base = it.pb; base < it.pe; base += SUPER) {
+        if (base != it.pb) it.load_super(A, base, lane, it.j, it.a);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (it.j[u] >= 0) {
@@ -454,7 +453,6 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
     DMat A, const double *__restrict__ b, double *xg, const int *__restrict__ wf_item_ptr, int W, int nsweeps, int G, int D,
     long long *dbg) {
     extern __shared__ double dyn_smem[];
-    long long t_wait = 0, t_fin = 0, t_fetch = 0, n_items = 0, t_begin = clock64();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = warp / G, r = warp - grp * G;
     const int n = A.nrows;
@@ -471,27 +469,41 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
     bool have = false;
     int my_g = grp, my_wl = grp;                  // next wavefront of this warp's group (global index, index within a sweep)
     while (my_wl >= W) my_wl -= W;
+    // Two-phase rows (warp-per-row, EXACT): the entries of a row that come before its first entry reading the
+    // wavefront in flight ("prefix", ~30 % of a row on Galerkin operators) only touch x values that are already
+    // final, so the waiting group folds them into the accumulator BEFORE the barrier; only the suffix chain
+    // is on the dependency path.  Storage order is preserved: prefix then suffix.
+    constexpr bool TWO_PHASE = KIND == 1 && EXACT;
+    double t_acc = 0.0;
     auto fetch = [&]() {
         i0 = wf_item_ptr[my_wl]; i1 = wf_item_ptr[my_wl + 1];
         have = i0 + r < i1;
-        if (have) { if constexpr (KIND == 0) ws.prologue(A, i0 + r, lane, b); else wc.prologue(A, i0 + r, lane, b); }
+        if (have) {
+            if constexpr (KIND == 0) ws.prologue(A, i0 + r, lane, b);
+            else wc.load_entries(A, CsrItem::load_desc(A, i0 + r), lane, b, TWO_PHASE);
+        }
     };
     // Wavefront g is produced by group g mod D and consumed (waited for) by group (g+1) mod D through the
     // named barrier 1 + (g mod 8): the producers only *arrive* (non-blocking) and go on to prefetch their
-    // next wavefront, so the prefetch latency never delays the consumers.  D >= 2.
+    // next wavefront, so the prefetch latency never delays the consumers.  D >= 2.  Barrier 9 + grp keeps
+    // the warps of one group together before they start reading x for their next wavefront's prefixes.
     const int pair_threads = 2 * G * 32;
     if (my_g < totalw) fetch();
     for (; my_g < totalw; my_g += D) {
-        long long c0 = clock64();
+        if constexpr (TWO_PHASE) {
+            if (have) {
+                t_acc = csr_chain_run<false, true>(A, wc, x, wc.bk, lane, sprod);     // prefix [p0, ps)
+                wc.begin_range(A, wc.ps, wc.p1, lane);                                // prefetch the suffix
+            }
+        }
         if (my_g > 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + ((my_g - 1) & 7)), "r"(pair_threads) : "memory");
-#ifdef AMGB200_TIMING
-        { volatile double *vs = sprod; if (vs[0] == 1.2345e300) ++n_items; }
-#endif
-        long long c1 = clock64();
-        t_wait += c1 - c0;
         if (have) {
-            ++n_items;
-            if constexpr (KIND == 0) gs_finish_sell<false>(ws, x); else gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod);
+            if constexpr (KIND == 0) gs_finish_sell<false>(ws, x);
+            else if constexpr (TWO_PHASE) {
+                const double t = csr_chain_run<false, true>(A, wc, x, t_acc, lane, sprod);   // suffix [ps, p1)
+                const double d = csr_diag(wc);
+                if (lane == 0 && fabs(d) > GS_TINY) x[wc.k] = __ddiv_rn(t, d);
+            } else gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod);
             for (int it = i0 + r + G; it < i1; it += G) {              // wavefront wider than the group
                 if constexpr (KIND == 0) { ws.prologue(A, it, lane, b); gs_finish_sell<false>(ws, x); }
                 else { wc.prologue(A, it, lane, b); gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod); }
@@ -499,19 +511,12 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
         }
         __threadfence_block();
         if (my_g + 1 < totalw) asm volatile("bar.arrive %0, %1;" ::"r"(1 + (my_g & 7)), "r"(pair_threads) : "memory");
-        long long c2 = clock64();
-        t_fin += c2 - c1;
         my_wl += D;
         while (my_wl >= W) my_wl -= W;
-        if (my_g + D < totalw) fetch();
-        t_fetch += clock64() - c2;
-    }
-#ifdef AMGB200_TIMING
-    if (dbg && lane == 0) { dbg[warp * 8 + 5] = wc.tg; dbg[warp * 8 + 6] = wc.tp; dbg[warp * 8 + 7] = wc.tc; }
-#endif
-    if (dbg && lane == 0) {
-        dbg[warp * 8 + 0] = t_wait; dbg[warp * 8 + 1] = t_fin; dbg[warp * 8 + 2] = t_fetch; dbg[warp * 8 + 3] = n_items;
-        dbg[warp * 8 + 4] = clock64() - t_begin;
+        if (my_g + D < totalw) {
+            if constexpr (TWO_PHASE) asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");   // whole group done with my_g
+            fetch();
+        }
     }
     __syncthreads();
     if (XS) for (int i = threadIdx.x; i < n; i += blockDim.x) xg[i] = dyn_smem[i];
