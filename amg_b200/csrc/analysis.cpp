@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 
 namespace amgb200 {
 
@@ -80,7 +81,8 @@ void build_schedule(const amgb200_mat &A, const int *mark, Schedule &S) {
 
 void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos, int kind,
                   const std::vector<int> *breaks, DevLayout &L) {
-    L = DevLayout();
+    L.~DevLayout();
+    new (&L) DevLayout();
     L.kind = kind;
     const int n = M.num_rows;
     L.nrows = n;
@@ -88,6 +90,7 @@ void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos
     L.nnz = M.row_ptr[n];
     auto nat = [&](int k) { return row_order ? row_order[k] : k; };
     int maxlen = 0;
+#pragma omp parallel for reduction(max : maxlen) schedule(static)
     for (int i = 0; i < n; ++i) maxlen = std::max(maxlen, M.row_ptr[i + 1] - M.row_ptr[i]);
     L.max_row = maxlen;
 
@@ -141,25 +144,33 @@ void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos
     L.slice_row.push_back(n);
     const int ns = (int)L.slice_row.size() - 1;
     L.slice_ptr.assign((size_t)ns + 1, 0);
+    std::vector<int> width((size_t)ns);
+#pragma omp parallel for schedule(static)
     for (int s = 0; s < ns; ++s) {
         int w = 0;
         for (int k = L.slice_row[s]; k < L.slice_row[s + 1]; ++k) { const int i = nat(k); w = std::max(w, M.row_ptr[i + 1] - M.row_ptr[i]); }
-        L.slice_ptr[s + 1] = L.slice_ptr[s] + 32LL * w;
+        width[s] = w;
     }
+    for (int s = 0; s < ns; ++s) L.slice_ptr[s + 1] = L.slice_ptr[s] + 32LL * width[s];
     const size_t total = (size_t)L.slice_ptr[ns];
-    L.col.assign(total, -1);
-    L.val.assign(total, 0.0);
+    L.col.resize(total);          // every slot is written below (entries or padding): no separate fill pass
+    L.val.resize(total);
 #pragma omp parallel for schedule(static)
     for (int s = 0; s < ns; ++s) {
         const long long base = L.slice_ptr[s];
-        for (int k = L.slice_row[s]; k < L.slice_row[s + 1]; ++k) {
-            const int i = nat(k), lane = k - L.slice_row[s];
+        const int nr = L.slice_row[s + 1] - L.slice_row[s];
+        for (int lane = 0; lane < 32; ++lane) {
             long long w = base + lane;
-            for (int q = M.row_ptr[i]; q < M.row_ptr[i + 1]; ++q, w += 32) {
-                const int j = M.col_idx[q];
-                L.col[(size_t)w] = col_pos ? col_pos[j] : j;
-                L.val[(size_t)w] = M.val[q];
+            int filled = 0;
+            if (lane < nr) {
+                const int i = nat(L.slice_row[s] + lane);
+                for (int q = M.row_ptr[i]; q < M.row_ptr[i + 1]; ++q, w += 32, ++filled) {
+                    const int j = M.col_idx[q];
+                    L.col[(size_t)w] = col_pos ? col_pos[j] : j;
+                    L.val[(size_t)w] = M.val[q];
+                }
             }
+            for (; filled < width[s]; ++filled, w += 32) { L.col[(size_t)w] = -1; L.val[(size_t)w] = 0.0; }
         }
     }
 }

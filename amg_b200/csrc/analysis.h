@@ -1,5 +1,6 @@
 // Host-side analysis of a level: Gauss-Seidel wavefront schedule and device matrix layouts.
 #pragma once
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/amg_b200.h"
@@ -7,6 +8,26 @@
 namespace amgb200 {
 
 enum MatKind { KIND_SELL = 0, KIND_CSR = 1 };
+
+// uninitialised host array (std::vector would zero-fill ~1 GB single-threaded before the parallel fill)
+template <class T>
+struct RawBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    RawBuf() = default;
+    RawBuf(const RawBuf &) = delete;
+    RawBuf &operator=(const RawBuf &) = delete;
+    RawBuf(RawBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    RawBuf &operator=(RawBuf &&o) noexcept { if (this != &o) { free(p); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~RawBuf() { free(p); }
+    void resize(size_t m) { free(p); p = m ? (T *)malloc(m * sizeof(T)) : nullptr; n = m; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+};
 
 // Row schedule of one smoothed level.  "Schedule numbering" k = position of a row in the order
 // [F-pass wavefront 0 | F-pass wavefront 1 | ... | C-pass wavefront 0 | ...], rows inside a
@@ -35,8 +56,8 @@ struct DevLayout {
     std::vector<int> slice_row;    // SELL: nslices+1, first schedule row of each slice
     std::vector<long long> slice_ptr;  // SELL: nslices+1
     std::vector<int> rptr;         // CSR: nrows+1
-    std::vector<int> col;
-    std::vector<double> val;
+    RawBuf<int> col;
+    RawBuf<double> val;
     std::vector<int> wf_item_ptr;  // (A of smoothed levels) first item (slice | row) of each wavefront
     std::vector<int> split;        // CSR + wavefronts: per row, index of the first entry whose column lies in the
                                    // cyclically preceding wavefront (row length if none)

@@ -42,25 +42,107 @@ double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Device memory pool: cudaMalloc/cudaFree of ~1 GB cost 0.2-0.6 s per SSS_amg_solve call; blocks of a freed
+// hierarchy are kept (size-class free lists, 2 MB granularity) and reused by the next upload.  Released at exit.
+struct DevPool {
+    std::vector<std::pair<size_t, void *>> free_blocks;
+    std::vector<std::pair<void *, size_t>> live;
+    static size_t round(size_t b) { const size_t g = b < (1u << 20) ? 512 : (2u << 20); return (std::max<size_t>(b, 1) + g - 1) / g * g; }
+    void *get(size_t bytes) {
+        const size_t need = round(bytes);
+        int best = -1;
+        for (int i = 0; i < (int)free_blocks.size(); ++i)
+            if (free_blocks[i].first >= need && free_blocks[i].first <= need + need / 4 && (best < 0 || free_blocks[i].first < free_blocks[best].first)) best = i;
+        void *p = nullptr;
+        size_t sz = need;
+        if (best >= 0) { p = free_blocks[best].second; sz = free_blocks[best].first; free_blocks.erase(free_blocks.begin() + best); }
+        else {
+            cudaError_t e = cudaMalloc(&p, need);
+            if (e != cudaSuccess) { trim(); e = cudaMalloc(&p, need); }
+            CUDA_CHECK(e);
+        }
+        live.emplace_back(p, sz);
+        return p;
+    }
+    void put(void *p) {
+        if (!p) return;
+        for (size_t i = 0; i < live.size(); ++i)
+            if (live[i].first == p) { free_blocks.emplace_back(live[i].second, p); live.erase(live.begin() + i); return; }
+        cudaFree(p);
+    }
+    void trim() { for (auto &b : free_blocks) cudaFree(b.second); free_blocks.clear(); }
+};
+DevPool &pool() { static DevPool *p = new DevPool(); return *p; }   // intentionally leaked: the driver reclaims at process exit
+void dev_free(const void *p) { pool().put(const_cast<void *>(p)); }
+
 template <class T>
-T *dev_alloc(size_t n) {
-    T *p = nullptr;
-    CUDA_CHECK(cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T)));
+T *dev_alloc(size_t n) { return (T *)pool().get(std::max<size_t>(n, 1) * sizeof(T)); }
+// Host -> device copy of pageable memory through a small ring of pinned staging buffers (allocated once per
+// process): OpenMP threads fill a staging buffer while the DMA engine drains the previous one.  ~4x faster than
+// cudaMemcpy from pageable memory for the ~1 GB of a hierarchy, without pinning the caller's arrays.
+struct Stager {
+    static constexpr size_t CHUNK = 32u << 20;
+    static constexpr int NBUF = 3;
+    char *buf[NBUF] = {nullptr, nullptr, nullptr};
+    cudaEvent_t done[NBUF];
+    cudaStream_t stream = nullptr;
+    bool ok = false;
+    void init() {
+        if (ok) return;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (int i = 0; i < NBUF; ++i) { CUDA_CHECK(cudaMallocHost((void **)&buf[i], CHUNK)); CUDA_CHECK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)); }
+        ok = true;
+    }
+    void copy(void *dst, const void *src, size_t bytes) {
+        init();
+        size_t off = 0;
+        int slot = 0;
+        bool used[NBUF] = {false, false, false};
+        while (off < bytes) {
+            const size_t m = std::min(CHUNK, bytes - off);
+            if (used[slot]) CUDA_CHECK(cudaEventSynchronize(done[slot]));
+            const char *sp = (const char *)src + off;
+            char *bp = buf[slot];
+            const size_t piece = (m + 7) / 8;
+#pragma omp parallel for schedule(static) num_threads(8)
+            for (int t = 0; t < 8; ++t) {
+                const size_t a = std::min(m, piece * t), b = std::min(m, piece * (t + 1));
+                if (b > a) memcpy(bp + a, sp + a, b - a);
+            }
+            CUDA_CHECK(cudaMemcpyAsync((char *)dst + off, bp, m, cudaMemcpyHostToDevice, stream));
+            CUDA_CHECK(cudaEventRecord(done[slot], stream));
+            used[slot] = true;
+            slot = (slot + 1) % NBUF;
+            off += m;
+        }
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+};
+Stager &stager() { static Stager s; return s; }
+
+template <class T>
+T *dev_upload_raw(const T *src, size_t n) {
+    T *p = dev_alloc<T>(n);
+    const size_t bytes = n * sizeof(T);
+    if (bytes >= (4u << 20)) stager().copy(p, src, bytes);
+    else if (bytes) CUDA_CHECK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
     return p;
 }
-template <class T>
-T *dev_upload(const std::vector<T> &v) {
-    T *p = dev_alloc<T>(v.size());
-    if (!v.empty()) CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    return p;
-}
+template <class T> T *dev_upload(const std::vector<T> &v) { return dev_upload_raw(v.data(), v.size()); }
+template <class T> T *dev_upload(const RawBuf<T> &v) { return dev_upload_raw(v.data(), v.size()); }
 
 struct DevMatOwner {
     DMat v{};
     long long nnz = 0, padded = 0;
     int max_row = 0;
     bool valid = false;
+    static double &t_upload() { static double t = 0; return t; }
     void upload(const DevLayout &L) {
+        const double t0 = now_s();
+        upload_impl(L);
+        t_upload() += now_s() - t0;
+    }
+    void upload_impl(const DevLayout &L) {
         v.kind = L.kind; v.nrows = L.nrows; v.ncols = L.ncols; v.nitems = L.nitems(); v.max_row = L.max_row;
         v.slice_row = nullptr; v.slice_ptr = nullptr; v.rptr = nullptr; v.split = nullptr;
         if (L.kind == KIND_SELL) { v.slice_row = dev_upload(L.slice_row); v.slice_ptr = dev_upload(L.slice_ptr); }
@@ -71,8 +153,8 @@ struct DevMatOwner {
     }
     void release() {
         if (!valid) return;
-        cudaFree((void *)v.slice_row); cudaFree((void *)v.slice_ptr); cudaFree((void *)v.rptr); cudaFree((void *)v.split);
-        cudaFree((void *)v.col); cudaFree((void *)v.val);
+        dev_free(v.slice_row); dev_free(v.slice_ptr); dev_free(v.rptr); dev_free(v.split);
+        dev_free(v.col); dev_free(v.val);
         valid = false;
     }
 };
@@ -255,7 +337,7 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
     }
     const int need = nsweeps * lv.W;
     if (need > lv.cnt_cap) {
-        if (lv.d_cnt) CUDA_CHECK(cudaFree(lv.d_cnt));
+        if (lv.d_cnt) dev_free(lv.d_cnt);
         lv.d_cnt = dev_alloc<unsigned>(need);
         lv.cnt_cap = need;
     }
@@ -329,7 +411,7 @@ double krylov_residual(amgb200_hier *h, const DMat &A, const double *u, const do
 
 void ensure_krylov(amgb200_hier *h, size_t len) {
     if (h->kry_len >= len) return;
-    if (h->kry) CUDA_CHECK(cudaFree(h->kry));
+    if (h->kry) dev_free(h->kry);
     h->kry = dev_alloc<double>(len);
     h->kry_len = len;
 }
@@ -649,14 +731,16 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     h->L.resize(nl);
     std::vector<Schedule> sched(nl);
     int maxn = 0;
+    for (int l = 0; l + 1 < nl; ++l)
+        if (!(mg->pars.cf_order && mg->cg[l].cfmark.d)) {
+            fprintf(stderr, "libamgb200: natural-order Gauss-Seidel (cf_order=0 / no cfmark, SSS_smooth.c:90-137) is not implemented yet\n");
+            exit(-12);
+        }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int l = 0; l < nl - 1; ++l) build_schedule(mg->cg[l].A, mg->cg[l].cfmark.d, sched[l]);   // levels are independent
     for (int l = 0; l < nl; ++l) {
         const amgb200_comp &c = mg->cg[l];
         if (l < nl - 1) {
-            if (!(mg->pars.cf_order && c.cfmark.d)) {
-                fprintf(stderr, "libamgb200: natural-order Gauss-Seidel (cf_order=0 / no cfmark, SSS_smooth.c:90-137) is not implemented yet\n");
-                exit(-12);
-            }
-            build_schedule(c.A, c.cfmark.d, sched[l]);
             if (sched[l].rows_without_diag) {
                 fprintf(stderr, "libamgb200: level %d has %d rows without a stored diagonal; the reference's carried-over "
                                 "diagonal (SSS_smooth.c:13,30) cannot be reproduced in parallel\n", l, sched[l].rows_without_diag);
@@ -668,6 +752,8 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         maxn = std::max(maxn, c.A.num_rows);
     }
     h->analysis_s = now_s() - t0;
+    DevMatOwner::t_upload() = 0;
+    double t_layout = 0;
 
     int max_items = 1;
     for (int l = 0; l < nl; ++l) {
@@ -684,12 +770,12 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         int gs_kind = kind_of(c.A);
         const double mean_len = (double)c.A.num_nnzs / std::max(1, c.A.num_rows);
         if (is_ordered && h->exact && mean_len > ordered_csr_min) gs_kind = KIND_CSR;
-        build_layout(c.A, S.order.data(), S.pos.data(), gs_kind, lv.smoothed ? &S.wf_row_ptr : nullptr, lay);
+        { const double tl = now_s(); build_layout(c.A, S.order.data(), S.pos.data(), gs_kind, lv.smoothed ? &S.wf_row_ptr : nullptr, lay); t_layout += now_s() - tl; }
         lv.A.upload(lay);
         max_items = std::max(max_items, lay.nitems());
         if (gs_kind != kind_of(c.A)) {
             DevLayout lsp;
-            build_layout(c.A, S.order.data(), S.pos.data(), kind_of(c.A), nullptr, lsp);
+            { const double tl = now_s(); build_layout(c.A, S.order.data(), S.pos.data(), kind_of(c.A), nullptr, lsp); t_layout += now_s() - tl; }
             lv.Asp.upload(lsp);
             max_items = std::max(max_items, lsp.nitems());
         }
@@ -738,10 +824,10 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             if (getenv("AMGB200_GS_STRATEGY") && lv.ordered) lv.strategy = std::max(1, std::min(3, atoi(getenv("AMGB200_GS_STRATEGY"))));
             // transfers: P_l rows in this level's schedule, columns in the next level's; R_l the other way round
             DevLayout lp, lr;
-            build_layout(c.P, S.order.data(), sched[l + 1].pos.data(), kind_of(c.P), nullptr, lp);
+            { const double tl = now_s(); build_layout(c.P, S.order.data(), sched[l + 1].pos.data(), kind_of(c.P), nullptr, lp); t_layout += now_s() - tl; }
             lv.P.upload(lp);
             max_items = std::max(max_items, lp.nitems());
-            build_layout(c.R, sched[l + 1].order.data(), S.pos.data(), kind_of(c.R), nullptr, lr);
+            { const double tl = now_s(); build_layout(c.R, sched[l + 1].order.data(), S.pos.data(), kind_of(c.R), nullptr, lr); t_layout += now_s() - tl; }
             lv.R.upload(lr);
             max_items = std::max(max_items, lr.nitems());
         }
@@ -756,7 +842,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     CUDA_CHECK(cudaDeviceSynchronize());
     h->upload_s = now_s() - t0;
     if (opt.verbose >= 2) {
-        printf("libamgb200: %d levels resident; analysis %.3f s, analysis+upload %.3f s\n", nl, h->analysis_s, h->upload_s);
+        printf("libamgb200: %d levels resident; schedule analysis %.3f s, layout build %.3f s, cudaMalloc+H2D %.3f s, total %.3f s\n", nl, h->analysis_s, t_layout, DevMatOwner::t_upload(), h->upload_s);
         printf("  mode %s; lvl       rows         nnz  kind  F-rows  wavefronts F/C   P nnz      R nnz   sym strat\n", h->exact ? "EXACT" : "FAST");
         for (int l = 0; l < nl; ++l) {
             const Level &lv = h->L[l];
@@ -774,11 +860,11 @@ void amgb200_free(amgb200_hier *h) {
     cudaStreamSynchronize(h->stream);
     for (Level &lv : h->L) {
         lv.A.release(); lv.Asp.release(); lv.P.release(); lv.R.release();
-        cudaFree(lv.d_order); cudaFree(lv.x); cudaFree(lv.b); cudaFree(lv.wp);
-        cudaFree(lv.d_item_wf); cudaFree(lv.d_wf_item_ptr); cudaFree(lv.d_cnt);
+        dev_free(lv.d_order); dev_free(lv.x); dev_free(lv.b); dev_free(lv.wp);
+        dev_free(lv.d_item_wf); dev_free(lv.d_wf_item_ptr); dev_free(lv.d_cnt);
     }
-    cudaFree(h->d_partial); cudaFree(h->d_scal); cudaFreeHost(h->h_scal);
-    cudaFree(h->d_xnat); cudaFree(h->d_bnat); cudaFree(h->kry);
+    dev_free(h->d_partial); dev_free(h->d_scal); cudaFreeHost(h->h_scal);
+    dev_free(h->d_xnat); dev_free(h->d_bnat); dev_free(h->kry); dev_free(h->d_dbg);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
