@@ -176,6 +176,7 @@ struct Level {
     double prof_ms[4] = {0, 0, 0, 0};  // AMGB200_PROFILE: GS, residual, restrict, prolong of the last solve
     bool x_in_smem = false;            // strategy 2 only: x fits in the CTA's shared memory
     int cta_G = 1, cta_D = 1;          // strategy 2: D groups of G warps (pipeline depth D)
+    int dsmem_sh = 0;                  // strategy 3: x distributed over the cluster's shared memory, 2^sh rows per CTA (0 = x in global memory)
 };
 
 }  // namespace
@@ -301,6 +302,28 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
             for (int w = 0; w < nw; ++w) printf("   warp %2d: wait %9lld  finish %9lld  fetch %9lld  items %6lld  total %9lld | gather %9lld prod %9lld chain %9lld\n", w, hd[w*8], hd[w*8+1], hd[w*8+2], hd[w*8+3], hd[w*8+4], hd[w*8+5], hd[w*8+6], hd[w*8+7]);
         }
         CUDA_CHECK(cudaGetLastError());
+        return;
+    }
+    if (lv.strategy == 3 && KIND == 1 && EXACT && lv.dsmem_sh > 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cluster_dsmem_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cluster_dsmem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+            attr_set = true;
+        }
+        const int nwc = std::max(1, std::min(CLUSTER_WARPS_CSR, (lv.max_width + CLUSTER_CTAS - 1) / CLUSTER_CTAS));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CLUSTER_CTAS);
+        cfg.blockDim = dim3(32 * nwc);
+        cfg.dynamicSmemBytes = ((size_t)1 << lv.dsmem_sh) * sizeof(double) + (size_t)nwc * STAGE * sizeof(double);
+        cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CLUSTER_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, gs_ordered_cluster_dsmem_kernel<true>, lv.A.v, (const double *)lv.b, lv.x, (const int *)lv.d_wf_item_ptr, lv.W, nsweeps, lv.dsmem_sh));
+        ++g_launches;
         return;
     }
     if (lv.strategy == 3) {
@@ -821,6 +844,14 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                 const size_t needb = (size_t)((lv.n + 1) & ~1) * 8 + (size_t)lv.cta_G * lv.cta_D * STAGE * 8;
                 lv.x_in_smem = lv.strategy == 2 && needb <= (size_t)h->max_dyn_smem && !(getenv("AMGB200_NO_SMEM_X") && atoi(getenv("AMGB200_NO_SMEM_X")));
             }
+            // measured on B200 (128^3, levels 2-4): scattered 8-byte remote shared-memory gathers are SLOWER than L2 gathers
+            // (5.0 / 2.8 / 4.8 ms per sweep vs 2.8 / 2.3 / 4.5 ms), so the distributed-x variant is opt-in only
+            if (lv.strategy == 3 && lay.kind == KIND_CSR && h->exact && getenv("AMGB200_DSMEM_X") && atoi(getenv("AMGB200_DSMEM_X"))) {
+                int sh = 6;
+                while (((long long)CLUSTER_CTAS << sh) < lv.n) ++sh;
+                const int nwc = std::max(1, std::min(CLUSTER_WARPS_CSR, (lv.max_width + CLUSTER_CTAS - 1) / CLUSTER_CTAS));
+                if (((size_t)1 << sh) * 8 + (size_t)nwc * STAGE * 8 <= (size_t)h->max_dyn_smem) lv.dsmem_sh = sh;
+            }
             if (getenv("AMGB200_GS_STRATEGY") && lv.ordered) lv.strategy = std::max(1, std::min(3, atoi(getenv("AMGB200_GS_STRATEGY"))));
             // transfers: P_l rows in this level's schedule, columns in the next level's; R_l the other way round
             DevLayout lp, lr;
@@ -850,6 +881,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                    lv.pass_rows[0], lv.wf_count[0], lv.wf_count[1], lv.P.valid ? lv.P.nnz : 0LL, lv.R.valid ? lv.R.nnz : 0LL, (int)lv.pattern_symmetric);
             printf("      strategy %d%s  max wavefront width %d items\n", lv.strategy, lv.x_in_smem ? " (x in smem)" : "", lv.max_width);
             if (lv.strategy == 2) printf("      CTA pipeline: %d groups x %d warps\n", lv.cta_D, lv.cta_G);
+            if (lv.strategy == 3 && lv.dsmem_sh) printf("      x distributed over the cluster's shared memory: %d rows per CTA\n", 1 << lv.dsmem_sh);
         }
     }
     return h;

@@ -15,6 +15,7 @@
 // FAST mode (opt-in) replaces the in-order chain of the warp-per-row kernels by a shuffle tree:
 // ~1e-16 relative per row, which the |x|/|r| amplification turns into ~1e-7 at the last V-cycle.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
@@ -42,6 +43,23 @@ constexpr unsigned FULL = 0xffffffffu;
 // COH: x is being updated by other SMs during this launch -> read it at L2 (L1 is not coherent)
 template <bool COH>
 __device__ __forceinline__ double ld_x(const double *p) { return COH ? __ldcg(p) : *p; }
+
+// where the x vector of a level lives during a launch
+template <bool COH>
+struct GlobalX {                       // global memory (or this CTA's shared memory: generic addressing)
+    double *x;
+    __device__ __forceinline__ double ld(int j) const { return ld_x<COH>(x + j); }
+    __device__ __forceinline__ void st(int k, double v) const { x[k] = v; }
+};
+struct ClusterX {                      // distributed over the shared memory of the CTAs of a cluster: row k lives in CTA k >> sh
+    double *xs;                        // this CTA's slice
+    int sh, mask;
+    __device__ __forceinline__ double *at(int j) const {
+        return cooperative_groups::this_cluster().map_shared_rank(xs, j >> sh) + (j & mask);
+    }
+    __device__ __forceinline__ double ld(int j) const { return *at(j); }
+    __device__ __forceinline__ void st(int k, double v) const { *at(k) = v; }
+};
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -296,12 +314,12 @@ __device__ __forceinline__ double chain_fold(double t, const double2 *sp2, int c
 // EXACT in-order accumulation over the range begun with begin_range().  GS: products are subtracted and the
 // diagonal entry is skipped (remembered in it.dl); otherwise products are added.  Padding and the skipped
 // diagonal contribute +0.0, which leaves t bit-unchanged.  Result valid in all lanes.
-template <bool COH, bool GS>
-__device__ __forceinline__ double csr_chain_run(const DMat &A, CsrItem &it, const double *x, double t, int lane, double *sprod) {
+template <class XA, bool GS>
+__device__ __forceinline__ double csr_chain_run_x(const DMat &A, CsrItem &it, const XA &xa, double t, int lane, double *sprod) {
     if (it.pb >= it.pe) return t;
     double xc[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) xc[u] = (it.j[u] >= 0 && !(GS && it.j[u] == it.k)) ? ld_x<COH>(x + it.j[u]) : 0.0;
+    for (int u = 0; u < 4; ++u) xc[u] = (it.j[u] >= 0 && !(GS && it.j[u] == it.k)) ? xa.ld(it.j[u]) : 0.0;
     for (int base = it.pb; base < it.pe; base += SUPER) {
         // stage 1: col/val of super chunk s+2 ; stage 2: x gather of s+1 (its col arrived an iteration ago)
         int jn[4];
@@ -314,7 +332,7 @@ __device__ __forceinline__ double csr_chain_run(const DMat &A, CsrItem &it, cons
         }
         if (more) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) xn[u] = (it.j1[u] >= 0 && !(GS && it.j1[u] == it.k)) ? ld_x<COH>(x + it.j1[u]) : 0.0;
+            for (int u = 0; u < 4; ++u) xn[u] = (it.j1[u] >= 0 && !(GS && it.j1[u] == it.k)) ? xa.ld(it.j1[u]) : 0.0;
         }
         // stage 3: products of super chunk s into the staging buffer, then the in-order chain
 #pragma unroll
@@ -335,6 +353,10 @@ __device__ __forceinline__ double csr_chain_run(const DMat &A, CsrItem &it, cons
         }
     }
     return t;
+}
+template <bool COH, bool GS>
+__device__ __forceinline__ double csr_chain_run(const DMat &A, CsrItem &it, const double *x, double t, int lane, double *sprod) {
+    return csr_chain_run_x<GlobalX<COH>, GS>(A, it, GlobalX<COH>{const_cast<double *>(x)}, t, lane, sprod);
 }
 __device__ __forceinline__ double csr_diag(const CsrItem &it) {   // exactly one lane saw the diagonal entry: broadcast it
     const unsigned m = __ballot_sync(FULL, it.dl != 0.0);
@@ -606,6 +628,61 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CLUSTER_WARPS_SELL : 32 * CLU
         dbg[s * 8 + 0] = tf; dbg[s * 8 + 1] = tf2; dbg[s * 8 + 2] = ta; dbg[s * 8 + 3] = tpre; dbg[s * 8 + 4] = tw; dbg[s * 8 + 5] = nit;
     }
 #endif
+}
+
+// Same walk, warp-per-row EXACT rows, with the x vector of the level DISTRIBUTED over the shared memory of the
+// 16 CTAs (row k in CTA k >> sh): gathers are remote shared-memory loads (~215 cycles instead of an L2 round trip)
+// and a finished row is a remote shared-memory store, so the release half of the cluster barrier does not wait for
+// a global store to reach L2.  Levels with n <= 16 * 2^sh rows, 2^sh * 8 bytes + staging <= 227 KB.
+// Dynamic shared memory: [x slice: 2^sh doubles] [nwarps * STAGE doubles]
+template <bool EXACT>
+__global__ void __launch_bounds__(32 * CLUSTER_WARPS_CSR) gs_ordered_cluster_dsmem_kernel(
+    DMat A, const double *__restrict__ b, double *xg, const int *__restrict__ wf_item_ptr, int W, int nsweeps, int sh) {
+    extern __shared__ double dyn_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    const int rank = (int)cluster_ctarank();
+    const int gw = rank * nw + warp;
+    const int TW = CLUSTER_CTAS * nw;
+    const int totalw = W * nsweeps;
+    const int chunk = 1 << sh, n = A.nrows;
+    double *xs = dyn_smem;
+    double *sp = dyn_smem + chunk + warp * STAGE;
+    for (int i = threadIdx.x; i < chunk; i += blockDim.x) { const int k = rank * chunk + i; xs[i] = k < n ? xg[k] : 0.0; }
+    cluster_arrive(); cluster_wait();
+    const ClusterX xa{xs, sh, chunk - 1};
+    auto finish = [&](CsrItem &w) {
+        const double t = EXACT ? csr_chain_run_x<ClusterX, true>(A, w, xa, w.bk, lane, sp) : 0.0;
+        const double d = csr_diag(w);
+        if (lane == 0 && fabs(d) > GS_TINY) xa.st(w.k, __ddiv_rn(t, d));
+    };
+    int wl2 = 2 % W;
+    int a0 = wf_item_ptr[0], a1 = wf_item_ptr[1];
+    int b0 = wf_item_ptr[1 % W], b1 = wf_item_ptr[1 % W + 1];
+    int c0 = wf_item_ptr[wl2], c1 = wf_item_ptr[wl2 + 1];
+    CsrItem cur;
+    CsrItem::Desc dn = {};
+    bool have = a0 + gw < a1, have_n = b0 + gw < b1;
+    if (have) cur.prologue(A, a0 + gw, lane, b);
+    if (have_n) dn = CsrItem::load_desc(A, b0 + gw);
+    for (int g = 0; g < totalw; ++g) {
+        if (have) {
+            finish(cur);
+            for (int it = a0 + gw + TW; it < a1; it += TW) { cur.prologue(A, it, lane, b); finish(cur); }
+        }
+        if (g + 1 < totalw) {
+            cluster_arrive();
+            a0 = b0; a1 = b1; have = have_n;
+            if (have) cur.load_entries(A, dn, lane, b);
+            b0 = c0; b1 = c1; have_n = b0 + gw < b1;
+            if (have_n) dn = CsrItem::load_desc(A, b0 + gw);
+            if (++wl2 == W) wl2 = 0;
+            c0 = wf_item_ptr[wl2]; c1 = wf_item_ptr[wl2 + 1];
+            cluster_wait();
+        }
+    }
+    cluster_arrive(); cluster_wait();            // every remote access to my slice is done
+    for (int i = threadIdx.x; i < chunk; i += blockDim.x) { const int k = rank * chunk + i; if (k < n) xg[k] = xs[i]; }
 }
 
 // ------------------------------------------------------------------------------------------
