@@ -117,13 +117,16 @@ void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos
             std::vector<int> wf_of((size_t)n);
             for (int w = 0; w < W; ++w) for (int k = (*breaks)[w]; k < (*breaks)[w + 1]; ++k) wf_of[k] = w;
             L.split.resize((size_t)n);
-#pragma omp parallel for schedule(static)
-            for (int k = 0; k < n; ++k) {
+            L.late.assign(((size_t)L.nnz + 31) / 32 + 1, 0u);
+            for (int k = 0; k < n; ++k) {              // (bit writes of neighbouring rows share words: keep this loop serial)
                 const int prev = wf_of[k] == 0 ? W - 1 : wf_of[k] - 1;
                 int sp = L.rptr[k + 1] - L.rptr[k];
                 for (int q = L.rptr[k]; q < L.rptr[k + 1]; ++q) {
                     const int c = L.col[q];
-                    if (c != k && c < n && wf_of[c] == prev) { sp = q - L.rptr[k]; break; }
+                    if (c != k && c < n && wf_of[c] == prev) {
+                        if (q - L.rptr[k] < sp) sp = q - L.rptr[k];
+                        L.late[(size_t)q >> 5] |= 1u << (q & 31);
+                    }
                 }
                 L.split[k] = sp;
             }

@@ -61,6 +61,7 @@ struct DevLayout {
     std::vector<int> wf_item_ptr;  // (A of smoothed levels) first item (slice | row) of each wavefront
     std::vector<int> split;        // CSR + wavefronts: per row, index of the first entry whose column lies in the
                                    // cyclically preceding wavefront (row length if none)
+    std::vector<unsigned> late;    // CSR + wavefronts: one bit per entry, set when its column lies in that preceding wavefront
     int nitems() const { return kind == KIND_SELL ? (int)slice_row.size() - 1 : nrows; }
 };
 

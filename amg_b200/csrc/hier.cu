@@ -144,16 +144,16 @@ struct DevMatOwner {
     }
     void upload_impl(const DevLayout &L) {
         v.kind = L.kind; v.nrows = L.nrows; v.ncols = L.ncols; v.nitems = L.nitems(); v.max_row = L.max_row;
-        v.slice_row = nullptr; v.slice_ptr = nullptr; v.rptr = nullptr; v.split = nullptr;
+        v.slice_row = nullptr; v.slice_ptr = nullptr; v.rptr = nullptr; v.split = nullptr; v.late = nullptr;
         if (L.kind == KIND_SELL) { v.slice_row = dev_upload(L.slice_row); v.slice_ptr = dev_upload(L.slice_ptr); }
-        else { v.rptr = dev_upload(L.rptr); if (!L.split.empty()) v.split = dev_upload(L.split); }
+        else { v.rptr = dev_upload(L.rptr); if (!L.split.empty()) { v.split = dev_upload(L.split); v.late = dev_upload(L.late); } }
         v.col = dev_upload(L.col);
         v.val = dev_upload(L.val);
         nnz = L.nnz; padded = (long long)L.col.size(); max_row = L.max_row; valid = true;
     }
     void release() {
         if (!valid) return;
-        dev_free(v.slice_row); dev_free(v.slice_ptr); dev_free(v.rptr); dev_free(v.split);
+        dev_free(v.slice_row); dev_free(v.slice_ptr); dev_free(v.rptr); dev_free(v.split); dev_free(v.late);
         dev_free(v.col); dev_free(v.val);
         valid = false;
     }
@@ -176,6 +176,7 @@ struct Level {
     double prof_ms[4] = {0, 0, 0, 0};  // AMGB200_PROFILE: GS, residual, restrict, prolong of the last solve
     bool x_in_smem = false;            // strategy 2 only: x fits in the CTA's shared memory
     int cta_G = 1, cta_D = 1;          // strategy 2: D groups of G warps (pipeline depth D)
+    int cta_cap = 0;                   // strategy 2, two-phase rows: parked suffix products per warp (0 = stream the suffix)
     int dsmem_sh = 0;                  // strategy 3: x distributed over the cluster's shared memory, 2^sh rows per CTA (0 = x in global memory)
 };
 
@@ -281,7 +282,8 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
     }
     if (lv.strategy == 2) {
         const int G = lv.cta_G, D = lv.cta_D, nw = G * D;
-        const size_t stage = (size_t)nw * STAGE * sizeof(double);
+        const int cap = lv.cta_cap;
+        const size_t stage = (size_t)nw * (STAGE + (cap ? cap + 24 + 2 * LATE_CAP : 0)) * sizeof(double);
         const size_t xbytes = (size_t)((lv.n + 1) & ~1) * sizeof(double);
         if (lv.x_in_smem) {
             static bool attr_set = false;
@@ -289,17 +291,22 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
                 CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cta_kernel<KIND, EXACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
                 attr_set = true;
             }
-            gs_ordered_cta_kernel<KIND, EXACT, true><<<1, 32 * nw, xbytes + stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D, h->d_dbg);
+            gs_ordered_cta_kernel<KIND, EXACT, true><<<1, 32 * nw, xbytes + stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D, cap, h->d_dbg);
         } else {
-            gs_ordered_cta_kernel<KIND, EXACT, false><<<1, 32 * nw, stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D, h->d_dbg);
+            static bool attr_set2 = false;
+            if (!attr_set2) {
+                CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cta_kernel<KIND, EXACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+                attr_set2 = true;
+            }
+            gs_ordered_cta_kernel<KIND, EXACT, false><<<1, 32 * nw, stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D, cap, h->d_dbg);
         }
         ++g_launches;
         if (h->d_dbg) {
-            long long hd[16 * 8];
+            long long hd[16 * 8 + 1];
             CUDA_CHECK(cudaStreamSynchronize(h->stream));
             CUDA_CHECK(cudaMemcpy(hd, h->d_dbg, sizeof(hd), cudaMemcpyDeviceToHost));
-            printf("[dbg] CTA kernel level n=%d G=%d D=%d W=%d sweeps=%d\n", lv.n, G, D, lv.W, nsweeps);
-            for (int w = 0; w < nw; ++w) printf("   warp %2d: wait %9lld  finish %9lld  fetch %9lld  items %6lld  total %9lld | gather %9lld prod %9lld chain %9lld\n", w, hd[w*8], hd[w*8+1], hd[w*8+2], hd[w*8+3], hd[w*8+4], hd[w*8+5], hd[w*8+6], hd[w*8+7]);
+            printf("[dbg] CTA kernel level n=%d G=%d D=%d W=%d sweeps=%d  warp0 suffix chunks %lld\n", lv.n, G, D, lv.W, nsweeps, hd[16 * 8]);
+            for (int w = 0; w < nw; ++w) printf("   warp %2d: prefix %9lld  wait %9lld  suffix %9lld  post(group barrier+fetch) %9lld  items %6lld | suffix: gather %8lld prod %8lld chain %8lld\n", w, hd[w*8], hd[w*8+1], hd[w*8+2], hd[w*8+3], hd[w*8+4], hd[w*8+5], hd[w*8+6], hd[w*8+7]);
         }
         CUDA_CHECK(cudaGetLastError());
         return;
@@ -841,8 +848,16 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                 // the prefix/suffix scheme of the warp-per-row EXACT kernel folds a row's prefix while exactly ONE earlier
                 // wavefront is still in flight: two alternating groups
                 if (lay.kind == KIND_CSR && h->exact) lv.cta_D = 2;
-                const size_t needb = (size_t)((lv.n + 1) & ~1) * 8 + (size_t)lv.cta_G * lv.cta_D * STAGE * 8;
-                lv.x_in_smem = lv.strategy == 2 && needb <= (size_t)h->max_dyn_smem && !(getenv("AMGB200_NO_SMEM_X") && atoi(getenv("AMGB200_NO_SMEM_X")));
+                const int nwarps = lv.cta_G * lv.cta_D;
+                const size_t xb = (size_t)((lv.n + 1) & ~1) * 8, stb = (size_t)nwarps * STAGE * 8;
+                lv.x_in_smem = lv.strategy == 2 && xb + stb <= (size_t)h->max_dyn_smem && !(getenv("AMGB200_NO_SMEM_X") && atoi(getenv("AMGB200_NO_SMEM_X")));
+                if (lv.strategy == 2 && lay.kind == KIND_CSR && h->exact && !(getenv("AMGB200_NO_PARK") && atoi(getenv("AMGB200_NO_PARK")))) {
+                    // park the whole suffix of a row (its products) in shared memory before the barrier when it fits
+                    int cap = std::min(1024, (lay.max_row + 31) / 32 * 32);
+                    const size_t base = (lv.x_in_smem ? xb : 0) + stb;
+                    while (cap >= 128 && base + (size_t)nwarps * (cap + 24 + 2 * LATE_CAP) * 8 > (size_t)h->max_dyn_smem) cap -= 128;
+                    lv.cta_cap = cap >= 128 ? cap : 0;
+                }
             }
             // measured on B200 (128^3, levels 2-4): scattered 8-byte remote shared-memory gathers are SLOWER than L2 gathers
             // (5.0 / 2.8 / 4.8 ms per sweep vs 2.8 / 2.3 / 4.5 ms), so the distributed-x variant is opt-in only
@@ -867,7 +882,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     h->d_partial = dev_alloc<double>((size_t)4 * h->partial_stride);
     h->d_scal = dev_alloc<double>(8);
     CUDA_CHECK(cudaMallocHost((void **)&h->h_scal, 8 * sizeof(double)));
-    if (getenv("AMGB200_DEBUG_TIMING")) h->d_dbg = dev_alloc<long long>(16 * 8);
+    if (getenv("AMGB200_DEBUG_TIMING")) h->d_dbg = dev_alloc<long long>(16 * 8 + 8);
     h->d_xnat = dev_alloc<double>(maxn);
     h->d_bnat = dev_alloc<double>(maxn);
     CUDA_CHECK(cudaDeviceSynchronize());
@@ -880,7 +895,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             printf("  %3d %10d %11lld  %s %8d  %6d/%-6d %9lld %9lld  %d\n", l, lv.n, lv.A.nnz, lv.A.v.kind == KIND_SELL ? "SELL" : "CSR ",
                    lv.pass_rows[0], lv.wf_count[0], lv.wf_count[1], lv.P.valid ? lv.P.nnz : 0LL, lv.R.valid ? lv.R.nnz : 0LL, (int)lv.pattern_symmetric);
             printf("      strategy %d%s  max wavefront width %d items\n", lv.strategy, lv.x_in_smem ? " (x in smem)" : "", lv.max_width);
-            if (lv.strategy == 2) printf("      CTA pipeline: %d groups x %d warps\n", lv.cta_D, lv.cta_G);
+            if (lv.strategy == 2) printf("      CTA pipeline: %d groups x %d warps, parked suffix capacity %d\n", lv.cta_D, lv.cta_G, lv.cta_cap);
             if (lv.strategy == 3 && lv.dsmem_sh) printf("      x distributed over the cluster's shared memory: %d rows per CTA\n", 1 << lv.dsmem_sh);
         }
     }

@@ -28,6 +28,7 @@ struct DMat {                      // device view of a DevLayout
     const long long *slice_ptr;    // SELL
     const int *rptr;               // CSR
     const int *split;              // CSR, ordered levels: per row, index of the first entry that reads the previous wavefront (or NULL)
+    const unsigned *late;          // CSR, ordered levels: one bit per entry, set when it reads the previous wavefront (or NULL)
     const int *col;
     const double *val;
 };
@@ -244,13 +245,39 @@ struct CsrItem {
     int pb, pe;                // range currently being streamed
     int j[4], j1[4];           // super chunks 0 and 1 of that range
     double a[4], a1[4];
+    unsigned lw[4], lw1[4];    // (two-phase rows) the late-flag words of those entries
     double bk, dl;             // right-hand side; diagonal entry if this lane has seen it
+#ifdef AMGB200_TIMING
+    long long tg = 0, tp = 0, tc = 0, nch = 0;
+#endif
     __device__ __forceinline__ void load_super(const DMat &A, int base, int lane, int (&jj)[4], double (&aa)[4]) const {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int p = base + u * 32 + lane;
             if (p < pe) { jj[u] = A.col[p]; aa[u] = A.val[p]; } else { jj[u] = -1; aa[u] = 0.0; }
         }
+    }
+    __device__ __forceinline__ void load_late(const DMat &A, int base, int lane, unsigned (&ll)[4]) const {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = base + u * 32 + lane;
+            ll[u] = p < pe ? A.late[p >> 5] : 0u;
+        }
+    }
+    // the late-flag words of the first two super chunks of the suffix [ps, p1), requested early ...
+    unsigned lwp[4], lwp1[4];
+    __device__ __forceinline__ void suffix_prefetch_late(const DMat &A, int lane) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = ps + u * 32 + lane, q = p + SUPER;
+            lwp[u] = p < p1 ? A.late[p >> 5] : 0u;
+            lwp1[u] = q < p1 ? A.late[q >> 5] : 0u;
+        }
+    }
+    // ... and adopted once the suffix range has been begun
+    __device__ __forceinline__ void adopt_late() {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { lw[u] = lwp[u]; lw1[u] = lwp1[u]; }
     }
     struct Desc { int row, p0, p1, ps; };
     __device__ __forceinline__ static Desc load_desc(const DMat &A, int row) {
@@ -282,6 +309,9 @@ struct CsrItem {
 // reads run up to 16 slots past the staged chunk (STAGE pad).
 template <bool GS>
 __device__ __forceinline__ double chain_fold(double t, const double2 *sp2, int cnt) {
+#if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 1
+    return t + sp2[0].x * 1e-300;      // timing experiment only: no chain
+#endif
 #define AMGB200_FOLD(v)                                                        \
     _Pragma("unroll") for (int u = 0; u < 4; ++u) {                            \
         if (GS) { t = __dsub_rn(t, v[u].x); t = __dsub_rn(t, v[u].y); }        \
@@ -318,9 +348,18 @@ template <class XA, bool GS>
 __device__ __forceinline__ double csr_chain_run_x(const DMat &A, CsrItem &it, const XA &xa, double t, int lane, double *sprod) {
     if (it.pb >= it.pe) return t;
     double xc[4];
+#ifdef AMGB200_TIMING
+    long long k0 = clock64();
+#endif
 #pragma unroll
     for (int u = 0; u < 4; ++u) xc[u] = (it.j[u] >= 0 && !(GS && it.j[u] == it.k)) ? xa.ld(it.j[u]) : 0.0;
+#ifdef AMGB200_TIMING
+    { double sink = xc[0] + xc[1] + xc[2] + xc[3]; if (sink == 1.2345e300) it.k = -1; it.tg += clock64() - k0; }
+#endif
     for (int base = it.pb; base < it.pe; base += SUPER) {
+#ifdef AMGB200_TIMING
+        long long k2 = clock64();
+#endif
         // stage 1: col/val of super chunk s+2 ; stage 2: x gather of s+1 (its col arrived an iteration ago)
         int jn[4];
         double an[4], xn[4];
@@ -345,7 +384,13 @@ __device__ __forceinline__ double csr_chain_run_x(const DMat &A, CsrItem &it, co
             sprod[u * 32 + lane] = prod;
         }
         __syncwarp();
+#ifdef AMGB200_TIMING
+        long long k3 = clock64(); it.tp += k3 - k2; ++it.nch;
+#endif
         t = chain_fold<GS>(t, reinterpret_cast<const double2 *>(sprod), min(SUPER, it.pe - base));
+#ifdef AMGB200_TIMING
+        { if (t == 1.2345e300) it.k = -1; it.tc += clock64() - k3; }
+#endif
         __syncwarp();
         if (more) {
 #pragma unroll
@@ -362,6 +407,54 @@ __device__ __forceinline__ double csr_diag(const CsrItem &it) {   // exactly one
     const unsigned m = __ballot_sync(FULL, it.dl != 0.0);
     return m ? __shfl_sync(FULL, it.dl, __ffs(m) - 1) : 0.0;
 }
+// Pre-barrier half of the two-phase Gauss-Seidel row: compute the (separately rounded) products of the suffix
+// entries [it.pb, it.pe) with the x values that are already final and park them, in storage order, in `big`.
+// Entries that read the wavefront still in flight ("late", flagged by the host analysis) get a +0.0 placeholder
+// and are appended to the warp's late list {slot, column, value}; after the barrier only those few products are
+// recomputed before the in-order chain runs over `big`.  Returns the number of late entries (warp-uniform),
+// or -1 if the list overflowed (the caller then falls back to streaming the suffix after the barrier).
+constexpr int LATE_CAP = 32;
+template <class XA>
+__device__ __forceinline__ int csr_stage_suffix(const DMat &A, CsrItem &it, const XA &xa, int lane, double *big,
+                                               int *late_slot, int *late_col, double *late_val) {
+    int nlate = 0;
+    const int len = it.pe - it.pb;
+    for (int base = it.pb; base < it.pe; base += SUPER) {
+        int jn[4];
+        double an[4];
+        unsigned ln[4];
+        if (base + 2 * SUPER < it.pe) { it.load_super(A, base + 2 * SUPER, lane, jn, an); it.load_late(A, base + 2 * SUPER, lane, ln); }
+        else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { jn[u] = -1; an[u] = 0.0; ln[u] = 0u; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = base + u * 32 + lane;
+            const int j = it.j[u];
+            bool late = false;
+            double prod = 0.0;
+            if (j >= 0) {
+                late = (it.lw[u] >> (p & 31)) & 1u;
+                if (j == it.k) it.dl = it.a[u];
+                else if (!late) prod = __dmul_rn(it.a[u], xa.ld(j));
+            }
+            if (p < it.pe) big[p - it.pb] = prod;
+            const unsigned m = __ballot_sync(FULL, late);
+            if (m) {
+                const int slot = nlate + __popc(m & ((1u << lane) - 1u));
+                if (late && slot < LATE_CAP) { late_slot[slot] = p - it.pb; late_col[slot] = j; late_val[slot] = it.a[u]; }
+                nlate += __popc(m);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { it.j[u] = it.j1[u]; it.a[u] = it.a1[u]; it.lw[u] = it.lw1[u]; it.j1[u] = jn[u]; it.a1[u] = an[u]; it.lw1[u] = ln[u]; }
+    }
+    if (lane < 24) big[len + lane] = 0.0;          // the chain reads in blocks of 8 and up to 16 slots ahead
+    __syncwarp();
+    return nlate <= LATE_CAP ? nlate : -1;
+}
+
 template <bool COH, bool GS>
 __device__ __forceinline__ double csr_row_exact(const DMat &A, CsrItem &it, const double *x, double t, double &d, int lane, double *sprod) {
     t = csr_chain_run<COH, GS>(A, it, x, t, lane, sprod);
@@ -473,13 +566,20 @@ constexpr int CTA_MAX_WARPS_SELL = 8, CTA_MAX_WARPS_CSR = 16;
 template <int KIND, bool EXACT, bool XS>
 __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA_MAX_WARPS_CSR) gs_ordered_cta_kernel(
     DMat A, const double *__restrict__ b, double *xg, const int *__restrict__ wf_item_ptr, int W, int nsweeps, int G, int D,
-    long long *dbg) {
+    int cap, long long *dbg) {
     extern __shared__ double dyn_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = warp / G, r = warp - grp * G;
     const int n = A.nrows;
     double *x = XS ? dyn_smem : xg;
-    double *sprod = dyn_smem + (XS ? ((n + 1) & ~1) : 0) + warp * STAGE;
+    // per warp: [STAGE streaming slots][cap + 24 parked suffix products][LATE_CAP values][LATE_CAP slots + LATE_CAP columns]
+    const int per_warp = STAGE + (cap ? cap + 24 + LATE_CAP + LATE_CAP : 0);
+    double *sprod = dyn_smem + (XS ? ((n + 1) & ~1) : 0) + warp * per_warp;
+    double *big = sprod + STAGE;
+    double *late_val = big + cap + 24;
+    int *late_slot = reinterpret_cast<int *>(late_val + LATE_CAP);
+    int *late_col = late_slot + LATE_CAP;
+    int nlate = -1;                               // >= 0: the suffix of my row is parked in `big`
     if (XS) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) dyn_smem[i] = xg[i];
         __syncthreads();
@@ -511,18 +611,46 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
     // the warps of one group together before they start reading x for their next wavefront's prefixes.
     const int pair_threads = 2 * G * 32;
     if (my_g < totalw) fetch();
+#ifdef AMGB200_TIMING
+    long long tm_prefix = 0, tm_wait = 0, tm_suffix = 0, tm_post = 0, tm_items = 0, tm_sg = 0, tm_sp = 0, tm_sc = 0, tm_sn = 0;
+#endif
     for (; my_g < totalw; my_g += D) {
+#ifdef AMGB200_TIMING
+        const long long q0 = clock64();
+#endif
         if constexpr (TWO_PHASE) {
             if (have) {
+                const bool park = cap && wc.p1 - wc.ps <= cap && A.late;
+                if (park) wc.suffix_prefetch_late(A, lane);                               // late words of the suffix fly during the prefix chain
                 t_acc = csr_chain_run<false, true>(A, wc, x, wc.bk, lane, sprod);     // prefix [p0, ps)
-                wc.begin_range(A, wc.ps, wc.p1, lane);                                // prefetch the suffix
+                nlate = -1;
+                if (park) {
+                    wc.begin_range(A, wc.ps, wc.p1, lane);
+                    wc.adopt_late();
+                    nlate = csr_stage_suffix(A, wc, GlobalX<false>{x}, lane, big, late_slot, late_col, late_val);
+                }
+                if (nlate < 0) wc.begin_range(A, wc.ps, wc.p1, lane);                 // stream the suffix after the barrier
             }
         }
+#ifdef AMGB200_TIMING
+        if (t_acc == 1.2345e300) ++tm_items;
+        const long long q1 = clock64();
+#endif
         if (my_g > 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + ((my_g - 1) & 7)), "r"(pair_threads) : "memory");
+#ifdef AMGB200_TIMING
+        { volatile double *vs = sprod; if (vs[0] == 1.2345e300) ++tm_items; }
+        const long long q2 = clock64();
+        if (have) ++tm_items;
+#endif
         if (have) {
             if constexpr (KIND == 0) gs_finish_sell<false>(ws, x);
             else if constexpr (TWO_PHASE) {
-                const double t = csr_chain_run<false, true>(A, wc, x, t_acc, lane, sprod);   // suffix [ps, p1)
+                double t;
+                if (nlate >= 0) {                 // patch the few products that needed the wavefront just completed, then fold
+                    if (lane < nlate) big[late_slot[lane]] = __dmul_rn(late_val[lane], x[late_col[lane]]);
+                    __syncwarp();
+                    t = chain_fold<true>(t_acc, reinterpret_cast<const double2 *>(big), wc.p1 - wc.ps);
+                } else t = csr_chain_run<false, true>(A, wc, x, t_acc, lane, sprod);        // suffix [ps, p1), streamed
                 const double d = csr_diag(wc);
                 if (lane == 0 && fabs(d) > GS_TINY) x[wc.k] = __ddiv_rn(t, d);
             } else gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod);
@@ -533,13 +661,24 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
         }
         __threadfence_block();
         if (my_g + 1 < totalw) asm volatile("bar.arrive %0, %1;" ::"r"(1 + (my_g & 7)), "r"(pair_threads) : "memory");
+#ifdef AMGB200_TIMING
+        const long long q3 = clock64();
+#endif
         my_wl += D;
         while (my_wl >= W) my_wl -= W;
         if (my_g + D < totalw) {
             if constexpr (TWO_PHASE) asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");   // whole group done with my_g
             fetch();
         }
+#ifdef AMGB200_TIMING
+        { volatile double *vs = sprod; if (vs[0] == 1.2345e300) ++tm_items; }
+        const long long q4 = clock64();
+        tm_prefix += q1 - q0; tm_wait += q2 - q1; tm_suffix += q3 - q2; tm_post += q4 - q3;
+#endif
     }
+#ifdef AMGB200_TIMING
+    if (dbg && lane == 0) { dbg[warp * 8 + 0] = tm_prefix; dbg[warp * 8 + 1] = tm_wait; dbg[warp * 8 + 2] = tm_suffix; dbg[warp * 8 + 3] = tm_post; dbg[warp * 8 + 4] = tm_items; dbg[warp * 8 + 5] = tm_sg; dbg[warp * 8 + 6] = tm_sp; dbg[warp * 8 + 7] = tm_sc; if (warp == 0) dbg[16 * 8] = tm_sn; }
+#endif
     __syncthreads();
     if (XS) for (int i = threadIdx.x; i < n; i += blockDim.x) xg[i] = dyn_smem[i];
 }
