@@ -86,20 +86,27 @@ void SSS_amg_coarest_solve(amgb200_mat *A, amgb200_vec *b, amgb200_vec *x, const
     amgb200_free(m.h);
 }
 
-static void smoother_dropin(amgb200_smtr *s) {
+static void smoother_dropin(amgb200_smtr *s, bool post) {
     assert(s != NULL);
     if (s->smoother != 2) {                          // SSS_smooth.c:216-218
         printf("### ERROR: Wrong smoother type %d!\n", s->smoother);
         exit(-12);
     }
-    if (!(s->cf_order && s->ordering)) {
-        fprintf(stderr, "libamgb200: natural-order Gauss-Seidel (SSS_smooth.c:90-137) is not implemented yet\n");
-        exit(-12);
+    const bool natural = !(s->cf_order && s->ordering);
+    if (natural) {                                   // SSS_smooth.c:176 / :261: gs(x, 0, n-1, +1) resp. gs(x, n-1, 0, -1)
+        const int n1 = s->A->num_rows - 1;
+        const bool std_pre = !post && s->istart == 0 && s->iend == n1 && s->istep == 1;
+        const bool std_post = post && s->istart == 0 && s->iend == n1 && s->istep == -1;
+        if (!(std_pre || std_post)) {
+            fprintf(stderr, "libamgb200: natural-order smoothing is implemented for the ranges the cycle uses (0..n-1, step +-1)\n");
+            exit(-12);
+        }
     }
     // two levels so that level 0 is a smoothed level; level 1 is a dummy 1x1 system
     int one_ptr[2] = {0, 1}, one_col[1] = {0};
     double one_val[1] = {1.0};
-    MiniHier m(s->A, s->ordering, 2);
+    MiniHier m(s->A, natural ? nullptr : s->ordering, 2);
+    m.mg.pars.cf_order = natural ? 0 : s->cf_order;
     amgb200_mat dummy = {1, 1, 1, one_ptr, one_col, one_val};
     m.comp[1].A = dummy;
     // transfers are never touched by the smoother hook: 1 x n / n x 1 empty operators
@@ -112,11 +119,11 @@ static void smoother_dropin(amgb200_smtr *s) {
     amgb200_options opt;
     amgb200_default_options(&opt);
     m.h = amgb200_upload(&m.mg, &opt);
-    amgb200_level_smooth(m.h, 0, s->nsweeps, s->x->d, s->b->d);
+    amgb200_level_smooth(m.h, 0, post ? -s->nsweeps : s->nsweeps, s->x->d, s->b->d);
     amgb200_free(m.h);
 }
-void SSS_amg_smoother_pre(amgb200_smtr *s) { smoother_dropin(s); }    // SSS_smooth.c:138-220
-void SSS_amg_smoother_post(amgb200_smtr *s) { smoother_dropin(s); }   // SSS_smooth.c:223-304 (same F-then-C order)
+void SSS_amg_smoother_pre(amgb200_smtr *s) { smoother_dropin(s, false); }   // SSS_smooth.c:138-220
+void SSS_amg_smoother_post(amgb200_smtr *s) { smoother_dropin(s, true); }   // SSS_smooth.c:223-304 (C/F: same F-then-C order; natural: backward)
 
 // amg/SSS_utils.c:182-201 and :161-178
 void amgb200_blas_mv_mxy(const amgb200_mat *A, const amgb200_vec *x, amgb200_vec *y) {

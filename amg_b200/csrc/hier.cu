@@ -143,7 +143,7 @@ struct DevMatOwner {
         t_upload() += now_s() - t0;
     }
     void upload_impl(const DevLayout &L) {
-        v.kind = L.kind; v.nrows = L.nrows; v.ncols = L.ncols; v.nitems = L.nitems(); v.max_row = L.max_row;
+        v.kind = L.kind; v.nrows = L.nrows; v.ncols = L.ncols; v.nitems = L.nitems(); v.max_row = L.max_row; v.recip = 0;
         v.slice_row = nullptr; v.slice_ptr = nullptr; v.rptr = nullptr; v.split = nullptr; v.late = nullptr;
         if (L.kind == KIND_SELL) { v.slice_row = dev_upload(L.slice_row); v.slice_ptr = dev_upload(L.slice_ptr); }
         else { v.rptr = dev_upload(L.rptr); if (!L.split.empty()) { v.split = dev_upload(L.split); v.late = dev_upload(L.late); } }
@@ -178,6 +178,9 @@ struct Level {
     int cta_G = 1, cta_D = 1;          // strategy 2: D groups of G warps (pipeline depth D)
     int cta_cap = 0;                   // strategy 2, two-phase rows: parked suffix products per warp (0 = stream the suffix)
     int dsmem_sh = 0;                  // strategy 3: x distributed over the cluster's shared memory, 2^sh rows per CTA (0 = x in global memory)
+    bool natural = false;              // natural-order Gauss-Seidel (cf_order = 0 or no cfmark): forward sweeps use this level's
+    Level *bk = nullptr;               // schedule, backward sweeps (post-smoothing) the schedule/layout/vectors of *bk
+    int *d_fb = nullptr;               // position in this level's numbering of row k of bk's numbering
 };
 
 }  // namespace
@@ -386,12 +389,25 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
     ++g_launches;
 }
 
-void smooth(amgb200_hier *h, int l, int nsweeps) {
-    Level &lv = h->L[l];
-    if (nsweeps <= 0) return;
+void smooth_level(amgb200_hier *h, Level &lv, int nsweeps) {
     if (lv.A.v.kind == KIND_SELL) smooth_k<0, true>(h, lv, nsweeps);
     else if (h->exact) smooth_k<1, true>(h, lv, nsweeps);
     else smooth_k<1, false>(h, lv, nsweeps);
+}
+// pre-smoothing (post = false) or post-smoothing.  With C/F ordering both run the same F-then-C sweeps
+// (SSS_smooth.c:16: only `if (order)` is tested); in natural order the post-smoother runs backwards (:122-134).
+void smooth(amgb200_hier *h, int l, int nsweeps, bool post = false) {
+    Level &lv = h->L[l];
+    if (nsweeps <= 0) return;
+    if (lv.natural && post) {
+        Level &bk = *lv.bk;
+        LAUNCH(gather_idx_kernel, grid_for(lv.n), BLOCK, h->stream, lv.n, lv.d_fb, lv.x, bk.x);
+        LAUNCH(gather_idx_kernel, grid_for(lv.n), BLOCK, h->stream, lv.n, lv.d_fb, lv.b, bk.b);
+        smooth_level(h, bk, nsweeps);
+        LAUNCH(scatter_idx_kernel, grid_for(lv.n), BLOCK, h->stream, lv.n, lv.d_fb, bk.x, lv.x);
+        return;
+    }
+    smooth_level(h, lv, nsweeps);
 }
 
 // ---- coarsest-level Krylov solvers (host control flow, device vectors) ---------------------
@@ -654,7 +670,7 @@ void cycle_from(amgb200_hier *h, int lstart) {
             l--;
             Level &lv = h->L[l];
             { PhaseTimer pt(h, 3, l); spmv(h, lv.P.v, MODE_AMXPY, RED_NONE, h->L[l + 1].x, lv.x, nullptr, 1.0); }
-            { PhaseTimer pt(h, 0, l); smooth(h, l, h->pars.post_iter); }
+            { PhaseTimer pt(h, 0, l); smooth(h, l, h->pars.post_iter, true); }
             if (visits[l] < cycle_type) break;
             visits[l] = 0;
             if (l == lstart) break;
@@ -761,13 +777,32 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     h->L.resize(nl);
     std::vector<Schedule> sched(nl);
     int maxn = 0;
-    for (int l = 0; l + 1 < nl; ++l)
-        if (!(mg->pars.cf_order && mg->cg[l].cfmark.d)) {
-            fprintf(stderr, "libamgb200: natural-order Gauss-Seidel (cf_order=0 / no cfmark, SSS_smooth.c:90-137) is not implemented yet\n");
-            exit(-12);
-        }
+    // natural-order Gauss-Seidel (SSS_smooth.c:90-137) when cf_order = 0 or a level has no C/F marks (SSS_smooth.c:171-176):
+    // forward sweeps before, backward sweeps after the coarse-grid correction -> a second (reversed) schedule per level
+    std::vector<Schedule> sched_b(nl);
+    std::vector<char> natural(nl, 0);
+    for (int l = 0; l + 1 < nl; ++l) natural[l] = !(mg->pars.cf_order && mg->cg[l].cfmark.d);
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int l = 0; l < nl - 1; ++l) build_schedule(mg->cg[l].A, mg->cg[l].cfmark.d, sched[l]);   // levels are independent
+    for (int l = 0; l < nl - 1; ++l) {                                                              // levels are independent
+        const amgb200_mat &A = mg->cg[l].A;
+        build_schedule(A, natural[l] ? nullptr : mg->cg[l].cfmark.d, sched[l]);
+        if (natural[l]) {
+            const int n = A.num_rows;                                                               // the matrix seen from the last row backwards
+            std::vector<int> rp((size_t)n + 1, 0), ci((size_t)A.num_nnzs);
+            for (int i = 0; i < n; ++i) rp[i + 1] = rp[i] + (A.row_ptr[n - i] - A.row_ptr[n - 1 - i]);
+            for (int i = 0; i < n; ++i) {
+                const int src = A.row_ptr[n - 1 - i];
+                for (int q = 0; q < rp[i + 1] - rp[i]; ++q) ci[rp[i] + q] = n - 1 - A.col_idx[src + q];
+            }
+            amgb200_mat Arev = {n, n, A.num_nnzs, rp.data(), ci.data(), A.val};
+            Schedule R;
+            build_schedule(Arev, nullptr, R);
+            Schedule &B = sched_b[l];
+            B = R;
+            for (int k = 0; k < n; ++k) B.order[k] = n - 1 - R.order[k];
+            for (int i = 0; i < n; ++i) B.pos[i] = R.pos[n - 1 - i];
+        }
+    }
     for (int l = 0; l < nl; ++l) {
         const amgb200_comp &c = mg->cg[l];
         if (l < nl - 1) {
@@ -786,6 +821,62 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     double t_layout = 0;
 
     int max_items = 1;
+    // wavefront tables and launch strategy of one level's smoother (used for the level itself and, in natural
+    // order, for its backward twin)
+    auto setup_smoother = [&](Level &lv, const DevLayout &lay, const Schedule &S) {
+    lv.W = S.wf_count[0] + S.wf_count[1];
+    lv.wf_count[0] = S.wf_count[0]; lv.wf_count[1] = S.wf_count[1];
+    lv.pass_rows[0] = S.pass_rows[0]; lv.pass_rows[1] = S.pass_rows[1];
+    lv.ordered = S.wf_count[0] > 1 || S.wf_count[1] > 1;
+    const std::vector<int> &wip = lay.wf_item_ptr;
+    lv.pass_items[0] = wip[S.wf_count[0]] - wip[0];
+    lv.pass_items[1] = wip[lv.W] - wip[S.wf_count[0]];
+    std::vector<int> item_wf((size_t)wip[lv.W]);
+    lv.max_width = 1;
+    for (int w = 0; w < lv.W; ++w) {
+        lv.max_width = std::max(lv.max_width, wip[w + 1] - wip[w]);
+        for (int it = wip[w]; it < wip[w + 1]; ++it) item_wf[it] = w;
+    }
+    lv.d_item_wf = dev_upload(item_wf);
+    lv.d_wf_item_ptr = dev_upload(wip);
+    // 0 parallel passes | 2 one CTA (narrow wavefronts) | 3 one 16-CTA cluster | 1 cooperative grid (fallback)
+    if (!lv.ordered) lv.strategy = 0;
+    else lv.strategy = ((double)wip[lv.W] / lv.W <= cta_max_avg) ? 2 : 3;
+    {
+        const int maxw = lay.kind == KIND_SELL ? CTA_MAX_WARPS_SELL : CTA_MAX_WARPS_CSR;
+        const double avg = (double)wip[lv.W] / lv.W;
+        (void)avg;
+        int G = std::max(1, std::min(lv.max_width, maxw / 2));
+        if (getenv("AMGB200_CTA_G")) G = std::max(1, std::min(maxw, atoi(getenv("AMGB200_CTA_G"))));
+        G = std::min(G, maxw / 2);                 // the producer/consumer barrier scheme needs >= 2 groups
+        lv.cta_G = G;
+        lv.cta_D = std::max(2, maxw / G);
+        if (getenv("AMGB200_CTA_D")) lv.cta_D = std::max(2, std::min(maxw / G, atoi(getenv("AMGB200_CTA_D"))));
+        // the prefix/suffix scheme of the warp-per-row EXACT kernel folds a row's prefix while exactly ONE earlier
+        // wavefront is still in flight: two alternating groups
+        if (lay.kind == KIND_CSR && h->exact) lv.cta_D = 2;
+        const int nwarps = lv.cta_G * lv.cta_D;
+        const size_t xb = (size_t)((lv.n + 1) & ~1) * 8, stb = (size_t)nwarps * STAGE * 8;
+        lv.x_in_smem = lv.strategy == 2 && xb + stb <= (size_t)h->max_dyn_smem && !(getenv("AMGB200_NO_SMEM_X") && atoi(getenv("AMGB200_NO_SMEM_X")));
+        if (lv.strategy == 2 && lay.kind == KIND_CSR && h->exact && !(getenv("AMGB200_NO_PARK") && atoi(getenv("AMGB200_NO_PARK")))) {
+            // park the whole suffix of a row (its products) in shared memory before the barrier when it fits
+            int cap = std::min(1024, (lay.max_row + 31) / 32 * 32);
+            const size_t base = (lv.x_in_smem ? xb : 0) + stb;
+            while (cap >= 128 && base + (size_t)nwarps * (cap + 24 + 2 * LATE_CAP) * 8 > (size_t)h->max_dyn_smem) cap -= 128;
+            lv.cta_cap = cap >= 128 ? cap : 0;
+        }
+    }
+    // measured on B200 (128^3, levels 2-4): scattered 8-byte remote shared-memory gathers are SLOWER than L2 gathers
+    // (5.0 / 2.8 / 4.8 ms per sweep vs 2.8 / 2.3 / 4.5 ms), so the distributed-x variant is opt-in only
+    if (lv.strategy == 3 && lay.kind == KIND_CSR && h->exact && getenv("AMGB200_DSMEM_X") && atoi(getenv("AMGB200_DSMEM_X"))) {
+        int sh = 6;
+        while (((long long)CLUSTER_CTAS << sh) < lv.n) ++sh;
+        const int nwc = std::max(1, std::min(CLUSTER_WARPS_CSR, (lv.max_width + CLUSTER_CTAS - 1) / CLUSTER_CTAS));
+        if (((size_t)1 << sh) * 8 + (size_t)nwc * STAGE * 8 <= (size_t)h->max_dyn_smem) lv.dsmem_sh = sh;
+    }
+    if (getenv("AMGB200_GS_STRATEGY") && lv.ordered) lv.strategy = std::max(1, std::min(3, atoi(getenv("AMGB200_GS_STRATEGY"))));
+    };
+
     for (int l = 0; l < nl; ++l) {
         const amgb200_comp &c = mg->cg[l];
         Level &lv = h->L[l];
@@ -817,57 +908,27 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         CUDA_CHECK(cudaMemset(lv.b, 0, (size_t)lv.n * sizeof(double)));
         lv.pattern_symmetric = S.pattern_symmetric;
         if (lv.smoothed) {
-            lv.W = S.wf_count[0] + S.wf_count[1];
-            lv.wf_count[0] = S.wf_count[0]; lv.wf_count[1] = S.wf_count[1];
-            lv.pass_rows[0] = S.pass_rows[0]; lv.pass_rows[1] = S.pass_rows[1];
-            lv.ordered = S.wf_count[0] > 1 || S.wf_count[1] > 1;
-            const std::vector<int> &wip = lay.wf_item_ptr;
-            lv.pass_items[0] = wip[S.wf_count[0]] - wip[0];
-            lv.pass_items[1] = wip[lv.W] - wip[S.wf_count[0]];
-            std::vector<int> item_wf((size_t)wip[lv.W]);
-            lv.max_width = 1;
-            for (int w = 0; w < lv.W; ++w) {
-                lv.max_width = std::max(lv.max_width, wip[w + 1] - wip[w]);
-                for (int it = wip[w]; it < wip[w + 1]; ++it) item_wf[it] = w;
+            setup_smoother(lv, lay, S);
+            if (natural[l]) {
+                // backward sweeps: own schedule, layout and vectors; d_fb maps its numbering into this level's
+                lv.natural = true;
+                lv.A.v.recip = 1;
+                const Schedule &B = sched_b[l];
+                Level *bk = new Level();
+                lv.bk = bk;
+                bk->n = lv.n; bk->smoothed = true; bk->natural = true;
+                DevLayout lb;
+                { const double tl = now_s(); build_layout(c.A, B.order.data(), B.pos.data(), gs_kind, &B.wf_row_ptr, lb); t_layout += now_s() - tl; }
+                bk->A.upload(lb);
+                bk->A.v.recip = 1;
+                max_items = std::max(max_items, lb.nitems());
+                bk->x = dev_alloc<double>(lv.n);
+                bk->b = dev_alloc<double>(lv.n);
+                setup_smoother(*bk, lb, B);
+                std::vector<int> fb((size_t)lv.n);
+                for (int k = 0; k < lv.n; ++k) fb[k] = S.pos[B.order[k]];
+                lv.d_fb = dev_upload(fb);
             }
-            lv.d_item_wf = dev_upload(item_wf);
-            lv.d_wf_item_ptr = dev_upload(wip);
-            // 0 parallel passes | 2 one CTA (narrow wavefronts) | 3 one 16-CTA cluster | 1 cooperative grid (fallback)
-            if (!lv.ordered) lv.strategy = 0;
-            else lv.strategy = ((double)wip[lv.W] / lv.W <= cta_max_avg) ? 2 : 3;
-            {
-                const int maxw = lay.kind == KIND_SELL ? CTA_MAX_WARPS_SELL : CTA_MAX_WARPS_CSR;
-                const double avg = (double)wip[lv.W] / lv.W;
-                (void)avg;
-                int G = std::max(1, std::min(lv.max_width, maxw / 2));
-                if (getenv("AMGB200_CTA_G")) G = std::max(1, std::min(maxw, atoi(getenv("AMGB200_CTA_G"))));
-                G = std::min(G, maxw / 2);                 // the producer/consumer barrier scheme needs >= 2 groups
-                lv.cta_G = G;
-                lv.cta_D = std::max(2, maxw / G);
-                if (getenv("AMGB200_CTA_D")) lv.cta_D = std::max(2, std::min(maxw / G, atoi(getenv("AMGB200_CTA_D"))));
-                // the prefix/suffix scheme of the warp-per-row EXACT kernel folds a row's prefix while exactly ONE earlier
-                // wavefront is still in flight: two alternating groups
-                if (lay.kind == KIND_CSR && h->exact) lv.cta_D = 2;
-                const int nwarps = lv.cta_G * lv.cta_D;
-                const size_t xb = (size_t)((lv.n + 1) & ~1) * 8, stb = (size_t)nwarps * STAGE * 8;
-                lv.x_in_smem = lv.strategy == 2 && xb + stb <= (size_t)h->max_dyn_smem && !(getenv("AMGB200_NO_SMEM_X") && atoi(getenv("AMGB200_NO_SMEM_X")));
-                if (lv.strategy == 2 && lay.kind == KIND_CSR && h->exact && !(getenv("AMGB200_NO_PARK") && atoi(getenv("AMGB200_NO_PARK")))) {
-                    // park the whole suffix of a row (its products) in shared memory before the barrier when it fits
-                    int cap = std::min(1024, (lay.max_row + 31) / 32 * 32);
-                    const size_t base = (lv.x_in_smem ? xb : 0) + stb;
-                    while (cap >= 128 && base + (size_t)nwarps * (cap + 24 + 2 * LATE_CAP) * 8 > (size_t)h->max_dyn_smem) cap -= 128;
-                    lv.cta_cap = cap >= 128 ? cap : 0;
-                }
-            }
-            // measured on B200 (128^3, levels 2-4): scattered 8-byte remote shared-memory gathers are SLOWER than L2 gathers
-            // (5.0 / 2.8 / 4.8 ms per sweep vs 2.8 / 2.3 / 4.5 ms), so the distributed-x variant is opt-in only
-            if (lv.strategy == 3 && lay.kind == KIND_CSR && h->exact && getenv("AMGB200_DSMEM_X") && atoi(getenv("AMGB200_DSMEM_X"))) {
-                int sh = 6;
-                while (((long long)CLUSTER_CTAS << sh) < lv.n) ++sh;
-                const int nwc = std::max(1, std::min(CLUSTER_WARPS_CSR, (lv.max_width + CLUSTER_CTAS - 1) / CLUSTER_CTAS));
-                if (((size_t)1 << sh) * 8 + (size_t)nwc * STAGE * 8 <= (size_t)h->max_dyn_smem) lv.dsmem_sh = sh;
-            }
-            if (getenv("AMGB200_GS_STRATEGY") && lv.ordered) lv.strategy = std::max(1, std::min(3, atoi(getenv("AMGB200_GS_STRATEGY"))));
             // transfers: P_l rows in this level's schedule, columns in the next level's; R_l the other way round
             DevLayout lp, lr;
             { const double tl = now_s(); build_layout(c.P, S.order.data(), sched[l + 1].pos.data(), kind_of(c.P), nullptr, lp); t_layout += now_s() - tl; }
@@ -908,7 +969,13 @@ void amgb200_free(amgb200_hier *h) {
     for (Level &lv : h->L) {
         lv.A.release(); lv.Asp.release(); lv.P.release(); lv.R.release();
         dev_free(lv.d_order); dev_free(lv.x); dev_free(lv.b); dev_free(lv.wp);
-        dev_free(lv.d_item_wf); dev_free(lv.d_wf_item_ptr); dev_free(lv.d_cnt);
+        dev_free(lv.d_item_wf); dev_free(lv.d_wf_item_ptr); dev_free(lv.d_cnt); dev_free(lv.d_fb);
+        if (lv.bk) {
+            lv.bk->A.release();
+            dev_free(lv.bk->x); dev_free(lv.bk->b);
+            dev_free(lv.bk->d_item_wf); dev_free(lv.bk->d_wf_item_ptr); dev_free(lv.bk->d_cnt);
+            delete lv.bk;
+        }
     }
     dev_free(h->d_partial); dev_free(h->d_scal); cudaFreeHost(h->h_scal);
     dev_free(h->d_xnat); dev_free(h->d_bnat); dev_free(h->kry); dev_free(h->d_dbg);
@@ -1101,7 +1168,7 @@ void amgb200_level_smooth(amgb200_hier *h, int level, int nsweeps, double *x, co
     CUDA_CHECK(cudaMemcpyAsync(h->d_bnat, b, (size_t)lv.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     to_schedule(h, level, h->d_xnat, lv.x);
     to_schedule(h, level, h->d_bnat, lv.b);
-    smooth(h, level, nsweeps);
+    smooth(h, level, nsweeps < 0 ? -nsweeps : nsweeps, nsweeps < 0);
     to_natural(h, level, lv.x, h->d_xnat);
     CUDA_CHECK(cudaMemcpyAsync(x, h->d_xnat, (size_t)lv.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));

@@ -24,6 +24,7 @@ namespace amgb200 {
 
 struct DMat {                      // device view of a DevLayout
     int kind, nrows, ncols, nitems, max_row;
+    int recip;                     // Gauss-Seidel update x = t * (1/d) (natural-order smoother, SSS_smooth.c:112-118) instead of t / d
     const int *slice_row;          // SELL
     const long long *slice_ptr;    // SELL
     const int *rptr;               // CSR
@@ -44,6 +45,11 @@ constexpr unsigned FULL = 0xffffffffu;
 // COH: x is being updated by other SMs during this launch -> read it at L2 (L1 is not coherent)
 template <bool COH>
 __device__ __forceinline__ double ld_x(const double *p) { return COH ? __ldcg(p) : *p; }
+
+// x_i from the accumulated t and the diagonal d: t / d (SSS_smooth.c:32) or t * (1/d) (SSS_smooth.c:112-118)
+__device__ __forceinline__ double gs_quotient(double t, double d, int recip) {
+    return recip ? __dmul_rn(t, __ddiv_rn(1.0, d)) : __ddiv_rn(t, d);
+}
 
 // where the x vector of a level lives during a launch
 template <bool COH>
@@ -106,7 +112,7 @@ template <int SCH>
 struct SellItem {
     const int *cp;
     const double *vp;
-    int width, k, r1;
+    int width, k, r1, recip;
     int j[SCH];
     double a[SCH];
     double bk;
@@ -128,6 +134,7 @@ struct SellItem {
     // stage 2: first chunk of matrix entries and the right-hand side
     __device__ __forceinline__ void load_entries(const DMat &A, const Desc &d, int lane, const double *__restrict__ b) {
         r1 = d.r1;
+        recip = A.recip;
         width = (int)((d.p1 - d.p0) >> 5);
         k = d.r0 + lane;
         cp = A.col + d.p0 + lane;
@@ -155,7 +162,7 @@ __device__ __forceinline__ void gs_finish_sell_one(SellItem<SCH> &it, double *x)
         if (it.j[u] == it.k) d = it.a[u];
         else if (it.j[u] >= 0) t = __dsub_rn(t, __dmul_rn(it.a[u], xv[u]));
     }
-    if (it.k < it.r1 && fabs(d) > GS_TINY) x[it.k] = __ddiv_rn(t, d);
+    if (it.k < it.r1 && fabs(d) > GS_TINY) x[it.k] = gs_quotient(t, d, it.recip);
 }
 template <int SCH>
 __device__ __forceinline__ double spmv_finish_sell_one(SellItem<SCH> &it, const double *__restrict__ x) {
@@ -197,7 +204,7 @@ __device__ __forceinline__ void gs_finish_sell(SellItem<SCH> &it, double *x) {
             for (int u = 0; u < SCH; ++u) { it.j[u] = jn[u]; it.a[u] = an[u]; }
         }
     }
-    if (active && fabs(d) > GS_TINY) x[it.k] = __ddiv_rn(t, d);
+    if (active && fabs(d) > GS_TINY) x[it.k] = gs_quotient(t, d, it.recip);
 }
 
 // row sum t = sum_k a_k x_{j_k} from 0.0 in storage order (amg/SSS_utils.c:169-177, :190-200)
@@ -486,7 +493,7 @@ template <bool COH, bool EXACT>
 __device__ __forceinline__ void gs_finish_csr(const DMat &A, CsrItem &it, double *x, int lane, double *sprod) {
     double d;
     const double t = EXACT ? csr_row_exact<COH, true>(A, it, x, it.bk, d, lane, sprod) : csr_row_fast<COH, true>(A, it, x, it.bk, d, lane);
-    if (lane == 0 && fabs(d) > GS_TINY) x[it.k] = __ddiv_rn(t, d);
+    if (lane == 0 && fabs(d) > GS_TINY) x[it.k] = gs_quotient(t, d, A.recip);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -652,7 +659,7 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
                     t = chain_fold<true>(t_acc, reinterpret_cast<const double2 *>(big), wc.p1 - wc.ps);
                 } else t = csr_chain_run<false, true>(A, wc, x, t_acc, lane, sprod);        // suffix [ps, p1), streamed
                 const double d = csr_diag(wc);
-                if (lane == 0 && fabs(d) > GS_TINY) x[wc.k] = __ddiv_rn(t, d);
+                if (lane == 0 && fabs(d) > GS_TINY) x[wc.k] = gs_quotient(t, d, A.recip);
             } else gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod);
             for (int it = i0 + r + G; it < i1; it += G) {              // wavefront wider than the group
                 if constexpr (KIND == 0) { ws.prologue(A, it, lane, b); gs_finish_sell<false>(ws, x); }
@@ -793,7 +800,7 @@ __global__ void __launch_bounds__(32 * CLUSTER_WARPS_CSR) gs_ordered_cluster_dsm
     auto finish = [&](CsrItem &w) {
         const double t = EXACT ? csr_chain_run_x<ClusterX, true>(A, w, xa, w.bk, lane, sp) : 0.0;
         const double d = csr_diag(w);
-        if (lane == 0 && fabs(d) > GS_TINY) xa.st(w.k, __ddiv_rn(t, d));
+        if (lane == 0 && fabs(d) > GS_TINY) xa.st(w.k, gs_quotient(t, d, A.recip));
     };
     int wl2 = 2 % W;
     int a0 = wf_item_ptr[0], a1 = wf_item_ptr[1];
@@ -979,6 +986,15 @@ __global__ void __launch_bounds__(BLOCK) gather_kernel(int n, const int *__restr
 __global__ void __launch_bounds__(BLOCK) scatter_kernel(int n, const int *__restrict__ order, const double *__restrict__ in, double *out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) out[order[k]] = in[k];
+}
+// the same two moves between the forward and the backward numbering of a natural-order level
+__global__ void __launch_bounds__(BLOCK) gather_idx_kernel(int n, const int *__restrict__ idx, const double *__restrict__ in, double *out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = in[idx[k]];
+}
+__global__ void __launch_bounds__(BLOCK) scatter_idx_kernel(int n, const int *__restrict__ idx, const double *__restrict__ in, double *out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[idx[k]] = in[k];
 }
 
 }  // namespace amgb200

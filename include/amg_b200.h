@@ -162,7 +162,9 @@ void amgb200_cycle(amgb200_hier *h, double *x, const double *b);
  *   which: 0 = A_l, 1 = P_l (coarse -> fine), 2 = R_l (fine -> coarse)
  *   y = beta*y + alpha * M x   with beta in {0,1}  (beta=0: SSS_blas_mv_mxy, beta=1: _amxpy) */
 void amgb200_level_spmv(amgb200_hier *h, int level, int which, double alpha, const double *x, int beta, double *y);
-/* nsweeps C/F-ordered Gauss-Seidel sweeps (SSS_smooth.c:4-87, order != 0 branch) on level l */
+/* |nsweeps| Gauss-Seidel sweeps on level l as the cycle applies them: C/F-ordered (SSS_smooth.c:4-87, order != 0 branch)
+ * or, when the hierarchy was set up with cf_order = 0, natural order (SSS_smooth.c:90-137): nsweeps > 0 = pre-smoothing
+ * (forward), nsweeps < 0 = post-smoothing (backward) */
 void amgb200_level_smooth(amgb200_hier *h, int level, int nsweeps, double *x, const double *b);
 /* r = b - A_l x, returns ||r||_2 */
 double amgb200_level_residual(amgb200_hier *h, int level, const double *x, const double *b, double *r);

@@ -48,6 +48,7 @@ class Oracle:
         L.orc_mv_mxy.argtypes = [C.POINTER(capi.Mat), dp, dp]
         L.orc_mv_amxpy.argtypes = [C.c_double, C.POINTER(capi.Mat), dp, dp]
         L.orc_gs_cf.argtypes = [dp, C.POINTER(capi.Mat), dp, C.c_int, ip, C.c_int]
+        L.orc_gs.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.POINTER(capi.Mat), dp, C.c_int]
         L.orc_cg.restype = C.c_int
         L.orc_cg.argtypes = [C.POINTER(capi.Mat), dp, dp, C.c_double, C.c_int, C.c_int]
         L.orc_gmres.restype = C.c_int
@@ -78,6 +79,17 @@ class Oracle:
         bb = np.ascontiguousarray(b, np.float64)
         mk = np.ascontiguousarray(mark, np.int32)
         self.L.orc_gs_cf(capi.dptr(x), C.byref(mat), capi.dptr(bb), sweeps, capi.iptr(mk), order)
+        return x
+
+    def gs_natural(self, mat, x0, b, sweeps, backward=False):
+        """SSS_smooth.c:90-137 as the cycle calls it: forward 0..n-1 (pre) or backward n-1..0 (post)"""
+        x = np.array(x0, np.float64, copy=True)
+        bb = np.ascontiguousarray(b, np.float64)
+        n = mat.num_rows
+        if backward:
+            self.L.orc_gs(capi.dptr(x), n - 1, 0, -1, C.byref(mat), capi.dptr(bb), sweeps)
+        else:
+            self.L.orc_gs(capi.dptr(x), 0, n - 1, 1, C.byref(mat), capi.dptr(bb), sweeps)
         return x
 
     def coarse_solve(self, mat, x0, b, tol, beta_mode=0):

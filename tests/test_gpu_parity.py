@@ -227,6 +227,46 @@ def test_w_cycle(oracle):
     assert (np.abs(hist - hist_o) / hist_o).max() <= RTOL_HISTORY
 
 
+@pytest.mark.parametrize("name", ["p2d64", "p3d16", "v27_12"])
+def test_natural_order_gauss_seidel(name, oracle):
+    """cf_order = 0: forward sweeps before, backward sweeps after the correction, x = t * (1/d)
+    (amg/Solve/SSS_smooth.c:90-137, reached through :176 and :261) -- every level, then whole solves"""
+    kind, N, eps = CASES[name]
+    A = generate(kind, N, eps)
+    hier = HostHierarchy(A, tol=1e-8, cf_order=0)
+    dev = DeviceHierarchy(hier)
+    for l in range(hier.num_levels - 1):
+        c = hier.level(l)
+        n = c.A.num_rows
+        x0, b = rng_vec(n, 200 + l), rng_vec(n, 300 + l)
+        for sweeps, backward in ((2, False), (2, True), (1, True)):
+            got = dev.smooth(l, -sweeps if backward else sweeps, x0, b)
+            want = oracle.gs_natural(c.A, x0, b, sweeps, backward)
+            assert got.tobytes() == want.tobytes(), f"natural GS level {l} backward={backward}: rel err {rel_err(got, want):.3e}"
+    n = A.nrows
+    rtn, x, hist = dev.solve(np.ones(n), np.ones(n))
+    rtn_o, x_o, hist_o = oracle.solve(hier, np.ones(n), np.ones(n), 0)
+    assert rtn.nits == rtn_o.nits
+    assert (np.abs(hist - hist_o) / hist_o).max() <= RTOL_HISTORY
+    assert x.tobytes() == x_o.tobytes()
+    dev.close()
+
+
+def test_natural_order_oracle_matches_reference(oracle, reference):
+    """pins the oracle's natural-order path against the reference's own objects"""
+    import ctypes as C
+    A = generate("p3d", 10)
+    pars = capi.default_pars(1e-8)
+    pars.cf_order = 0
+    mg = reference.setup(A, pars)
+    n = A.nrows
+    x_ref, hist_ref = reference.solve_history(mg, np.ones(n), np.ones(n), 1e-8)
+    reference.destroy(mg)
+    hier = HostHierarchy(A, tol=1e-8, cf_order=0)
+    rtn, x, hist = oracle.solve(hier, np.ones(n), np.ones(n), 0)
+    assert list(hist) == list(hist_ref) and x.tobytes() == x_ref.tobytes()
+
+
 def test_random_rhs_and_initial_guess(oracle):
     A, hier, dev = case("p3d16")
     n = A.nrows
