@@ -309,6 +309,18 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
             CUDA_CHECK(cudaStreamSynchronize(h->stream));
             CUDA_CHECK(cudaMemcpy(hd, h->d_dbg, sizeof(hd), cudaMemcpyDeviceToHost));
             printf("[dbg] CTA kernel level n=%d G=%d D=%d W=%d sweeps=%d  warp0 suffix chunks %lld\n", lv.n, G, D, lv.W, nsweeps, hd[16 * 8]);
+#ifdef AMGB200_TIMELINE
+            {
+                const char *nm[14] = {"prefix chain", "stage suffix", "bar.sync(prev wavefront)", "patch late", "suffix chain", "diag+div+store", "fence+arrive", "group barrier", "fetch", "L1 prefetch", "prefix load wait", "suffix begin issue", "suffix load wait", "-"};
+                const int iters = (lv.W * nsweeps + 1) / 2;
+                for (int g2 = 0; g2 < 2; ++g2) {
+                    printf("   timeline group %d warp 0 (cycles per wavefront of this group, %d wavefronts):", g2, iters);
+                    long long tot = 0;
+                    for (int i = 0; i < 13; ++i) { printf("  %s %lld", nm[i], hd[g2 * 16 + i] / iters); tot += hd[g2 * 16 + i]; }
+                    printf("  | total %lld\n", tot / iters);
+                }
+            }
+#endif
             for (int w = 0; w < nw; ++w) printf("   warp %2d: prefix %9lld  wait %9lld  suffix %9lld  post(group barrier+fetch) %9lld  items %6lld | suffix: gather %8lld prod %8lld chain %8lld\n", w, hd[w*8], hd[w*8+1], hd[w*8+2], hd[w*8+3], hd[w*8+4], hd[w*8+5], hd[w*8+6], hd[w*8+7]);
         }
         CUDA_CHECK(cudaGetLastError());

@@ -309,6 +309,19 @@ struct CsrItem {
     }
 };
 
+// pull the col/val (and late-flag) lines of the rows [i0, i1) towards this SM's L1: the warps of a group do this for
+// the wavefront after their next one, so that the dependent loads of fetch() and the chunk stream of the rows hit
+// L1 (~70 cycles) instead of L2 (~450) when their turn comes
+__device__ __forceinline__ void csr_prefetch_rows(const DMat &A, int i0, int i1, int lane, int worker, int nworkers) {
+    for (int row = i0 + worker; row < i1; row += nworkers) {
+        const int p0 = A.rptr[row], p1 = A.rptr[row + 1];
+        for (int p = p0 + lane * 16; p < p1; p += 32 * 16) {          // one touch per 128-byte line of val, every other line of col
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(A.val + p));
+            if ((lane & 1) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.col + p));
+        }
+    }
+}
+
 // fold `cnt` staged products into t in order: 8-term blocks, ping-pong registers; the LDS.128 of the next
 // block are issued before the chain of the current one, and the __syncwarp between them keeps ptxas from
 // sinking the loads next to their uses (which would expose ~30 cycles of shared-memory latency every few
@@ -421,41 +434,69 @@ __device__ __forceinline__ double csr_diag(const CsrItem &it) {   // exactly one
 // recomputed before the in-order chain runs over `big`.  Returns the number of late entries (warp-uniform),
 // or -1 if the list overflowed (the caller then falls back to streaming the suffix after the barrier).
 constexpr int LATE_CAP = 32;
+// one super chunk of the staging loop: `cur` holds the chunk at `base`, the loads of the chunk two ahead go into
+// the free buffer.  The three buffers change roles at compile time (see csr_stage_suffix): a register that a load
+// in flight will write is never moved, so nothing here waits for the loads this step issues.
+template <class XA>
+__device__ __forceinline__ void csr_stage_step(const DMat &A, CsrItem &it, const XA &xa, int lane, double *big, int *late_slot,
+                                               int *late_col, double *late_val, int base, int &nlate,
+                                               const int (&cj)[4], const double (&ca)[4], const unsigned (&cl)[4],
+                                               int (&fj)[4], double (&fa)[4], unsigned (&fl)[4]) {
+    it.load_super(A, base + 2 * SUPER, lane, fj, fa);
+    it.load_late(A, base + 2 * SUPER, lane, fl);
+    // all four gathers in flight together, no divergent region between them; the (rare) late entries are
+    // collected afterwards
+    bool late[4];
+    double xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int p = base + u * 32 + lane;
+        const int j = cj[u];
+        late[u] = j >= 0 && ((cl[u] >> (p & 31)) & 1u);
+        const bool use = j >= 0 && j != it.k && !late[u];
+        xv[u] = use ? xa.ld(j) : 0.0;
+        if (j >= 0 && j == it.k) it.dl = ca[u];
+    }
+    unsigned any = 0u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int p = base + u * 32 + lane;
+        const int j = cj[u];
+        const bool use = j >= 0 && j != it.k && !late[u];
+        if (p < it.pe) big[p - it.pb] = use ? __dmul_rn(ca[u], xv[u]) : 0.0;
+        any |= late[u] ? 1u << u : 0u;
+    }
+    if (__any_sync(FULL, any != 0u)) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned m = __ballot_sync(FULL, late[u]);
+            if (m) {
+                const int slot = nlate + __popc(m & ((1u << lane) - 1u));
+                if (late[u] && slot < LATE_CAP) { late_slot[slot] = base + u * 32 + lane - it.pb; late_col[slot] = cj[u]; late_val[slot] = ca[u]; }
+                nlate += __popc(m);
+            }
+        }
+    }
+}
 template <class XA>
 __device__ __forceinline__ int csr_stage_suffix(const DMat &A, CsrItem &it, const XA &xa, int lane, double *big,
                                                int *late_slot, int *late_col, double *late_val) {
     int nlate = 0;
     const int len = it.pe - it.pb;
-    for (int base = it.pb; base < it.pe; base += SUPER) {
-        int jn[4];
-        double an[4];
-        unsigned ln[4];
-        if (base + 2 * SUPER < it.pe) { it.load_super(A, base + 2 * SUPER, lane, jn, an); it.load_late(A, base + 2 * SUPER, lane, ln); }
-        else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { jn[u] = -1; an[u] = 0.0; ln[u] = 0u; }
+    if (len > 0) {
+        int j2[4];
+        double a2[4];
+        unsigned lw2[4];
+        int base = it.pb;
+#pragma unroll 1
+        for (;;) {
+            csr_stage_step(A, it, xa, lane, big, late_slot, late_col, late_val, base, nlate, it.j, it.a, it.lw, j2, a2, lw2);
+            base += SUPER; if (base >= it.pe) break;
+            csr_stage_step(A, it, xa, lane, big, late_slot, late_col, late_val, base, nlate, it.j1, it.a1, it.lw1, it.j, it.a, it.lw);
+            base += SUPER; if (base >= it.pe) break;
+            csr_stage_step(A, it, xa, lane, big, late_slot, late_col, late_val, base, nlate, j2, a2, lw2, it.j1, it.a1, it.lw1);
+            base += SUPER; if (base >= it.pe) break;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int p = base + u * 32 + lane;
-            const int j = it.j[u];
-            bool late = false;
-            double prod = 0.0;
-            if (j >= 0) {
-                late = (it.lw[u] >> (p & 31)) & 1u;
-                if (j == it.k) it.dl = it.a[u];
-                else if (!late) prod = __dmul_rn(it.a[u], xa.ld(j));
-            }
-            if (p < it.pe) big[p - it.pb] = prod;
-            const unsigned m = __ballot_sync(FULL, late);
-            if (m) {
-                const int slot = nlate + __popc(m & ((1u << lane) - 1u));
-                if (late && slot < LATE_CAP) { late_slot[slot] = p - it.pb; late_col[slot] = j; late_val[slot] = it.a[u]; }
-                nlate += __popc(m);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { it.j[u] = it.j1[u]; it.a[u] = it.a1[u]; it.lw[u] = it.lw1[u]; it.j1[u] = jn[u]; it.a1[u] = an[u]; it.lw1[u] = ln[u]; }
     }
     if (lane < 24) big[len + lane] = 0.0;          // the chain reads in blocks of 8 and up to 16 slots ahead
     __syncwarp();
@@ -576,7 +617,7 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
     int cap, long long *dbg) {
     extern __shared__ double dyn_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int grp = warp / G, r = warp - grp * G;
+    const int grp = warp % D, r = warp / D;      // row r of both groups on neighbouring warps = different SM sub-partitions (fp64 pipe, see the cluster kernel)
     const int n = A.nrows;
     double *x = XS ? dyn_smem : xg;
     // per warp: [STAGE streaming slots][cap + 24 parked suffix products][LATE_CAP values][LATE_CAP slots + LATE_CAP columns]
@@ -621,6 +662,15 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
 #ifdef AMGB200_TIMING
     long long tm_prefix = 0, tm_wait = 0, tm_suffix = 0, tm_post = 0, tm_items = 0, tm_sg = 0, tm_sp = 0, tm_sc = 0, tm_sn = 0;
 #endif
+#ifdef AMGB200_TIMELINE
+    long long tl[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define TL_FORCE(v) { if ((v) == -12345) t_acc = 0; }
+#define TL_MARK(i) { volatile double *vs_ = sprod; if (vs_[0] == 1.2345e300) t_acc = 0; const long long c_ = clock64(); tl[i] += c_ - tl_prev; tl_prev = c_; }
+    long long tl_prev = clock64();
+#else
+#define TL_MARK(i)
+#define TL_FORCE(v)
+#endif
     for (; my_g < totalw; my_g += D) {
 #ifdef AMGB200_TIMING
         const long long q0 = clock64();
@@ -629,14 +679,18 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
             if (have) {
                 const bool park = cap && wc.p1 - wc.ps <= cap && A.late;
                 if (park) wc.suffix_prefetch_late(A, lane);                               // late words of the suffix fly during the prefix chain
+                TL_FORCE(wc.j[0]) TL_MARK(10)
                 t_acc = csr_chain_run<false, true>(A, wc, x, wc.bk, lane, sprod);     // prefix [p0, ps)
+                TL_MARK(0)
                 nlate = -1;
                 if (park) {
                     wc.begin_range(A, wc.ps, wc.p1, lane);
                     wc.adopt_late();
+                    TL_MARK(11) TL_FORCE(wc.j[0]) TL_MARK(12)
                     nlate = csr_stage_suffix(A, wc, GlobalX<false>{x}, lane, big, late_slot, late_col, late_val);
                 }
                 if (nlate < 0) wc.begin_range(A, wc.ps, wc.p1, lane);                 // stream the suffix after the barrier
+                TL_MARK(1)
             }
         }
 #ifdef AMGB200_TIMING
@@ -644,6 +698,7 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
         const long long q1 = clock64();
 #endif
         if (my_g > 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + ((my_g - 1) & 7)), "r"(pair_threads) : "memory");
+        TL_MARK(2)
 #ifdef AMGB200_TIMING
         { volatile double *vs = sprod; if (vs[0] == 1.2345e300) ++tm_items; }
         const long long q2 = clock64();
@@ -656,18 +711,27 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
                 if (nlate >= 0) {                 // patch the few products that needed the wavefront just completed, then fold
                     if (lane < nlate) big[late_slot[lane]] = __dmul_rn(late_val[lane], x[late_col[lane]]);
                     __syncwarp();
+                    TL_MARK(3)
                     t = chain_fold<true>(t_acc, reinterpret_cast<const double2 *>(big), wc.p1 - wc.ps);
                 } else t = csr_chain_run<false, true>(A, wc, x, t_acc, lane, sprod);        // suffix [ps, p1), streamed
+#ifdef AMGB200_TIMELINE
+                if (t == 1.2345e300) t_acc = 1;
+#endif
+                TL_MARK(4)
                 const double d = csr_diag(wc);
                 if (lane == 0 && fabs(d) > GS_TINY) x[wc.k] = gs_quotient(t, d, A.recip);
+                TL_MARK(5)
             } else gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod);
             for (int it = i0 + r + G; it < i1; it += G) {              // wavefront wider than the group
                 if constexpr (KIND == 0) { ws.prologue(A, it, lane, b); gs_finish_sell<false>(ws, x); }
                 else { wc.prologue(A, it, lane, b); gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod); }
             }
         }
-        __threadfence_block();
+        // bar.arrive orders this thread's prior shared-memory stores before the consumers' bar.sync (PTX ISA, bar:
+        // producer/consumer example); x in global memory additionally needs the CTA-scope fence
+        if (!XS) __threadfence_block();
         if (my_g + 1 < totalw) asm volatile("bar.arrive %0, %1;" ::"r"(1 + (my_g & 7)), "r"(pair_threads) : "memory");
+        TL_MARK(6)
 #ifdef AMGB200_TIMING
         const long long q3 = clock64();
 #endif
@@ -675,7 +739,17 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
         while (my_wl >= W) my_wl -= W;
         if (my_g + D < totalw) {
             if constexpr (TWO_PHASE) asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");   // whole group done with my_g
+            TL_MARK(7)
             fetch();
+            TL_MARK(8)
+            if constexpr (KIND == 1) {
+                if (my_g + 2 * D < totalw) {                          // warm L1 for the wavefront after that one
+                    int wl2 = my_wl + D;
+                    while (wl2 >= W) wl2 -= W;
+                    csr_prefetch_rows(A, wf_item_ptr[wl2], wf_item_ptr[wl2 + 1], lane, r, G);
+                }
+            }
+            TL_MARK(9)
         }
 #ifdef AMGB200_TIMING
         { volatile double *vs = sprod; if (vs[0] == 1.2345e300) ++tm_items; }
@@ -683,6 +757,9 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
         tm_prefix += q1 - q0; tm_wait += q2 - q1; tm_suffix += q3 - q2; tm_post += q4 - q3;
 #endif
     }
+#ifdef AMGB200_TIMELINE
+    if (dbg && lane == 0 && warp < 2) for (int i = 0; i < 14; ++i) dbg[(warp ? 16 : 0) + i] = tl[i];
+#endif
 #ifdef AMGB200_TIMING
     if (dbg && lane == 0) { dbg[warp * 8 + 0] = tm_prefix; dbg[warp * 8 + 1] = tm_wait; dbg[warp * 8 + 2] = tm_suffix; dbg[warp * 8 + 3] = tm_post; dbg[warp * 8 + 4] = tm_items; dbg[warp * 8 + 5] = tm_sg; dbg[warp * 8 + 6] = tm_sp; dbg[warp * 8 + 7] = tm_sc; if (warp == 0) dbg[16 * 8] = tm_sn; }
 #endif
@@ -710,7 +787,10 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CLUSTER_WARPS_SELL : 32 * CLU
     using Desc = typename Item::Desc;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nw = blockDim.x >> 5;
-    const int gw = (int)cluster_ctarank() * nw + warp;        // warp index within the cluster
+    // rows of a wavefront go round-robin over the 16 SMs first, then over the warps of an SM: a warp-wide DADD
+    // occupies an SM sub-partition's fp64 pipe for 4 cycles (measured, tools/ubench2.cu), so more than two
+    // chaining warps per sub-partition slow every chain down
+    const int gw = warp * CLUSTER_CTAS + (int)cluster_ctarank();
     const int TW = CLUSTER_CTAS * nw;
     const int totalw = W * nsweeps;
     double *sp = sprod + (KIND == 1 ? warp * STAGE : 0);
@@ -788,7 +868,7 @@ __global__ void __launch_bounds__(32 * CLUSTER_WARPS_CSR) gs_ordered_cluster_dsm
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nw = blockDim.x >> 5;
     const int rank = (int)cluster_ctarank();
-    const int gw = rank * nw + warp;
+    const int gw = warp * CLUSTER_CTAS + rank;
     const int TW = CLUSTER_CTAS * nw;
     const int totalw = W * nsweeps;
     const int chunk = 1 << sh, n = A.nrows;
