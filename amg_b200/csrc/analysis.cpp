@@ -178,4 +178,68 @@ void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos
     }
 }
 
+void build_stream(const DevLayout &L, StreamLayout &S) {
+    const int W = (int)L.wf_item_ptr.size() - 1;
+    const std::vector<int> &wip = L.wf_item_ptr;
+    auto r8 = [](int v) { return (v + 7) & ~7; };
+    auto late_bit = [&](int q) { return (L.late[(size_t)q >> 5] >> (q & 31)) & 1u; };
+    // per-row record size
+    std::vector<int> rec_bytes((size_t)L.nrows);
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < L.nrows; ++k) {
+        const int p0 = L.rptr[k], len = L.rptr[k + 1] - p0, sp = L.split[k];
+        int nlate = 0;
+        for (int q = p0 + sp; q < p0 + len; ++q) nlate += late_bit(q);
+        const int len_pad = r8(sp) + r8(len - sp);
+        rec_bytes[k] = 32 + len_pad * 12 + nlate * 16;
+    }
+    S.blk_ptr.assign((size_t)W + 1, 0);
+    S.max_block = 0;
+    for (int w = 0; w < W; ++w) {
+        const int nr = wip[w + 1] - wip[w];
+        long long bytes = 16 + (long long)((nr + 3) & ~3) * 4;
+        for (int k = wip[w]; k < wip[w + 1]; ++k) bytes += rec_bytes[k];
+        const int i0a = wip[w] & ~1, bcnt = (wip[w + 1] - i0a + 1) & ~1;
+        S.blk_ptr[w + 1] = S.blk_ptr[w] + (int)(bytes / 16);
+        S.max_block = (int)std::max<long long>(S.max_block, bytes + (long long)bcnt * 8);
+    }
+    S.data.resize((size_t)S.blk_ptr[W] * 16);
+    S.mean_block = W ? (long long)S.blk_ptr[W] * 16 / W : 0;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int w = 0; w < W; ++w) {
+        unsigned char *blk = S.data.data() + (size_t)S.blk_ptr[w] * 16;
+        const int nr = wip[w + 1] - wip[w];
+        int *hd = reinterpret_cast<int *>(blk);
+        const int i0a = wip[w] & ~1;
+        hd[0] = nr; hd[1] = i0a; hd[2] = (wip[w + 1] - i0a + 1) & ~1; hd[3] = (S.blk_ptr[w + 1] - S.blk_ptr[w]) * 16;
+        int *rec_off = hd + 4;
+        int off = 16 + ((nr + 3) & ~3) * 4;
+        for (int i = nr; i < ((nr + 3) & ~3); ++i) rec_off[i] = 0;
+        for (int k = wip[w]; k < wip[w + 1]; ++k) {
+            rec_off[k - wip[w]] = off;
+            unsigned char *rec = blk + off;
+            const int p0 = L.rptr[k], len = L.rptr[k + 1] - p0, sp = L.split[k];
+            const int pre_pad = r8(sp), len_pad = pre_pad + r8(len - sp);
+            int *rh = reinterpret_cast<int *>(rec);
+            double *rd = reinterpret_cast<double *>(rec);
+            double *val = rd + 4;
+            int *col = reinterpret_cast<int *>(val + len_pad);
+            StreamLate *lt = reinterpret_cast<StreamLate *>(col + len_pad);
+            for (int i = 0; i < len_pad; ++i) { val[i] = 0.0; col[i] = -1; }
+            double diag = 0.0;
+            int nlate = 0;
+            for (int i = 0; i < len; ++i) {
+                const int q = p0 + i, pos = i < sp ? i : pre_pad + (i - sp);
+                const int c = L.col[q];
+                if (c == k) { diag = L.val[q]; continue; }          // (SSS_smooth.c:29-30: the diagonal is not part of the sum)
+                val[pos] = L.val[q]; col[pos] = c;
+                if (late_bit(q)) { lt[nlate].val = L.val[q]; lt[nlate].pos = pos; lt[nlate].col = c; ++nlate; }
+            }
+            rh[0] = k; rh[1] = pre_pad; rh[2] = len_pad; rh[3] = nlate;
+            rd[2] = diag; rd[3] = 0.0;
+            off += rec_bytes[k];
+        }
+    }
+}
+
 }  // namespace amgb200

@@ -65,6 +65,26 @@ struct DevLayout {
     int nitems() const { return kind == KIND_SELL ? (int)slice_row.size() - 1 : nrows; }
 };
 
+// CSR + wavefronts, re-packed for the streaming single-CTA smoother (kernels.cuh, gs_stream_cta_kernel): ONE
+// contiguous, 16-byte aligned block per wavefront, so that a single bulk-async copy brings everything the
+// wavefront needs into shared memory.
+//   block  : int32 nrows, int32 first_row & ~1, int32 rhs doubles to fetch (even), int32 block bytes
+//            int32 rec_off[nrows]  (bytes from the block start, padded to a multiple of 4 ints)
+//            records
+//   record : int32 row, int32 prefix_pad, int32 len_pad, int32 nlate, double diag, double scratch     (32 bytes)
+//            double val[len_pad]   prefix entries, zero padding to a multiple of 8, suffix entries, padding to 8
+//            int32  col[len_pad]   (-1 for padding and for the diagonal entry, whose value moves to `diag`)
+//            {double val; int32 pos; int32 col} late[nlate]   entries whose column lies in the preceding wavefront
+// The storage order of a row is untouched: padding only inserts exact no-ops (+0.0 products).
+struct StreamLayout {
+    RawBuf<unsigned char> data;
+    std::vector<int> blk_ptr;      // W+1, in units of 16 bytes
+    int max_block = 0;             // largest block incl. its right-hand-side segment, bytes
+    long long mean_block = 0;
+};
+struct StreamLate { double val; int pos; int col; };
+void build_stream(const DevLayout &L, StreamLayout &S);
+
 // mark == nullptr: single pass over all rows in natural order (no C/F ordering).
 void build_schedule(const amgb200_mat &A, const int *mark, Schedule &S);
 void identity_schedule(int n, Schedule &S);

@@ -172,11 +172,14 @@ struct Level {
     unsigned *d_cnt = nullptr;
     int cnt_cap = 0;
     bool pattern_symmetric = true;
-    int strategy = 0;                  // 0 = parallel passes, 1 = ordered across the grid, 2 = ordered inside one CTA
+    int strategy = 0;                  // 0 = parallel passes, 1 = ordered across the grid, 2 = ordered inside one CTA, 3 = one cluster, 4 = streaming CTA
     double prof_ms[4] = {0, 0, 0, 0};  // AMGB200_PROFILE: GS, residual, restrict, prolong of the last solve
     bool x_in_smem = false;            // strategy 2 only: x fits in the CTA's shared memory
     int cta_G = 1, cta_D = 1;          // strategy 2: D groups of G warps (pipeline depth D)
     int cta_cap = 0;                   // strategy 2, two-phase rows: parked suffix products per warp (0 = stream the suffix)
+    unsigned char *d_stream = nullptr; // strategy 4 (streaming single CTA): per-wavefront blocks (analysis.h, StreamLayout)
+    int *d_blk_ptr = nullptr;
+    int stream_G = 1, stream_ring = 0;
     int dsmem_sh = 0;                  // strategy 3: x distributed over the cluster's shared memory, 2^sh rows per CTA (0 = x in global memory)
     bool natural = false;              // natural-order Gauss-Seidel (cf_order = 0 or no cfmark): forward sweeps use this level's
     Level *bk = nullptr;               // schedule, backward sweeps (post-smoothing) the schedule/layout/vectors of *bk
@@ -281,6 +284,20 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
                 first += cnt;
             }
         }
+        return;
+    }
+    if (lv.strategy == 4) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(gs_stream_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+            attr_set = true;
+        }
+        const size_t xb = ((size_t)lv.n * 8 + 15) & ~(size_t)15;
+        const size_t smem = 128 + xb + (size_t)lv.stream_ring + 128;
+        gs_stream_cta_kernel<<<1, 32 * (2 * lv.stream_G + 1), smem, h->stream>>>(lv.d_stream, lv.d_blk_ptr, lv.d_wf_item_ptr, lv.b, lv.x, lv.n, lv.W, nsweeps,
+                                                                            lv.stream_G, lv.stream_ring, lv.A.v.recip, h->d_dbg);
+        ++g_launches;
+        CUDA_CHECK(cudaGetLastError());
         return;
     }
     if (lv.strategy == 2) {
@@ -780,6 +797,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     }
     const double sell_max_mean = getenv("AMGB200_SELL_MAX_MEAN") ? atof(getenv("AMGB200_SELL_MAX_MEAN")) : (h->exact ? 48.0 : 24.0);
     const double cta_max_avg = getenv("AMGB200_CTA_MAX_AVG") ? atof(getenv("AMGB200_CTA_MAX_AVG")) : 6.0;
+    const double stream_max_avg = getenv("AMGB200_STREAM_MAX_AVG") ? atof(getenv("AMGB200_STREAM_MAX_AVG")) : 12.0;
     if (getenv("AMGB200_CLUSTER_BLOCK")) h->cluster_block = std::max(32, std::min(BLOCK, atoi(getenv("AMGB200_CLUSTER_BLOCK")) / 32 * 32));
     auto kind_of = [&](const amgb200_mat &M) { return choose_kind(M, sell_max_mean); };
     const double ordered_csr_min = getenv("AMGB200_ORDERED_CSR_MIN") ? atof(getenv("AMGB200_ORDERED_CSR_MIN")) : 24.0;
@@ -887,6 +905,26 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         if (((size_t)1 << sh) * 8 + (size_t)nwc * STAGE * 8 <= (size_t)h->max_dyn_smem) lv.dsmem_sh = sh;
     }
     if (getenv("AMGB200_GS_STRATEGY") && lv.ordered) lv.strategy = std::max(1, std::min(3, atoi(getenv("AMGB200_GS_STRATEGY"))));
+    // streaming single-CTA smoother: warp-per-row EXACT levels whose x vector plus a ring of at least two of the
+    // largest wavefront blocks fit in shared memory
+    if (lv.ordered && lay.kind == KIND_CSR && h->exact && !getenv("AMGB200_GS_STRATEGY") && (double)wip[lv.W] / lv.W <= stream_max_avg) {
+        const size_t xb = ((size_t)lv.n * 8 + 15) & ~(size_t)15;
+        const long long ring = (long long)h->max_dyn_smem - 128 - (long long)xb - 128;
+        if (ring >= 4096) {
+            StreamLayout SL;
+            const double tl = now_s();
+            build_stream(lay, SL);
+            t_layout += now_s() - tl;
+            if ((long long)SL.max_block * 2 <= ring) {
+                lv.strategy = 4;
+                lv.stream_ring = (int)(ring & ~15LL);
+                lv.stream_G = std::max(1, std::min(lv.max_width, STREAM_MAX_G));
+                lv.d_stream = dev_upload(SL.data);
+                lv.d_blk_ptr = dev_upload(SL.blk_ptr);
+                if (h->opt.verbose >= 2) printf("      streaming CTA smoother: %d consumer warps/group, ring %d B, wavefront block mean %lld B max %d B, stream %.1f MB\n", lv.stream_G, lv.stream_ring, SL.mean_block, SL.max_block, SL.data.size() / 1e6);
+            }
+        }
+    }
     };
 
     for (int l = 0; l < nl; ++l) {
@@ -914,7 +952,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         }
         lv.d_order = dev_upload(S.order);
         lv.x = dev_alloc<double>(lv.n);
-        lv.b = dev_alloc<double>(lv.n);
+        lv.b = dev_alloc<double>(lv.n + 2);               // (+2: the streaming smoother fetches 16-byte aligned segments of b)
         lv.wp = dev_alloc<double>(lv.n);
         CUDA_CHECK(cudaMemset(lv.x, 0, (size_t)lv.n * sizeof(double)));
         CUDA_CHECK(cudaMemset(lv.b, 0, (size_t)lv.n * sizeof(double)));
@@ -935,7 +973,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                 bk->A.v.recip = 1;
                 max_items = std::max(max_items, lb.nitems());
                 bk->x = dev_alloc<double>(lv.n);
-                bk->b = dev_alloc<double>(lv.n);
+                bk->b = dev_alloc<double>(lv.n + 2);
                 setup_smoother(*bk, lb, B);
                 std::vector<int> fb((size_t)lv.n);
                 for (int k = 0; k < lv.n; ++k) fb[k] = S.pos[B.order[k]];
@@ -981,11 +1019,11 @@ void amgb200_free(amgb200_hier *h) {
     for (Level &lv : h->L) {
         lv.A.release(); lv.Asp.release(); lv.P.release(); lv.R.release();
         dev_free(lv.d_order); dev_free(lv.x); dev_free(lv.b); dev_free(lv.wp);
-        dev_free(lv.d_item_wf); dev_free(lv.d_wf_item_ptr); dev_free(lv.d_cnt); dev_free(lv.d_fb);
+        dev_free(lv.d_item_wf); dev_free(lv.d_wf_item_ptr); dev_free(lv.d_cnt); dev_free(lv.d_fb); dev_free(lv.d_stream); dev_free(lv.d_blk_ptr);
         if (lv.bk) {
             lv.bk->A.release();
             dev_free(lv.bk->x); dev_free(lv.bk->b);
-            dev_free(lv.bk->d_item_wf); dev_free(lv.bk->d_wf_item_ptr); dev_free(lv.bk->d_cnt);
+            dev_free(lv.bk->d_item_wf); dev_free(lv.bk->d_wf_item_ptr); dev_free(lv.bk->d_cnt); dev_free(lv.bk->d_stream); dev_free(lv.bk->d_blk_ptr);
             delete lv.bk;
         }
     }
@@ -1054,7 +1092,7 @@ const char *amgb200_level_kernel(const amgb200_hier *h, int level) {
     check_level(h, level);
     const Level &lv = h->L[level];
     if (!lv.smoothed) return "none";
-    static const char *names[4] = {"gs_pass_kernel", "gs_ordered_grid_kernel", "gs_ordered_cta_kernel", "gs_ordered_cluster_kernel"};
+    static const char *names[5] = {"gs_pass_kernel", "gs_ordered_grid_kernel", "gs_ordered_cta_kernel", "gs_ordered_cluster_kernel", "gs_stream_cta_kernel"};
     return names[lv.strategy];
 }
 

@@ -767,6 +767,139 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
     if (XS) for (int i = threadIdx.x; i < n; i += blockDim.x) xg[i] = dyn_smem[i];
 }
 
+// ------------------------------------------------------------------------------------------
+// Streaming single-CTA ordered sweeps (warp-per-row EXACT rows, x in shared memory).
+//
+// The matrix of the level is pre-packed on the host into one self-contained block per wavefront
+// (analysis.h, StreamLayout).  A LOADER warp walks the static schedule ahead of everybody else and pulls each
+// block -- plus the right-hand-side entries of its rows -- from L2 into a byte ring in shared memory with
+// cp.async.bulk (one elected thread, completion on an mbarrier): no consumer ever waits for an L2 round trip.
+// 2*G CONSUMER warps in two alternating groups walk the wavefronts: while group A finishes wavefront g-1,
+// group B (wavefront g) multiplies all its rows' entries by x in place (the values become the separately
+// rounded products, in storage order) and folds each row's prefix -- the entries before the first one that
+// reads wavefront g-1 -- into the accumulator.  After the named barrier that announces g-1, B only has to
+// recompute the few "late" products, fold the suffix, divide and store: that chain is the whole critical path.
+// Dynamic shared memory: [mbarriers full[NS], empty[NS] | ring offsets : 128 B][x : n doubles][ring]
+// ------------------------------------------------------------------------------------------
+constexpr int STREAM_NS = 4;                  // wavefront blocks in flight (ring descriptors)
+constexpr int STREAM_MAX_G = 8;               // consumer warps per group
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+struct StreamLateDev { double val; int pos; int col; };
+
+__global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_kernel(
+    const unsigned char *__restrict__ stream, const int *__restrict__ blk_ptr, const int *__restrict__ wf_row_ptr,
+    const double *__restrict__ b, double *xg, int n, int W, int nsweeps, int G, int ring_bytes, int recip, long long *dbg) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);      // full[0..NS), empty[0..NS)
+    volatile int *stage_off = reinterpret_cast<volatile int *>(smem_raw + 64);
+    double *x = reinterpret_cast<double *>(smem_raw + 128);
+    unsigned char *ring = smem_raw + 128 + (((size_t)n * 8 + 15) & ~(size_t)15);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int totalw = W * nsweeps;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STREAM_NS; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + STREAM_NS + s), G); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = xg[i];
+    __syncthreads();
+    if (warp < 2 * G) {
+        const int grp = warp & 1, r = warp >> 1;
+        const int pair_threads = 2 * G * 32;
+        for (int g = grp; g < totalw; g += 2) {
+            const int s = g & (STREAM_NS - 1);
+            mbar_wait(smem_u32(bars + s), (g / STREAM_NS) & 1);
+            unsigned char *blk = ring + stage_off[s];
+            const int4 hd = *reinterpret_cast<const int4 *>(blk);                   // nrows, first row & ~1, rhs count, block bytes
+            const int *rec_off = reinterpret_cast<const int *>(blk + 16);
+            const double *bseg = reinterpret_cast<const double *>(blk + hd.w);
+            // ---- before the barrier: products of every entry (late ones are redone below), prefix chain
+            for (int ri = r; ri < hd.x; ri += G) {
+                unsigned char *rec = blk + rec_off[ri];
+                const int4 rh = *reinterpret_cast<const int4 *>(rec);               // row, prefix_pad, len_pad, nlate
+                double *val = reinterpret_cast<double *>(rec + 32);
+                const int *col = reinterpret_cast<const int *>(val + rh.z);
+                for (int p0 = 0; p0 < rh.z; p0 += 128) {
+                    int j[4];
+                    double v[4], xv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int p = p0 + u * 32 + lane; j[u] = p < rh.z ? col[p] : -1; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int p = p0 + u * 32 + lane; v[u] = j[u] >= 0 ? val[p] : 0.0; xv[u] = j[u] >= 0 ? x[j[u]] : 0.0; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int p = p0 + u * 32 + lane; if (j[u] >= 0) val[p] = __dmul_rn(v[u], xv[u]); }
+                }
+                __syncwarp();
+                const double t = chain_fold<true>(bseg[rh.x - hd.y], reinterpret_cast<const double2 *>(val), rh.y);
+                if (lane == 0) reinterpret_cast<double *>(rec)[3] = t;
+            }
+            __syncwarp();
+            if (g > 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + ((g - 1) & 7)), "r"(pair_threads) : "memory");
+            // ---- after the barrier: late products, suffix chain, x_k
+            for (int ri = r; ri < hd.x; ri += G) {
+                unsigned char *rec = blk + rec_off[ri];
+                const int4 rh = *reinterpret_cast<const int4 *>(rec);
+                double *val = reinterpret_cast<double *>(rec + 32);
+                const StreamLateDev *lt = reinterpret_cast<const StreamLateDev *>(reinterpret_cast<const int *>(val + rh.z) + rh.z);
+                for (int i = lane; i < rh.w; i += 32) { const StreamLateDev e = lt[i]; val[e.pos] = __dmul_rn(e.val, x[e.col]); }
+                __syncwarp();
+                const double2 dt = *reinterpret_cast<const double2 *>(rec + 16);    // diag, prefix accumulator
+                const double t = chain_fold<true>(dt.y, reinterpret_cast<const double2 *>(val + rh.y), rh.z - rh.y);
+                if (lane == 0 && fabs(dt.x) > GS_TINY) x[rh.x] = gs_quotient(t, dt.x, recip);
+            }
+            // bar.arrive orders this thread's prior shared-memory stores before the consumers' bar.sync (PTX ISA, bar:
+            // producer/consumer example)
+            if (g + 1 < totalw) asm volatile("bar.arrive %0, %1;" ::"r"(1 + (g & 7)), "r"(pair_threads) : "memory");
+            __syncwarp();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // my generic writes to the block precede its reuse by the async proxy
+            if (lane == 0) mbar_arrive(smem_u32(bars + STREAM_NS + s));
+            if (g + 2 < totalw) asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");   // whole group done with g
+        }
+    } else if (lane == 0) {
+        // ---- loader: in-order ring allocation; a block is released when all G warps of its group have arrived on empty[s]
+        int head = 0, tail = 0, inflight = 0, g_old = 0, wl = 0;
+        for (int g = 0; g < totalw; ++g) {
+            const int s = g & (STREAM_NS - 1);
+            const int o0 = blk_ptr[wl], o1 = blk_ptr[wl + 1];
+            const int i0a = wf_row_ptr[wl] & ~1, bcnt = (wf_row_ptr[wl + 1] - i0a + 1) & ~1;
+            const int bytes = (o1 - o0) * 16, need = bytes + bcnt * 8;
+            for (;;) {
+                if (inflight == 0) { head = tail = 0; break; }
+                if (inflight < STREAM_NS) {
+                    if (head >= tail) {                       // (head == tail only when nothing is in flight: strict tests below)
+                        if (head + need <= ring_bytes) break;
+                        if (need < tail) { head = 0; break; }
+                    } else if (head + need < tail) break;
+                }
+                mbar_wait(smem_u32(bars + STREAM_NS + (g_old & (STREAM_NS - 1))), (g_old / STREAM_NS) & 1);
+                ++g_old; --inflight;
+                tail = inflight ? stage_off[g_old & (STREAM_NS - 1)] : head;
+            }
+            stage_off[s] = head;
+            const unsigned full = smem_u32(bars + s);
+            mbar_arrive_expect_tx(full, (unsigned)need);
+            bulk_g2s(smem_u32(ring + head), stream + (size_t)o0 * 16, (unsigned)bytes, full);
+            bulk_g2s(smem_u32(ring + head + bytes), b + i0a, (unsigned)(bcnt * 8), full);
+            head += need; ++inflight;
+            if (++wl == W) wl = 0;
+        }
+    }
+    __syncwarp();
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) xg[i] = x[i];
+}
+
 // Ordered sweeps inside ONE thread-block cluster (16 CTAs = 16 SMs on one die): the wavefronts of the
 // level are walked in order, the items of a wavefront are spread over all warps of the cluster, and
 // consecutive wavefronts are separated by the hardware cluster barrier (barrier.cluster, ~0.2 us)
