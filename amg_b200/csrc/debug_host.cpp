@@ -34,10 +34,57 @@ void amgb200_debug_gs_walk(const amgb200_mat *A, const int *mark, int kind, int 
     Schedule S;
     build_schedule(*A, mark, S);
     DevLayout L;
-    build_layout(*A, S.order.data(), S.pos.data(), kind, &S.wf_row_ptr, L);
+    build_layout(*A, S.order.data(), S.pos.data(), kind == 2 ? (int)KIND_CSR : kind, &S.wf_row_ptr, L);
     const int n = S.n, W = S.wf_count[0] + S.wf_count[1];
     std::vector<double> xs(n), bs(n);
     for (int k = 0; k < n; ++k) { xs[k] = x[S.order[k]]; bs[k] = b[S.order[k]]; }
+    if (kind == 2) {
+        // the streaming smoother's algorithm on its packed blocks (kernels.cuh, gs_stream_cta_kernel), in the least
+        // favourable legal interleaving: the pre-barrier half of wavefront g+1 runs entirely BEFORE the post-barrier
+        // half of wavefront g
+        StreamLayout SL;
+        build_stream(L, SL);
+        const int total = W * nsweeps;
+        std::vector<std::vector<unsigned char>> live(2);
+        auto pre = [&](int g) {
+            const int w = g % W;
+            std::vector<unsigned char> &blk = live[g & 1];
+            blk.assign(SL.data.data() + (size_t)SL.blk_ptr[w] * 16, SL.data.data() + (size_t)SL.blk_ptr[w + 1] * 16);
+            const int *hd = reinterpret_cast<const int *>(blk.data());
+            for (int ri = 0; ri < hd[0]; ++ri) {
+                unsigned char *rec = blk.data() + hd[4 + ri];
+                const int *rh = reinterpret_cast<const int *>(rec);
+                double *val = reinterpret_cast<double *>(rec + 32);
+                const int *col = reinterpret_cast<const int *>(val + rh[2]);
+                for (int p = 0; p < rh[2]; ++p) if (col[p] >= 0) val[p] = val[p] * xs[col[p]];
+                double t = bs[rh[0]];
+                for (int p = 0; p < rh[1]; ++p) t -= val[p];
+                reinterpret_cast<double *>(rec)[3] = t;
+            }
+        };
+        auto post = [&](int g) {
+            std::vector<unsigned char> &blk = live[g & 1];
+            const int *hd = reinterpret_cast<const int *>(blk.data());
+            for (int ri = hd[0] - 1; ri >= 0; --ri) {
+                unsigned char *rec = blk.data() + hd[4 + ri];
+                const int *rh = reinterpret_cast<const int *>(rec);
+                double *val = reinterpret_cast<double *>(rec + 32);
+                const StreamLate *lt = reinterpret_cast<const StreamLate *>(reinterpret_cast<const int *>(val + rh[2]) + rh[2]);
+                for (int i = 0; i < rh[3]; ++i) val[lt[i].pos] = lt[i].val * xs[lt[i].col];
+                double t = reinterpret_cast<double *>(rec)[3];
+                for (int p = rh[1]; p < rh[2]; ++p) t -= val[p];
+                const double d = reinterpret_cast<double *>(rec)[2];
+                if (fabs(d) > 1e-20) xs[rh[0]] = t / d;
+            }
+        };
+        if (total > 0) pre(0);
+        for (int g = 0; g < total; ++g) {
+            if (g + 1 < total) pre(g + 1);
+            post(g);
+        }
+        for (int k = 0; k < n; ++k) x[S.order[k]] = xs[k];
+        return;
+    }
     for (int s = 0; s < nsweeps; ++s)
         for (int w = 0; w < W; ++w)
             for (int it = L.wf_item_ptr[w + 1] - 1; it >= L.wf_item_ptr[w]; --it) {     // reverse order inside the wavefront

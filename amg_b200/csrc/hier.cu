@@ -179,7 +179,7 @@ struct Level {
     int cta_cap = 0;                   // strategy 2, two-phase rows: parked suffix products per warp (0 = stream the suffix)
     unsigned char *d_stream = nullptr; // strategy 4 (streaming single CTA): per-wavefront blocks (analysis.h, StreamLayout)
     int *d_blk_ptr = nullptr;
-    int stream_G = 1, stream_ring = 0;
+    int stream_G = 1, stream_S = 1, stream_ring = 0;   // consumer warps per group, row slots per warp
     int dsmem_sh = 0;                  // strategy 3: x distributed over the cluster's shared memory, 2^sh rows per CTA (0 = x in global memory)
     bool natural = false;              // natural-order Gauss-Seidel (cf_order = 0 or no cfmark): forward sweeps use this level's
     Level *bk = nullptr;               // schedule, backward sweeps (post-smoothing) the schedule/layout/vectors of *bk
@@ -293,10 +293,25 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
             attr_set = true;
         }
         const size_t xb = ((size_t)lv.n * 8 + 15) & ~(size_t)15;
-        const size_t smem = 128 + xb + (size_t)lv.stream_ring + 128;
+        const size_t smem = 256 + xb + (size_t)lv.stream_ring + 128;
         gs_stream_cta_kernel<<<1, 32 * (2 * lv.stream_G + 1), smem, h->stream>>>(lv.d_stream, lv.d_blk_ptr, lv.d_wf_item_ptr, lv.b, lv.x, lv.n, lv.W, nsweeps,
-                                                                            lv.stream_G, lv.stream_ring, lv.A.v.recip, h->d_dbg);
+                                                                            lv.stream_G, lv.stream_S, lv.stream_ring, lv.A.v.recip, h->d_dbg);
         ++g_launches;
+#ifdef AMGB200_TIMELINE
+        if (h->d_dbg) {
+            long long hd[32];
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            CUDA_CHECK(cudaMemcpy(hd, h->d_dbg, sizeof(hd), cudaMemcpyDeviceToHost));
+            const char *nm[9] = {"wait block", "products", "prefix fold", "bar.sync(prev wavefront)", "patch late", "suffix fold", "div+store", "group barrier", "arrive+release"};
+            const int iters = (lv.W * nsweeps + 1) / 2;
+            for (int g2 = 0; g2 < 2; ++g2) {
+                printf("   stream timeline group %d warp r=0 (cycles per wavefront, %d wavefronts, G=%d):", g2, iters, lv.stream_G);
+                long long tot = 0;
+                for (int i = 0; i < 9; ++i) { printf("  %s %lld", nm[i], hd[g2 * 16 + i] / iters); tot += hd[g2 * 16 + i]; }
+                printf("  | total %lld\n", tot / iters);
+            }
+        }
+#endif
         CUDA_CHECK(cudaGetLastError());
         return;
     }
@@ -909,7 +924,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     // largest wavefront blocks fit in shared memory
     if (lv.ordered && lay.kind == KIND_CSR && h->exact && !getenv("AMGB200_GS_STRATEGY") && (double)wip[lv.W] / lv.W <= stream_max_avg) {
         const size_t xb = ((size_t)lv.n * 8 + 15) & ~(size_t)15;
-        const long long ring = (long long)h->max_dyn_smem - 128 - (long long)xb - 128;
+        const long long ring = (long long)h->max_dyn_smem - 256 - (long long)xb - 128;
         if (ring >= 4096) {
             StreamLayout SL;
             const double tl = now_s();
@@ -918,10 +933,18 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             if ((long long)SL.max_block * 2 <= ring) {
                 lv.strategy = 4;
                 lv.stream_ring = (int)(ring & ~15LL);
-                lv.stream_G = std::max(1, std::min(lv.max_width, STREAM_MAX_G));
+                // 2 groups x 4 warps = two chaining warps per SM sub-partition (more only contend for the fp64 pipe;
+                // measured sweep on 128^3 levels 4-6: G=4 best or within 1 %)
+                lv.stream_G = std::max(1, std::min(lv.max_width, 4));
+                if (getenv("AMGB200_STREAM_G")) lv.stream_G = std::max(1, std::min(STREAM_MAX_G, atoi(getenv("AMGB200_STREAM_G"))));
+                // row slots per warp: the widest wavefront in one round if possible (rows go to different warps first,
+                // so unused slots cost nothing)
+                lv.stream_S = 1;
+                while (lv.stream_S < 8 && lv.stream_G * lv.stream_S < lv.max_width) lv.stream_S *= 2;
+                if (getenv("AMGB200_STREAM_S")) lv.stream_S = std::max(1, std::min(32, atoi(getenv("AMGB200_STREAM_S"))));
                 lv.d_stream = dev_upload(SL.data);
                 lv.d_blk_ptr = dev_upload(SL.blk_ptr);
-                if (h->opt.verbose >= 2) printf("      streaming CTA smoother: %d consumer warps/group, ring %d B, wavefront block mean %lld B max %d B, stream %.1f MB\n", lv.stream_G, lv.stream_ring, SL.mean_block, SL.max_block, SL.data.size() / 1e6);
+                if (h->opt.verbose >= 2) printf("      streaming CTA smoother: %d consumer warps/group x %d row slots, ring %d B, wavefront block mean %lld B max %d B, stream %.1f MB\n", lv.stream_G, lv.stream_S, lv.stream_ring, SL.mean_block, SL.max_block, SL.data.size() / 1e6);
             }
         }
     }

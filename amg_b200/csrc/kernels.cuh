@@ -779,7 +779,7 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
 // rounded products, in storage order) and folds each row's prefix -- the entries before the first one that
 // reads wavefront g-1 -- into the accumulator.  After the named barrier that announces g-1, B only has to
 // recompute the few "late" products, fold the suffix, divide and store: that chain is the whole critical path.
-// Dynamic shared memory: [mbarriers full[NS], empty[NS] | ring offsets : 128 B][x : n doubles][ring]
+// Dynamic shared memory: [mbarriers full[NS], empty[NS] | ring offsets | 64 B of zeros : 256 B][x : n doubles][ring]
 // ------------------------------------------------------------------------------------------
 constexpr int STREAM_NS = 4;                  // wavefront blocks in flight (ring descriptors)
 constexpr int STREAM_MAX_G = 8;               // consumer warps per group
@@ -796,67 +796,182 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 struct StreamLateDev { double val; int pos; int col; };
 
+// chain_fold for a warp whose lanes are split into row slots: every lane folds the `cnt` (multiple of 8) products at
+// sp2 of ITS slot's row; slots with fewer terms than the warp-wide maximum `maxc` idle on exact no-ops (t - (+0.0)).
+// One warp-wide DSUB then advances up to 32/sub rows at once: the fp64 pipe (4 cycles per warp instruction per
+// sub-partition) is shared by a quarter as many chaining warps.  Nothing beyond a slot's own cnt is read.
+__device__ __forceinline__ double chain_fold_slots(double t, const double2 *sp2, int cnt, int maxc, const double2 *zeros) {
+#define AMGB200_FOLD(v)                                                        \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) { t = __dsub_rn(t, v[u].x); t = __dsub_rn(t, v[u].y); }
+    // blocks past this slot's own cnt are read from a 64-byte block of zeros: no branch, no select on the chain
+#define AMGB200_LOAD(v, q)                                                     \
+    {                                                                          \
+        const double2 *src_ = (q) < cnt ? sp2 + ((q) >> 1) : zeros;            \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) v[u] = src_[u];          \
+    }                                                                          \
+    __syncwarp();
+    double2 va[4], vb[4];
+    int q = 0;
+    AMGB200_LOAD(va, 0)
+#pragma unroll 1
+    for (; q + 32 <= maxc; q += 32) {
+        AMGB200_LOAD(vb, q + 8)  AMGB200_FOLD(va)
+        AMGB200_LOAD(va, q + 16) AMGB200_FOLD(vb)
+        AMGB200_LOAD(vb, q + 24) AMGB200_FOLD(va)
+        AMGB200_LOAD(va, q + 32) AMGB200_FOLD(vb)
+    }
+#pragma unroll 1
+    for (; q < maxc; q += 8) {
+        AMGB200_LOAD(vb, q + 8)  AMGB200_FOLD(va)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) va[u] = vb[u];
+    }
+#undef AMGB200_FOLD
+#undef AMGB200_LOAD
+    return t;
+}
+
+// row ri of a wavefront -> consumer warp ri % G, slot (ri / G) % S of that warp, round ri / (G*S)
 __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_kernel(
     const unsigned char *__restrict__ stream, const int *__restrict__ blk_ptr, const int *__restrict__ wf_row_ptr,
-    const double *__restrict__ b, double *xg, int n, int W, int nsweeps, int G, int ring_bytes, int recip, long long *dbg) {
+    const double *__restrict__ b, double *xg, int n, int W, int nsweeps, int G, int S, int ring_bytes, int recip, long long *dbg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);      // full[0..NS), empty[0..NS)
     volatile int *stage_off = reinterpret_cast<volatile int *>(smem_raw + 64);
-    double *x = reinterpret_cast<double *>(smem_raw + 128);
-    unsigned char *ring = smem_raw + 128 + (((size_t)n * 8 + 15) & ~(size_t)15);
+    const double2 *zeros = reinterpret_cast<const double2 *>(smem_raw + 128);
+    double *x = reinterpret_cast<double *>(smem_raw + 256);
+    unsigned char *ring = smem_raw + 256 + (((size_t)n * 8 + 15) & ~(size_t)15);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int totalw = W * nsweeps;
+    const unsigned x_a = smem_u32(x);
+#ifdef AMGB200_TIMELINE
+    long long tl[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tl_prev = clock64();
+#define SL_MARK(i) { const long long c_ = clock64(); tl[i] += c_ - tl_prev; tl_prev = c_; }
+#else
+#define SL_MARK(i)
+#endif
     if (threadIdx.x == 0) {
         for (int s = 0; s < STREAM_NS; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + STREAM_NS + s), G); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x < 8) reinterpret_cast<double *>(smem_raw + 128)[threadIdx.x] = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = xg[i];
     __syncthreads();
     if (warp < 2 * G) {
         const int grp = warp & 1, r = warp >> 1;
         const int pair_threads = 2 * G * 32;
+        const int sub = 32 / S, slot = lane / sub;
+        const int lis = lane - slot * sub;       // lane in slot
+        const bool leader = lis == 0;
+        const int GS = G * S;
         for (int g = grp; g < totalw; g += 2) {
             const int s = g & (STREAM_NS - 1);
+            SL_MARK(7)
             mbar_wait(smem_u32(bars + s), (g / STREAM_NS) & 1);
+            SL_MARK(0)
             unsigned char *blk = ring + stage_off[s];
             const int4 hd = *reinterpret_cast<const int4 *>(blk);                   // nrows, first row & ~1, rhs count, block bytes
             const int *rec_off = reinterpret_cast<const int *>(blk + 16);
             const double *bseg = reinterpret_cast<const double *>(blk + hd.w);
-            // ---- before the barrier: products of every entry (late ones are redone below), prefix chain
-            for (int ri = r; ri < hd.x; ri += G) {
-                unsigned char *rec = blk + rec_off[ri];
-                const int4 rh = *reinterpret_cast<const int4 *>(rec);               // row, prefix_pad, len_pad, nlate
-                double *val = reinterpret_cast<double *>(rec + 32);
-                const int *col = reinterpret_cast<const int *>(val + rh.z);
-                for (int p0 = 0; p0 < rh.z; p0 += 128) {
-                    int j[4];
-                    double v[4], xv[4];
+            // ---- before the barrier: products of every entry (late ones are redone below), prefix chains.
+            // Everything the post-barrier half of the FIRST round needs is kept in registers (c_*), so that its
+            // dependent path is: x of the late entries -> product -> store -> suffix chain -> divide -> store.
+            bool c_mine = false;
+            unsigned c_suf = 0;                    // shared-space address of the suffix products
+            int c_cnt = 0, c_maxc = 0, c_row = 0, c_nlate = 0;
+            double c_t = 0.0, c_d = 0.0;
+            unsigned c_late = 0;                   // shared-space address of the late list
+            StreamLateDev c_e = {0.0, 0, 0};
+            unsigned c_val = 0;
+            for (int base = 0; base < hd.x; base += GS) {
+                for (int ri = base + r; ri < min(base + GS, hd.x); ri += G) {        // all 32 lanes on one row at a time
+                    unsigned char *rec = blk + rec_off[ri];
+                    const int len_pad = reinterpret_cast<const int *>(rec)[2];
+                    // explicit shared-space accesses in program order (volatile asm): 8 column loads, then the 16 value /
+                    // x loads they feed, then the products -- ptxas otherwise sinks every value load next to its multiply
+                    const unsigned val_a = smem_u32(rec + 32), col_a = val_a + 8u * (unsigned)len_pad;
+                    for (int p0 = 0; p0 < len_pad; p0 += 256) {
+                        int j[8];
+                        double v[8], xv[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const int p = p0 + u * 32 + lane; j[u] = p < rh.z ? col[p] : -1; }
+                        for (int u = 0; u < 8; ++u) { const int p = p0 + u * 32 + lane; j[u] = lds_s32(col_a + 4u * (unsigned)(p < len_pad ? p : 0)); if (p >= len_pad) j[u] = -1; }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const int p = p0 + u * 32 + lane; v[u] = j[u] >= 0 ? val[p] : 0.0; xv[u] = j[u] >= 0 ? x[j[u]] : 0.0; }
+                        for (int u = 0; u < 8; ++u) {
+                            const int p = p0 + u * 32 + lane;
+                            v[u] = lds_f64(val_a + 8u * (unsigned)(p < len_pad ? p : 0));
+                            xv[u] = lds_f64(x_a + 8u * (unsigned)max(j[u], 0));
+                        }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const int p = p0 + u * 32 + lane; if (j[u] >= 0) val[p] = __dmul_rn(v[u], xv[u]); }
+                        for (int u = 0; u < 8; ++u) { const int p = p0 + u * 32 + lane; if (j[u] >= 0) sts_f64(val_a + 8u * (unsigned)p, __dmul_rn(v[u], xv[u])); }
+                    }
                 }
                 __syncwarp();
-                const double t = chain_fold<true>(bseg[rh.x - hd.y], reinterpret_cast<const double2 *>(val), rh.y);
-                if (lane == 0) reinterpret_cast<double *>(rec)[3] = t;
+                SL_MARK(1)
+                const int ri = base + slot * G + r;
+                const bool mine = ri < hd.x;
+                unsigned char *rec = blk + (mine ? rec_off[ri] : rec_off[0]);
+                const int4 rh = *reinterpret_cast<const int4 *>(rec);               // row, prefix_pad, len_pad, nlate
+                const int cnt = mine ? rh.y : 0;
+                const int maxc = __reduce_max_sync(FULL, cnt);
+                const double t = chain_fold_slots(mine ? bseg[rh.x - hd.y] : 0.0, reinterpret_cast<const double2 *>(rec + 32), cnt, maxc, zeros);
+                if (base == 0) {
+                    c_mine = mine; c_row = rh.x; c_t = t; c_d = reinterpret_cast<const double *>(rec)[2];
+                    c_val = smem_u32(rec + 32);
+                    c_suf = c_val + 8u * (unsigned)rh.y;
+                    c_cnt = mine ? rh.z - rh.y : 0;
+                    c_maxc = __reduce_max_sync(FULL, c_cnt);
+                    c_nlate = mine ? rh.w : 0;
+                    c_late = c_val + 12u * (unsigned)rh.z;
+                    if (lis < c_nlate) c_e = *reinterpret_cast<const StreamLateDev *>(rec + 32 + 12 * rh.z + 16 * lis);
+                } else if (mine && leader) reinterpret_cast<double *>(rec)[3] = t;
+#ifdef AMGB200_TIMELINE
+                if (t == 1.2345e300) tl[9] = 1;
+#endif
+                SL_MARK(2)
             }
             __syncwarp();
             if (g > 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + ((g - 1) & 7)), "r"(pair_threads) : "memory");
-            // ---- after the barrier: late products, suffix chain, x_k
-            for (int ri = r; ri < hd.x; ri += G) {
-                unsigned char *rec = blk + rec_off[ri];
+            SL_MARK(3)
+            // ---- after the barrier: late products, suffix chains, x_k
+            {
+                if (lis < c_nlate) sts_f64(c_val + 8u * (unsigned)c_e.pos, __dmul_rn(c_e.val, lds_f64(x_a + 8u * (unsigned)c_e.col)));
+                for (int i = lis + sub; i < c_nlate; i += sub) {
+                    const double lv = lds_f64(c_late + 16u * (unsigned)i);
+                    const int lp = lds_s32(c_late + 16u * (unsigned)i + 8u), lc = lds_s32(c_late + 16u * (unsigned)i + 12u);
+                    sts_f64(c_val + 8u * (unsigned)lp, __dmul_rn(lv, lds_f64(x_a + 8u * (unsigned)lc)));
+                }
+                __syncwarp();
+                SL_MARK(4)
+                const double t = chain_fold_slots(c_t, reinterpret_cast<const double2 *>(__cvta_shared_to_generic(c_suf)), c_cnt, c_maxc, zeros);
+#ifdef AMGB200_TIMELINE
+                if (t == 1.2345e300) tl[9] = 1;
+                SL_MARK(5)
+#endif
+                if (c_mine && leader && fabs(c_d) > GS_TINY) sts_f64(x_a + 8u * (unsigned)c_row, gs_quotient(t, c_d, recip));
+                SL_MARK(6)
+            }
+            for (int base = GS; base < hd.x; base += GS) {                           // wavefront wider than G*S rows: further rounds
+                const int ri = base + slot * G + r;
+                const bool mine = ri < hd.x;
+                unsigned char *rec = blk + (mine ? rec_off[ri] : rec_off[0]);
                 const int4 rh = *reinterpret_cast<const int4 *>(rec);
                 double *val = reinterpret_cast<double *>(rec + 32);
-                const StreamLateDev *lt = reinterpret_cast<const StreamLateDev *>(reinterpret_cast<const int *>(val + rh.z) + rh.z);
-                for (int i = lane; i < rh.w; i += 32) { const StreamLateDev e = lt[i]; val[e.pos] = __dmul_rn(e.val, x[e.col]); }
+                if (mine) {
+                    const StreamLateDev *lt = reinterpret_cast<const StreamLateDev *>(reinterpret_cast<const int *>(val + rh.z) + rh.z);
+                    for (int i = lis; i < rh.w; i += sub) { const StreamLateDev e = lt[i]; val[e.pos] = __dmul_rn(e.val, lds_f64(x_a + 8u * (unsigned)e.col)); }
+                }
                 __syncwarp();
                 const double2 dt = *reinterpret_cast<const double2 *>(rec + 16);    // diag, prefix accumulator
-                const double t = chain_fold<true>(dt.y, reinterpret_cast<const double2 *>(val + rh.y), rh.z - rh.y);
-                if (lane == 0 && fabs(dt.x) > GS_TINY) x[rh.x] = gs_quotient(t, dt.x, recip);
+                const int cnt = mine ? rh.z - rh.y : 0;
+                const int maxc = __reduce_max_sync(FULL, cnt);
+                const double t = chain_fold_slots(dt.y, reinterpret_cast<const double2 *>(val + rh.y), cnt, maxc, zeros);
+                if (mine && leader && fabs(dt.x) > GS_TINY) sts_f64(x_a + 8u * (unsigned)rh.x, gs_quotient(t, dt.x, recip));
             }
             // bar.arrive orders this thread's prior shared-memory stores before the consumers' bar.sync (PTX ISA, bar:
             // producer/consumer example)
@@ -864,6 +979,7 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
             __syncwarp();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // my generic writes to the block precede its reuse by the async proxy
             if (lane == 0) mbar_arrive(smem_u32(bars + STREAM_NS + s));
+            SL_MARK(8)
             if (g + 2 < totalw) asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");   // whole group done with g
         }
     } else if (lane == 0) {
@@ -895,6 +1011,9 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
             if (++wl == W) wl = 0;
         }
     }
+#ifdef AMGB200_TIMELINE
+    if (dbg && lane == 0 && warp < 2) for (int i = 0; i < 10; ++i) dbg[warp * 16 + i] = tl[i];
+#endif
     __syncwarp();
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) xg[i] = x[i];
