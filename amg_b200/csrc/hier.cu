@@ -308,7 +308,7 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
                 printf("   stream timeline group %d warp r=0 (cycles per wavefront, %d wavefronts, G=%d):", g2, iters, lv.stream_G);
                 long long tot = 0;
                 for (int i = 0; i < 9; ++i) { printf("  %s %lld", nm[i], hd[g2 * 16 + i] / iters); tot += hd[g2 * 16 + i]; }
-                printf("  | total %lld\n", tot / iters);
+                printf("  | total %lld | suffix terms folded per wavefront %lld\n", tot / iters, hd[g2 * 16 + 9] / iters);
             }
         }
 #endif
@@ -933,18 +933,16 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             if ((long long)SL.max_block * 2 <= ring) {
                 lv.strategy = 4;
                 lv.stream_ring = (int)(ring & ~15LL);
-                // 2 groups x 4 warps = two chaining warps per SM sub-partition (more only contend for the fp64 pipe;
-                // measured sweep on 128^3 levels 4-6: G=4 best or within 1 %)
-                lv.stream_G = std::max(1, std::min(lv.max_width, 4));
-                if (getenv("AMGB200_STREAM_G")) lv.stream_G = std::max(1, std::min(STREAM_MAX_G, atoi(getenv("AMGB200_STREAM_G"))));
-                // row slots per warp: the widest wavefront in one round if possible (rows go to different warps first,
-                // so unused slots cost nothing)
+                // product warps per group (1, 2 or 4) and row slots of the folding warp (the widest wavefront in one
+                // round if possible: unused slots cost nothing)
+                lv.stream_G = lv.max_width >= 3 ? 4 : lv.max_width;
+                if (getenv("AMGB200_STREAM_G")) { const int g = atoi(getenv("AMGB200_STREAM_G")); lv.stream_G = g >= 4 ? 4 : g >= 2 ? 2 : 1; }
                 lv.stream_S = 1;
-                while (lv.stream_S < 8 && lv.stream_G * lv.stream_S < lv.max_width) lv.stream_S *= 2;
-                if (getenv("AMGB200_STREAM_S")) lv.stream_S = std::max(1, std::min(32, atoi(getenv("AMGB200_STREAM_S"))));
+                while (lv.stream_S < 32 && lv.stream_S < lv.max_width) lv.stream_S *= 2;
+                if (getenv("AMGB200_STREAM_S")) { int v = std::max(1, std::min(32, atoi(getenv("AMGB200_STREAM_S")))); lv.stream_S = 1; while (lv.stream_S < v) lv.stream_S *= 2; }
                 lv.d_stream = dev_upload(SL.data);
                 lv.d_blk_ptr = dev_upload(SL.blk_ptr);
-                if (h->opt.verbose >= 2) printf("      streaming CTA smoother: %d consumer warps/group x %d row slots, ring %d B, wavefront block mean %lld B max %d B, stream %.1f MB\n", lv.stream_G, lv.stream_S, lv.stream_ring, SL.mean_block, SL.max_block, SL.data.size() / 1e6);
+                if (h->opt.verbose >= 2) printf("      streaming CTA smoother: 2 groups of %d product warps, %d row slots in the folding warp, ring %d B, wavefront block mean %lld B max %d B, stream %.1f MB\n", lv.stream_G, lv.stream_S, lv.stream_ring, SL.mean_block, SL.max_block, SL.data.size() / 1e6);
             }
         }
     }

@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
 // Dynamic shared memory: [mbarriers full[NS], empty[NS] | ring offsets | 64 B of zeros : 256 B][x : n doubles][ring]
 // ------------------------------------------------------------------------------------------
 constexpr int STREAM_NS = 4;                  // wavefront blocks in flight (ring descriptors)
-constexpr int STREAM_MAX_G = 8;               // consumer warps per group
+constexpr int STREAM_MAX_G = 4;               // product warps per group (1, 2 or 4)
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
@@ -792,6 +792,14 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     do {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
+}
+__device__ __forceinline__ void mbar_wait_sleep(unsigned bar, unsigned parity) {
+    unsigned ok;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(400);
+    }
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -805,45 +813,51 @@ struct StreamLateDev { double val; int pos; int col; };
 // sp2 of ITS slot's row; slots with fewer terms than the warp-wide maximum `maxc` idle on exact no-ops (t - (+0.0)).
 // One warp-wide DSUB then advances up to 32/sub rows at once: the fp64 pipe (4 cycles per warp instruction per
 // sub-partition) is shared by a quarter as many chaining warps.  Nothing beyond a slot's own cnt is read.
-__device__ __forceinline__ double chain_fold_slots(double t, const double2 *sp2, int cnt, int maxc, const double2 *zeros) {
+__device__ __forceinline__ double2 lds_v2f64(unsigned a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
+// sp / zeros are shared-space addresses.  The loads are volatile asm in program order, two blocks (16 terms) ahead of the
+// chain; no __syncwarp in the loop (inside a branch the compiler cannot prove uniform it becomes a BRA.DIV per block,
+// measured +1.9 cycles per term).
+__device__ __forceinline__ double chain_fold_slots(double t, unsigned sp, int cnt, int maxc, unsigned zeros) {
 #define AMGB200_FOLD(v)                                                        \
     _Pragma("unroll") for (int u = 0; u < 4; ++u) { t = __dsub_rn(t, v[u].x); t = __dsub_rn(t, v[u].y); }
     // blocks past this slot's own cnt are read from a 64-byte block of zeros: no branch, no select on the chain
 #define AMGB200_LOAD(v, q)                                                     \
     {                                                                          \
-        const double2 *src_ = (q) < cnt ? sp2 + ((q) >> 1) : zeros;            \
-        _Pragma("unroll") for (int u = 0; u < 4; ++u) v[u] = src_[u];          \
-    }                                                                          \
-    __syncwarp();
-    double2 va[4], vb[4];
+        const unsigned src_ = (q) < cnt ? sp + 8u * (unsigned)(q) : zeros;     \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) v[u] = lds_v2f64(src_ + 16u * u); \
+    }
+    double2 v0[4], v1[4], v2[4];
     int q = 0;
-    AMGB200_LOAD(va, 0)
+    AMGB200_LOAD(v0, 0)
+    AMGB200_LOAD(v1, 8)
 #pragma unroll 1
-    for (; q + 32 <= maxc; q += 32) {
-        AMGB200_LOAD(vb, q + 8)  AMGB200_FOLD(va)
-        AMGB200_LOAD(va, q + 16) AMGB200_FOLD(vb)
-        AMGB200_LOAD(vb, q + 24) AMGB200_FOLD(va)
-        AMGB200_LOAD(va, q + 32) AMGB200_FOLD(vb)
+    for (; q + 24 <= maxc; q += 24) {
+        AMGB200_LOAD(v2, q + 16) AMGB200_FOLD(v0)
+        AMGB200_LOAD(v0, q + 24) AMGB200_FOLD(v1)
+        AMGB200_LOAD(v1, q + 32) AMGB200_FOLD(v2)
     }
 #pragma unroll 1
     for (; q < maxc; q += 8) {
-        AMGB200_LOAD(vb, q + 8)  AMGB200_FOLD(va)
+        AMGB200_LOAD(v2, q + 16) AMGB200_FOLD(v0)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) va[u] = vb[u];
+        for (int u = 0; u < 4; ++u) { v0[u] = v1[u]; v1[u] = v2[u]; }
     }
 #undef AMGB200_FOLD
 #undef AMGB200_LOAD
     return t;
 }
 
-// row ri of a wavefront -> consumer warp ri % G, slot (ri / G) % S of that warp, round ri / (G*S)
 __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_kernel(
     const unsigned char *__restrict__ stream, const int *__restrict__ blk_ptr, const int *__restrict__ wf_row_ptr,
     const double *__restrict__ b, double *xg, int n, int W, int nsweeps, int G, int S, int ring_bytes, int recip, long long *dbg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);      // full[0..NS), empty[0..NS)
     volatile int *stage_off = reinterpret_cast<volatile int *>(smem_raw + 64);
-    const double2 *zeros = reinterpret_cast<const double2 *>(smem_raw + 128);
+    const unsigned zeros_a = smem_u32(smem_raw + 128);
     double *x = reinterpret_cast<double *>(smem_raw + 256);
     unsigned char *ring = smem_raw + 256 + (((size_t)n * 8 + 15) & ~(size_t)15);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -857,19 +871,23 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
 #define SL_MARK(i)
 #endif
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STREAM_NS; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + STREAM_NS + s), G); }
+        for (int s = 0; s < STREAM_NS; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + STREAM_NS + s), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 8) reinterpret_cast<double *>(smem_raw + 128)[threadIdx.x] = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = xg[i];
     __syncthreads();
     if (warp < 2 * G) {
-        const int grp = warp & 1, r = warp >> 1;
-        const int pair_threads = 2 * G * 32;
+        // warps [0,G) = group 0, [G,2G) = group 1.  All G warps of a group multiply (one row at a time, rows dealt round-robin);
+        // ONE warp per group folds: its lanes are split into S row slots, so a single warp-wide DSUB advances every row
+        // of the wavefront, and the two folding warps sit on different SM sub-partitions (a warp-wide DADD occupies a
+        // sub-partition's fp64 pipe for 4 cycles: two chains on one pipe slow each other down, measured 8.6 -> 11 cycles
+        // per term).  G is 1, 2 or 4.
+        const int grp = warp / G, r = warp - grp * G;
+        const bool folder = r == (G > 1 ? grp : 0);
         const int sub = 32 / S, slot = lane / sub;
         const int lis = lane - slot * sub;       // lane in slot
         const bool leader = lis == 0;
-        const int GS = G * S;
         for (int g = grp; g < totalw; g += 2) {
             const int s = g & (STREAM_NS - 1);
             SL_MARK(7)
@@ -879,111 +897,118 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
             const int4 hd = *reinterpret_cast<const int4 *>(blk);                   // nrows, first row & ~1, rhs count, block bytes
             const int *rec_off = reinterpret_cast<const int *>(blk + 16);
             const double *bseg = reinterpret_cast<const double *>(blk + hd.w);
-            // ---- before the barrier: products of every entry (late ones are redone below), prefix chains.
-            // Everything the post-barrier half of the FIRST round needs is kept in registers (c_*), so that its
-            // dependent path is: x of the late entries -> product -> store -> suffix chain -> divide -> store.
-            bool c_mine = false;
-            unsigned c_suf = 0;                    // shared-space address of the suffix products
-            int c_cnt = 0, c_maxc = 0, c_row = 0, c_nlate = 0;
-            double c_t = 0.0, c_d = 0.0;
-            unsigned c_late = 0;                   // shared-space address of the late list
-            StreamLateDev c_e = {0.0, 0, 0};
-            unsigned c_val = 0;
-            for (int base = 0; base < hd.x; base += GS) {
-                for (int ri = base + r; ri < min(base + GS, hd.x); ri += G) {        // all 32 lanes on one row at a time
-                    unsigned char *rec = blk + rec_off[ri];
-                    const int len_pad = reinterpret_cast<const int *>(rec)[2];
-                    // explicit shared-space accesses in program order (volatile asm): 8 column loads, then the 16 value /
-                    // x loads they feed, then the products -- ptxas otherwise sinks every value load next to its multiply
-                    const unsigned val_a = smem_u32(rec + 32), col_a = val_a + 8u * (unsigned)len_pad;
-                    for (int p0 = 0; p0 < len_pad; p0 += 256) {
-                        int j[8];
-                        double v[8], xv[8];
+            // ---- before the barrier: products of every entry (late ones are redone below) ...
+            for (int ri = r; ri < hd.x; ri += G) {                                   // all 32 lanes on one row at a time
+                unsigned char *rec = blk + rec_off[ri];
+                const int len_pad = reinterpret_cast<const int *>(rec)[2];
+                // explicit shared-space accesses in program order (volatile asm): 8 column loads, then the 16 value /
+                // x loads they feed, then the products -- ptxas otherwise sinks every value load next to its multiply
+                const unsigned val_a = smem_u32(rec + 32), col_a = val_a + 8u * (unsigned)len_pad;
+                for (int p0 = 0; p0 < len_pad; p0 += 256) {
+                    int j[8];
+                    double v[8], xv[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) { const int p = p0 + u * 32 + lane; j[u] = lds_s32(col_a + 4u * (unsigned)(p < len_pad ? p : 0)); if (p >= len_pad) j[u] = -1; }
+                    for (int u = 0; u < 8; ++u) { const int p = p0 + u * 32 + lane; j[u] = lds_s32(col_a + 4u * (unsigned)(p < len_pad ? p : 0)); if (p >= len_pad) j[u] = -1; }
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int p = p0 + u * 32 + lane;
-                            v[u] = lds_f64(val_a + 8u * (unsigned)(p < len_pad ? p : 0));
-                            xv[u] = lds_f64(x_a + 8u * (unsigned)max(j[u], 0));
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) { const int p = p0 + u * 32 + lane; if (j[u] >= 0) sts_f64(val_a + 8u * (unsigned)p, __dmul_rn(v[u], xv[u])); }
+                    for (int u = 0; u < 8; ++u) {
+                        const int p = p0 + u * 32 + lane;
+                        v[u] = lds_f64(val_a + 8u * (unsigned)(p < len_pad ? p : 0));
+                        xv[u] = lds_f64(x_a + 8u * (unsigned)max(j[u], 0));
                     }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const int p = p0 + u * 32 + lane; if (j[u] >= 0) sts_f64(val_a + 8u * (unsigned)p, __dmul_rn(v[u], xv[u])); }
                 }
-                __syncwarp();
-                SL_MARK(1)
-                const int ri = base + slot * G + r;
-                const bool mine = ri < hd.x;
-                unsigned char *rec = blk + (mine ? rec_off[ri] : rec_off[0]);
-                const int4 rh = *reinterpret_cast<const int4 *>(rec);               // row, prefix_pad, len_pad, nlate
-                const int cnt = mine ? rh.y : 0;
-                const int maxc = __reduce_max_sync(FULL, cnt);
-                const double t = chain_fold_slots(mine ? bseg[rh.x - hd.y] : 0.0, reinterpret_cast<const double2 *>(rec + 32), cnt, maxc, zeros);
-                if (base == 0) {
-                    c_mine = mine; c_row = rh.x; c_t = t; c_d = reinterpret_cast<const double *>(rec)[2];
-                    c_val = smem_u32(rec + 32);
-                    c_suf = c_val + 8u * (unsigned)rh.y;
-                    c_cnt = mine ? rh.z - rh.y : 0;
-                    c_maxc = __reduce_max_sync(FULL, c_cnt);
-                    c_nlate = mine ? rh.w : 0;
-                    c_late = c_val + 12u * (unsigned)rh.z;
-                    if (lis < c_nlate) c_e = *reinterpret_cast<const StreamLateDev *>(rec + 32 + 12 * rh.z + 16 * lis);
-                } else if (mine && leader) reinterpret_cast<double *>(rec)[3] = t;
+            }
+            SL_MARK(1)
+            if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");      // all products of the wavefront are in place
+            else __syncwarp();
+            if (folder) {
+                // ... and the prefix chains.  Everything the post-barrier half of the FIRST round needs is kept in
+                // registers (c_*): its dependent path is x of the late entries -> product -> store -> suffix chain ->
+                // divide -> store.
+                bool c_mine = false;
+                unsigned c_suf = 0, c_late = 0, c_val = 0;       // shared-space addresses: suffix products, late list, products
+                int c_cnt = 0, c_maxc = 0, c_row = 0, c_nlate = 0;
+                double c_t = 0.0, c_d = 0.0;
+                StreamLateDev c_e = {0.0, 0, 0};
+                for (int base = 0; base < hd.x; base += S) {
+                    const int ri = base + slot;
+                    const bool mine = ri < hd.x;
+                    unsigned char *rec = blk + (mine ? rec_off[ri] : rec_off[0]);
+                    const int4 rh = *reinterpret_cast<const int4 *>(rec);               // row, prefix_pad, len_pad, nlate
+                    const int cnt = mine ? rh.y : 0;
+                    const int maxc = __reduce_max_sync(FULL, cnt);
+                    const double t = chain_fold_slots(mine ? bseg[rh.x - hd.y] : 0.0, smem_u32(rec + 32), cnt, maxc, zeros_a);
+                    if (base == 0) {
+                        c_mine = mine; c_row = rh.x; c_t = t; c_d = reinterpret_cast<const double *>(rec)[2];
+                        c_val = smem_u32(rec + 32);
+                        c_suf = c_val + 8u * (unsigned)rh.y;
+                        c_cnt = mine ? rh.z - rh.y : 0;
+                        c_maxc = __reduce_max_sync(FULL, c_cnt);
+                        c_nlate = mine ? rh.w : 0;
+                        c_late = c_val + 12u * (unsigned)rh.z;
+                        if (lis < c_nlate) c_e = *reinterpret_cast<const StreamLateDev *>(rec + 32 + 12 * rh.z + 16 * lis);
+                    } else if (mine && leader) reinterpret_cast<double *>(rec)[3] = t;
 #ifdef AMGB200_TIMELINE
-                if (t == 1.2345e300) tl[9] = 1;
+                    if (t == 1.2345e300) tl[9] = 1;
 #endif
+                }
                 SL_MARK(2)
-            }
-            __syncwarp();
-            if (g > 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + ((g - 1) & 7)), "r"(pair_threads) : "memory");
-            SL_MARK(3)
-            // ---- after the barrier: late products, suffix chains, x_k
-            {
-                if (lis < c_nlate) sts_f64(c_val + 8u * (unsigned)c_e.pos, __dmul_rn(c_e.val, lds_f64(x_a + 8u * (unsigned)c_e.col)));
-                for (int i = lis + sub; i < c_nlate; i += sub) {
-                    const double lv = lds_f64(c_late + 16u * (unsigned)i);
-                    const int lp = lds_s32(c_late + 16u * (unsigned)i + 8u), lc = lds_s32(c_late + 16u * (unsigned)i + 12u);
-                    sts_f64(c_val + 8u * (unsigned)lp, __dmul_rn(lv, lds_f64(x_a + 8u * (unsigned)lc)));
-                }
                 __syncwarp();
-                SL_MARK(4)
-                const double t = chain_fold_slots(c_t, reinterpret_cast<const double2 *>(__cvta_shared_to_generic(c_suf)), c_cnt, c_maxc, zeros);
+                if (g > 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + ((g - 1) & 7)), "r"(64) : "memory");
+                SL_MARK(3)
+                // ---- after the barrier: late products, suffix chains, x_k
+                {
+                    if (lis < c_nlate) sts_f64(c_val + 8u * (unsigned)c_e.pos, __dmul_rn(c_e.val, lds_f64(x_a + 8u * (unsigned)c_e.col)));
+                    for (int i = lis + sub; i < c_nlate; i += sub) {
+                        const double lv = lds_f64(c_late + 16u * (unsigned)i);
+                        const int lp = lds_s32(c_late + 16u * (unsigned)i + 8u), lc = lds_s32(c_late + 16u * (unsigned)i + 12u);
+                        sts_f64(c_val + 8u * (unsigned)lp, __dmul_rn(lv, lds_f64(x_a + 8u * (unsigned)lc)));
+                    }
+                    __syncwarp();
+                    SL_MARK(4)
+                    const double t = chain_fold_slots(c_t, c_suf, c_cnt, c_maxc, zeros_a);
 #ifdef AMGB200_TIMELINE
-                if (t == 1.2345e300) tl[9] = 1;
-                SL_MARK(5)
+                    if (t == 1.2345e300) tl[9] = 1;
+                    SL_MARK(5)
+                    tl[9] += c_maxc;
 #endif
-                if (c_mine && leader && fabs(c_d) > GS_TINY) sts_f64(x_a + 8u * (unsigned)c_row, gs_quotient(t, c_d, recip));
-                SL_MARK(6)
-            }
-            for (int base = GS; base < hd.x; base += GS) {                           // wavefront wider than G*S rows: further rounds
-                const int ri = base + slot * G + r;
-                const bool mine = ri < hd.x;
-                unsigned char *rec = blk + (mine ? rec_off[ri] : rec_off[0]);
-                const int4 rh = *reinterpret_cast<const int4 *>(rec);
-                double *val = reinterpret_cast<double *>(rec + 32);
-                if (mine) {
-                    const StreamLateDev *lt = reinterpret_cast<const StreamLateDev *>(reinterpret_cast<const int *>(val + rh.z) + rh.z);
-                    for (int i = lis; i < rh.w; i += sub) { const StreamLateDev e = lt[i]; val[e.pos] = __dmul_rn(e.val, lds_f64(x_a + 8u * (unsigned)e.col)); }
+                    if (c_mine && leader && fabs(c_d) > GS_TINY) sts_f64(x_a + 8u * (unsigned)c_row, gs_quotient(t, c_d, recip));
+                    SL_MARK(6)
                 }
-                __syncwarp();
-                const double2 dt = *reinterpret_cast<const double2 *>(rec + 16);    // diag, prefix accumulator
-                const int cnt = mine ? rh.z - rh.y : 0;
-                const int maxc = __reduce_max_sync(FULL, cnt);
-                const double t = chain_fold_slots(dt.y, reinterpret_cast<const double2 *>(val + rh.y), cnt, maxc, zeros);
-                if (mine && leader && fabs(dt.x) > GS_TINY) sts_f64(x_a + 8u * (unsigned)rh.x, gs_quotient(t, dt.x, recip));
+                for (int base = S; base < hd.x; base += S) {                             // wavefront wider than S rows: further rounds
+                    const int ri = base + slot;
+                    const bool mine = ri < hd.x;
+                    unsigned char *rec = blk + (mine ? rec_off[ri] : rec_off[0]);
+                    const int4 rh = *reinterpret_cast<const int4 *>(rec);
+                    double *val = reinterpret_cast<double *>(rec + 32);
+                    if (mine) {
+                        const StreamLateDev *lt = reinterpret_cast<const StreamLateDev *>(reinterpret_cast<const int *>(val + rh.z) + rh.z);
+                        for (int i = lis; i < rh.w; i += sub) { const StreamLateDev e = lt[i]; val[e.pos] = __dmul_rn(e.val, lds_f64(x_a + 8u * (unsigned)e.col)); }
+                    }
+                    __syncwarp();
+                    const double2 dt = *reinterpret_cast<const double2 *>(rec + 16);    // diag, prefix accumulator
+                    const int cnt = mine ? rh.z - rh.y : 0;
+                    const int maxc = __reduce_max_sync(FULL, cnt);
+                    const double t = chain_fold_slots(dt.y, smem_u32(val + rh.y), cnt, maxc, zeros_a);
+                    if (mine && leader && fabs(dt.x) > GS_TINY) sts_f64(x_a + 8u * (unsigned)rh.x, gs_quotient(t, dt.x, recip));
+                }
+                // bar.arrive orders this thread's prior shared-memory stores before the consumer's bar.sync (PTX ISA, bar:
+                // producer/consumer example)
+                if (g + 1 < totalw) asm volatile("bar.arrive %0, %1;" ::"r"(1 + (g & 7)), "r"(64) : "memory");
+                SL_MARK(8)
             }
-            // bar.arrive orders this thread's prior shared-memory stores before the consumers' bar.sync (PTX ISA, bar:
-            // producer/consumer example)
-            if (g + 1 < totalw) asm volatile("bar.arrive %0, %1;" ::"r"(1 + (g & 7)), "r"(pair_threads) : "memory");
-            __syncwarp();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // my generic writes to the block precede its reuse by the async proxy
-            if (lane == 0) mbar_arrive(smem_u32(bars + STREAM_NS + s));
-            SL_MARK(8)
-            if (g + 2 < totalw) asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");   // whole group done with g
+            // every warp's generic writes to the block precede its reuse by the async proxy: fence, group barrier, release
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");   // wavefront g is complete
+            else __syncwarp();
+            if (folder && lane == 0) mbar_arrive(smem_u32(bars + STREAM_NS + s));
         }
+#ifdef AMGB200_TIMELINE
+        if (dbg && lane == 0 && folder) for (int i = 0; i < 10; ++i) dbg[grp * 16 + i] = tl[i];
+#endif
     } else if (lane == 0) {
-        // ---- loader: in-order ring allocation; a block is released when all G warps of its group have arrived on empty[s]
+        // ---- loader: in-order ring allocation; a block is released when its group's folding warp has arrived on empty[s]
         int head = 0, tail = 0, inflight = 0, g_old = 0, wl = 0;
         for (int g = 0; g < totalw; ++g) {
             const int s = g & (STREAM_NS - 1);
@@ -998,7 +1023,9 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
                         if (need < tail) { head = 0; break; }
                     } else if (head + need < tail) break;
                 }
-                mbar_wait(smem_u32(bars + STREAM_NS + (g_old & (STREAM_NS - 1))), (g_old / STREAM_NS) & 1);
+                // (polite wait: the loader is several wavefronts ahead, and a tight try_wait loop would steal issue slots
+                // from the folding warp that shares its SM sub-partition)
+                mbar_wait_sleep(smem_u32(bars + STREAM_NS + (g_old & (STREAM_NS - 1))), (g_old / STREAM_NS) & 1);
                 ++g_old; --inflight;
                 tail = inflight ? stage_off[g_old & (STREAM_NS - 1)] : head;
             }
@@ -1011,9 +1038,6 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
             if (++wl == W) wl = 0;
         }
     }
-#ifdef AMGB200_TIMELINE
-    if (dbg && lane == 0 && warp < 2) for (int i = 0; i < 10; ++i) dbg[warp * 16 + i] = tl[i];
-#endif
     __syncwarp();
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) xg[i] = x[i];
