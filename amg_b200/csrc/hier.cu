@@ -936,7 +936,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                 // product warps per group (1, 2 or 4) and row slots of the folding warp (the widest wavefront in one
                 // round if possible: unused slots cost nothing)
                 lv.stream_G = lv.max_width >= 3 ? 4 : lv.max_width;
-                if (getenv("AMGB200_STREAM_G")) { const int g = atoi(getenv("AMGB200_STREAM_G")); lv.stream_G = g >= 4 ? 4 : g >= 2 ? 2 : 1; }
+                if (getenv("AMGB200_STREAM_G")) { const int g = atoi(getenv("AMGB200_STREAM_G")); lv.stream_G = g >= 8 ? 8 : g >= 4 ? 4 : g >= 2 ? 2 : 1; }
                 lv.stream_S = 1;
                 while (lv.stream_S < 32 && lv.stream_S < lv.max_width) lv.stream_S *= 2;
                 if (getenv("AMGB200_STREAM_S")) { int v = std::max(1, std::min(32, atoi(getenv("AMGB200_STREAM_S")))); lv.stream_S = 1; while (lv.stream_S < v) lv.stream_S *= 2; }

@@ -327,6 +327,11 @@ __device__ __forceinline__ void csr_prefetch_rows(const DMat &A, int i0, int i1,
 // sinking the loads next to their uses (which would expose ~30 cycles of shared-memory latency every few
 // terms).  Four blocks per loop trip: one taken branch per 32 terms.  Slots >= cnt hold +0.0 (exact no-ops);
 // reads run up to 16 slots past the staged chunk (STAGE pad).
+__device__ __forceinline__ double2 lds_v2f64(unsigned a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
 template <bool GS>
 __device__ __forceinline__ double chain_fold(double t, const double2 *sp2, int cnt) {
 #if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 1
@@ -337,9 +342,11 @@ __device__ __forceinline__ double chain_fold(double t, const double2 *sp2, int c
         if (GS) { t = __dsub_rn(t, v[u].x); t = __dsub_rn(t, v[u].y); }        \
         else { t = __dadd_rn(t, v[u].x); t = __dadd_rn(t, v[u].y); }           \
     }
+    // volatile-asm shared loads stay in program order and ahead of the chain; a __syncwarp fence here turns into a
+    // BRA.DIV per block wherever the compiler cannot prove the warp converged (+1.9 cycles per term, tools/ubench2.cu)
 #define AMGB200_LOAD(v, q)                                                     \
-    _Pragma("unroll") for (int u = 0; u < 4; ++u) v[u] = sp2[((q) >> 1) + u];  \
-    __syncwarp();
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) v[u] = lds_v2f64(sp + 8u * (unsigned)(q) + 16u * u);
+    const unsigned sp = (unsigned)__cvta_generic_to_shared(sp2);
     double2 va[4], vb[4];
     int q = 0;
     AMGB200_LOAD(va, 0)
@@ -782,7 +789,7 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
 // Dynamic shared memory: [mbarriers full[NS], empty[NS] | ring offsets | 64 B of zeros : 256 B][x : n doubles][ring]
 // ------------------------------------------------------------------------------------------
 constexpr int STREAM_NS = 4;                  // wavefront blocks in flight (ring descriptors)
-constexpr int STREAM_MAX_G = 4;               // product warps per group (1, 2 or 4)
+constexpr int STREAM_MAX_G = 8;               // product warps per group (1, 2, 4 or 8)
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
@@ -813,11 +820,6 @@ struct StreamLateDev { double val; int pos; int col; };
 // sp2 of ITS slot's row; slots with fewer terms than the warp-wide maximum `maxc` idle on exact no-ops (t - (+0.0)).
 // One warp-wide DSUB then advances up to 32/sub rows at once: the fp64 pipe (4 cycles per warp instruction per
 // sub-partition) is shared by a quarter as many chaining warps.  Nothing beyond a slot's own cnt is read.
-__device__ __forceinline__ double2 lds_v2f64(unsigned a) {
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
-    return v;
-}
 // sp / zeros are shared-space addresses.  The loads are volatile asm in program order, two blocks (16 terms) ahead of the
 // chain; no __syncwarp in the loop (inside a branch the compiler cannot prove uniform it becomes a BRA.DIV per block,
 // measured +1.9 cycles per term).

@@ -96,6 +96,34 @@ def test_gauss_seidel_cf_all_levels(name, sweeps, oracle):
         check_vec(dev, l, got, want, f"GS x{sweeps}")
 
 
+@pytest.mark.parametrize("strategy,kernel", [(None, "gs_stream_cta_kernel"), ("1", "gs_ordered_grid_kernel"),
+                                             ("2", "gs_ordered_cta_kernel"), ("3", "gs_ordered_cluster_kernel")])
+@pytest.mark.parametrize("name", ["p3d32", "v27_16"])
+def test_every_ordered_smoother_kernel_is_bit_identical(name, strategy, kernel, oracle, monkeypatch):
+    """the four launch strategies for ordered (wavefront) levels -- streaming single CTA (default where x fits in
+    shared memory), cooperative grid, single CTA, 16-CTA cluster -- all reproduce the sequential sweep bit for bit,
+    for 1, 2 and 3 sweeps per launch (3 sweeps wrap the shared-memory ring and the mbarrier phases several times)"""
+    if strategy is None:
+        monkeypatch.delenv("AMGB200_GS_STRATEGY", raising=False)
+    else:
+        monkeypatch.setenv("AMGB200_GS_STRATEGY", strategy)
+    kind, N, eps = CASES[name]
+    hier = HostHierarchy(generate(kind, N, eps), tol=1e-8)
+    dev = DeviceHierarchy(hier)
+    used = set()
+    for l in range(hier.num_levels - 1):
+        c = hier.level(l)
+        n = c.A.num_rows
+        used.add(dev.gs_kernel(l))
+        for sweeps in (1, 2, 3):
+            x0 = rng_vec(n, 170 + l)
+            b = rng_vec(n, 180 + l)
+            got = dev.smooth(l, sweeps, x0, b)
+            want = oracle.gs_cf(c.A, hier.cfmark(l), x0, b, sweeps, 1)
+            check_vec(dev, l, got, want, f"GS x{sweeps} ({dev.gs_kernel(l)})")
+    assert kernel in used, f"{kernel} was not exercised (kernels used: {sorted(used)})"
+
+
 @pytest.mark.parametrize("name", ["p2d64", "p3d16", "v27_12"])
 def test_residual_and_norm(name, oracle):
     A, hier, dev = case(name)

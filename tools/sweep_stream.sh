@@ -1,4 +1,4 @@
-for l in 4 5 6; do for G in 2 4 6 8; do for S in 1 2 4 8; do
-  r=$(AMGB200_STREAM_G=$G AMGB200_STREAM_S=$S timeout 100 python tools/prof_level.py p3d 128 $l 2>&1 | grep "ms per" | tail -1)
-  echo "L$l G=$G S=$S $r"
-done; done; done
+for l in 4 5 6; do for G in 2 8; do
+  r=$(AMGB200_STREAM_G=$G timeout 100 python tools/prof_level.py p3d 128 $l 2>&1 | grep "ms per" | tail -1)
+  echo "L$l G=$G $r"
+done; done
