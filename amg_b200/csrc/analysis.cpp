@@ -242,4 +242,92 @@ void build_stream(const DevLayout &L, StreamLayout &S) {
     }
 }
 
+void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, ClusterStreamLayout &SL) {
+    const int n = S.n, W = S.wf_count[0] + S.wf_count[1];
+    const std::vector<int> &wrp = S.wf_row_ptr;
+    auto r8 = [](int v) { return (v + 7) & ~7; };
+    std::vector<int> wf_of((size_t)n);
+    for (int w = 0; w < W; ++w) for (int k = wrp[w]; k < wrp[w + 1]; ++k) wf_of[k] = w;
+    // cyclic distance from the wavefront of column c back to wavefront w (1 = the wavefront just before)
+    auto dist = [&](int w, int c) { const int d = w - wf_of[c]; return d > 0 ? d : d + W; };
+    SL.C = C;
+    std::vector<int> rec_bytes((size_t)n), split((size_t)n), nlate((size_t)n);
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < n; ++k) {
+        const int i = S.order[k];
+        const int p0 = A.row_ptr[i], len = A.row_ptr[i + 1] - p0;
+        int sp = len, nl = 0;
+        for (int q = 0; q < len; ++q) {
+            const int c = S.pos[A.col_idx[p0 + q]];
+            if (c != k && dist(wf_of[k], c) <= 2) { if (q < sp) sp = q; ++nl; }
+        }
+        split[k] = sp; nlate[k] = nl;
+        rec_bytes[k] = 32 + (r8(sp) + r8(len - sp)) * 12 + nl * 24;
+        rec_bytes[k] = (rec_bytes[k] + 15) & ~15;
+    }
+    SL.blk_ptr.assign((size_t)W * C + 1, 0);
+    SL.max_block = 0; SL.max_local = 0; SL.max_width = 0;
+    for (int w = 0; w < W; ++w) {
+        const int width = wrp[w + 1] - wrp[w];
+        for (int c = 0; c < C; ++c) {
+            const int nr = width > c ? (width - c + C - 1) / C : 0;
+            long long bytes = 16 + (long long)((nr + 3) & ~3) * 4;
+            for (int li = 0; li < nr; ++li) bytes += rec_bytes[wrp[w] + c + li * C];
+            SL.blk_ptr[(size_t)w * C + c + 1] = SL.blk_ptr[(size_t)w * C + c] + (int)(bytes / 16);
+            SL.max_block = (int)std::max<long long>(SL.max_block, bytes);
+            SL.max_local = std::max(SL.max_local, nr);
+            SL.max_width = std::max(SL.max_width, width);
+        }
+    }
+    SL.data.resize((size_t)SL.blk_ptr[(size_t)W * C] * 16);
+    SL.mean_block = W ? (long long)SL.blk_ptr[(size_t)W * C] * 16 / ((long long)W * C) : 0;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int w = 0; w < W; ++w) {
+        const int width = wrp[w + 1] - wrp[w];
+        for (int c = 0; c < C; ++c) {
+            unsigned char *blk = SL.data.data() + (size_t)SL.blk_ptr[(size_t)w * C + c] * 16;
+            const int nr = width > c ? (width - c + C - 1) / C : 0;
+            int *hd = reinterpret_cast<int *>(blk);
+            hd[0] = nr; hd[1] = wrp[w]; hd[2] = width; hd[3] = (SL.blk_ptr[(size_t)w * C + c + 1] - SL.blk_ptr[(size_t)w * C + c]) * 16;
+            int *rec_off = hd + 4;
+            int off = 16 + ((nr + 3) & ~3) * 4;
+            for (int li = nr; li < ((nr + 3) & ~3); ++li) rec_off[li] = 0;
+            for (int li = 0; li < nr; ++li) {
+                const int k = wrp[w] + c + li * C, i = S.order[k];
+                rec_off[li] = off;
+                unsigned char *rec = blk + off;
+                const int p0 = A.row_ptr[i], len = A.row_ptr[i + 1] - p0, sp = split[k];
+                const int pre_pad = r8(sp), len_pad = pre_pad + r8(len - sp);
+                int *rh = reinterpret_cast<int *>(rec);
+                double *rd = reinterpret_cast<double *>(rec);
+                double *val = rd + 4;
+                int *col = reinterpret_cast<int *>(val + len_pad);
+                unsigned char *lt = reinterpret_cast<unsigned char *>(col + len_pad);
+                memset(rec, 0, (size_t)rec_bytes[k]);
+                for (int q = 0; q < len_pad; ++q) col[q] = -1;
+                double diag = 0.0;
+                int nl = 0;
+                for (int q = 0; q < len; ++q) {
+                    const int pos = q < sp ? q : pre_pad + (q - sp);
+                    const int cc = S.pos[A.col_idx[p0 + q]];
+                    const double v = A.val[p0 + q];
+                    if (cc == k) { diag = v; continue; }
+                    val[pos] = v; col[pos] = cc;
+                    const int d = dist(w, cc);
+                    if (d <= 2) {
+                        const int ii = cc - wrp[wf_of[cc]];
+                        StreamLateC e;
+                        e.val = v; e.pos = pos; e.col = cc; e.src = (d - 1) | (ii << 1); e.pad = 0;
+                        memcpy(lt + (size_t)nl * 24, &e, 24);
+                        ++nl;
+                    }
+                }
+                rh[0] = k; rh[1] = pre_pad; rh[2] = len_pad; rh[3] = nl;
+                rd[2] = diag; rd[3] = 0.0;
+                off += rec_bytes[k];
+            }
+        }
+    }
+}
+
 }  // namespace amgb200

@@ -85,6 +85,26 @@ struct StreamLayout {
 struct StreamLate { double val; int pos; int col; };
 void build_stream(const DevLayout &L, StreamLayout &S);
 
+// The same idea for levels that need several SMs (kernels.cuh, gs_stream_cluster_kernel): row i of a wavefront
+// (i = schedule row - first row of the wavefront) belongs to CTA i % C of a C-CTA cluster, local index i / C; block
+// (w, c) = blk_ptr[w*C + c] holds CTA c's rows of wavefront w.  x stays in global memory for entries at cyclic
+// wavefront distance >= 3; entries at distance 1 or 2 ("late") are read from the exchange buffers in
+// shared memory (every CTA receives every x of the last three wavefronts): late record = {double val; int32 pos;
+// int32 col; int32 src; int32 0} with src = (distance-1) | index within its wavefront << 1.  Block header: rows of
+// this CTA, first row of the wavefront, width of the wavefront, block bytes.  Record header and val/col arrays as in StreamLayout;
+// the prefix ends at the first late entry.
+struct StreamLateC { double val; int pos; int col; int src; int pad; };
+struct ClusterStreamLayout {
+    RawBuf<unsigned char> data;
+    std::vector<int> blk_ptr;      // W*C+1, in units of 16 bytes
+    int C = 0;
+    int max_block = 0;             // bytes
+    long long mean_block = 0;
+    int max_local = 0;             // largest number of rows one CTA gets from one wavefront
+    int max_width = 0;             // widest wavefront (rows)
+};
+void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, ClusterStreamLayout &SL);
+
 // mark == nullptr: single pass over all rows in natural order (no C/F ordering).
 void build_schedule(const amgb200_mat &A, const int *mark, Schedule &S);
 void identity_schedule(int n, Schedule &S);

@@ -4,6 +4,8 @@
 // right (rows of one wavefront are independent) the result is bit-identical to the reference's
 // sequential sweep.  Not a compute path of the product: nothing in hier.cu calls these.
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -34,10 +36,61 @@ void amgb200_debug_gs_walk(const amgb200_mat *A, const int *mark, int kind, int 
     Schedule S;
     build_schedule(*A, mark, S);
     DevLayout L;
-    build_layout(*A, S.order.data(), S.pos.data(), kind == 2 ? (int)KIND_CSR : kind, &S.wf_row_ptr, L);
+    build_layout(*A, S.order.data(), S.pos.data(), kind >= 2 ? (int)KIND_CSR : kind, &S.wf_row_ptr, L);
     const int n = S.n, W = S.wf_count[0] + S.wf_count[1];
     std::vector<double> xs(n), bs(n);
     for (int k = 0; k < n; ++k) { xs[k] = x[S.order[k]]; bs[k] = b[S.order[k]]; }
+    if (kind == 3) {
+        // the cluster streaming smoother's algorithm on its packed blocks (C = 4 CTAs), with the WEAKEST visibility the
+        // kernel guarantees: the product pass of wavefront g sees global x only through wavefront g-3; entries at
+        // distance 1 and 2 come from the exchange buffers of the producing CTA
+        const int Cc = 4;
+        ClusterStreamLayout SL;
+        build_stream_cluster(*A, S, Cc, SL);
+        const int total = W * nsweeps;
+        std::vector<double> vis(xs);                                   // global x as visible to the product pass
+        std::vector<std::vector<std::pair<int, double>>> pending((size_t)total);
+        std::vector<std::vector<std::vector<double>>> exb((size_t)total);   // [step][cta][local index]
+        for (int g = 0; g < total; ++g) {
+            if (g >= 3) for (auto &pr : pending[g - 3]) vis[pr.first] = pr.second;
+            const int w = g % W;
+            exb[g].assign(Cc, {});
+            for (int c = Cc - 1; c >= 0; --c) {
+                std::vector<unsigned char> blk(SL.data.data() + (size_t)SL.blk_ptr[(size_t)w * Cc + c] * 16,
+                                               SL.data.data() + (size_t)SL.blk_ptr[(size_t)w * Cc + c + 1] * 16);
+                const int *hd = reinterpret_cast<const int *>(blk.data());
+                exb[g][c].assign(hd[0], 0.0);
+                for (int li = hd[0] - 1; li >= 0; --li) {
+                    unsigned char *rec = blk.data() + hd[4 + li];
+                    const int *rh = reinterpret_cast<const int *>(rec);
+                    double *val = reinterpret_cast<double *>(rec + 32);
+                    const int *col = reinterpret_cast<const int *>(val + rh[2]);
+                    if (rh[0] != hd[1] + c + li * Cc) { fprintf(stderr, "cluster stream: row dealing broken\n"); abort(); }
+                    for (int p = 0; p < rh[2]; ++p) if (col[p] >= 0) val[p] = val[p] * vis[col[p]];
+                    double t = bs[rh[0]];
+                    for (int p = 0; p < rh[1]; ++p) t -= val[p];
+                    const unsigned char *lt = reinterpret_cast<const unsigned char *>(col + rh[2]);
+                    for (int i = 0; i < rh[3]; ++i) {
+                        StreamLateC e;
+                        memcpy(&e, lt + (size_t)i * 24, 24);
+                        const int d = (e.src & 1) + 1, ii = e.src >> 1;
+                        const double xv = g - d >= 0 ? exb[g - d][ii % Cc][ii / Cc] : vis[e.col];
+                        val[e.pos] = e.val * xv;
+                    }
+                    for (int p = rh[1]; p < rh[2]; ++p) t -= val[p];
+                    const double d = reinterpret_cast<double *>(rec)[2];
+                    double xn = xs[rh[0]];
+                    if (fabs(d) > 1e-20) xn = t / d;
+                    xs[rh[0]] = xn;
+                    exb[g][c][li] = xn;
+                    pending[g].emplace_back(rh[0], xn);
+                }
+            }
+            if (g >= 3) exb[g - 3].clear();
+        }
+        for (int k = 0; k < n; ++k) x[S.order[k]] = xs[k];
+        return;
+    }
     if (kind == 2) {
         // the streaming smoother's algorithm on its packed blocks (kernels.cuh, gs_stream_cta_kernel), in the least
         // favourable legal interleaving: the pre-barrier half of wavefront g+1 runs entirely BEFORE the post-barrier

@@ -168,11 +168,11 @@ struct Level {
     double *x = nullptr, *b = nullptr, *wp = nullptr;
     bool smoothed = false, ordered = false;
     int W = 0, wf_count[2] = {0, 0}, pass_items[2] = {0, 0}, pass_rows[2] = {0, 0}, max_width = 0;
-    int *d_item_wf = nullptr, *d_wf_item_ptr = nullptr;
+    int *d_item_wf = nullptr, *d_wf_item_ptr = nullptr, *d_wf_row_ptr = nullptr;
     unsigned *d_cnt = nullptr;
     int cnt_cap = 0;
     bool pattern_symmetric = true;
-    int strategy = 0;                  // 0 = parallel passes, 1 = ordered across the grid, 2 = ordered inside one CTA, 3 = one cluster, 4 = streaming CTA
+    int strategy = 0;                  // 0 = parallel passes, 1 = ordered across the grid, 2 = ordered inside one CTA, 3 = one cluster, 4 = streaming CTA, 5 = streaming cluster
     double prof_ms[4] = {0, 0, 0, 0};  // AMGB200_PROFILE: GS, residual, restrict, prolong of the last solve
     bool x_in_smem = false;            // strategy 2 only: x fits in the CTA's shared memory
     int cta_G = 1, cta_D = 1;          // strategy 2: D groups of G warps (pipeline depth D)
@@ -180,6 +180,7 @@ struct Level {
     unsigned char *d_stream = nullptr; // strategy 4 (streaming single CTA): per-wavefront blocks (analysis.h, StreamLayout)
     int *d_blk_ptr = nullptr;
     int stream_G = 1, stream_S = 1, stream_ring = 0;   // consumer warps per group, row slots per warp
+    int xc_F = 1, xc_S = 1, xc_P = 32, xc_ring = 0, xc_cap = 0;   // strategy 5 (streaming cluster): folding warps per group, row slots, ring bytes, exchange-buffer doubles
     int dsmem_sh = 0;                  // strategy 3: x distributed over the cluster's shared memory, 2^sh rows per CTA (0 = x in global memory)
     bool natural = false;              // natural-order Gauss-Seidel (cf_order = 0 or no cfmark): forward sweeps use this level's
     Level *bk = nullptr;               // schedule, backward sweeps (post-smoothing) the schedule/layout/vectors of *bk
@@ -284,6 +285,43 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
                 first += cnt;
             }
         }
+        return;
+    }
+    if (lv.strategy == 5) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(gs_stream_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            CUDA_CHECK(cudaFuncSetAttribute(gs_stream_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+            attr_set = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(XC_CTAS);
+        cfg.blockDim = dim3(32 * XC_WARPS);
+        cfg.dynamicSmemBytes = 256 + (size_t)3 * lv.xc_cap * 8 + (size_t)lv.xc_ring + 128;
+        cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = XC_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, gs_stream_cluster_kernel, (const unsigned char *)lv.d_stream, (const int *)lv.d_blk_ptr, (const int *)lv.d_wf_row_ptr,
+                                      (const double *)lv.b, lv.x, lv.W, nsweeps, lv.xc_F, lv.xc_S, lv.xc_P, lv.xc_ring, lv.xc_cap, lv.A.v.recip, h->d_dbg));
+        ++g_launches;
+#ifdef AMGB200_TIMELINE
+        if (h->d_dbg) {
+            long long hd[32];
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            CUDA_CHECK(cudaMemcpy(hd, h->d_dbg, sizeof(hd), cudaMemcpyDeviceToHost));
+            const char *nm[11] = {"wait block", "wait GV(g-3)", "products", "group barrier", "prefix fold", "wait WF(g-1)", "late patch", "suffix fold", "quotient", "loop top", "push x"};
+            const int iters = (lv.W * nsweeps + 1) / 2;
+            for (int g2 = 0; g2 < 2; ++g2) {
+                printf("   cluster stream timeline CTA 0 group %d folder (cycles per wavefront, %d wavefronts, F=%d S=%d):", g2, iters, lv.xc_F, lv.xc_S);
+                long long tot = 0;
+                for (int i = 0; i < 11; ++i) { printf("  %s %lld", nm[i], hd[g2 * 16 + i] / iters); tot += hd[g2 * 16 + i]; }
+                printf("  | total %lld\n", tot / iters);
+            }
+        }
+#endif
         return;
     }
     if (lv.strategy == 4) {
@@ -868,7 +906,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     int max_items = 1;
     // wavefront tables and launch strategy of one level's smoother (used for the level itself and, in natural
     // order, for its backward twin)
-    auto setup_smoother = [&](Level &lv, const DevLayout &lay, const Schedule &S) {
+    auto setup_smoother = [&](Level &lv, const DevLayout &lay, const Schedule &S, const amgb200_mat &Amat) {
     lv.W = S.wf_count[0] + S.wf_count[1];
     lv.wf_count[0] = S.wf_count[0]; lv.wf_count[1] = S.wf_count[1];
     lv.pass_rows[0] = S.pass_rows[0]; lv.pass_rows[1] = S.pass_rows[1];
@@ -946,6 +984,34 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             }
         }
     }
+    // streaming cluster smoother: the other ordered levels (any layout; the packer works from the host matrix)
+    if (lv.ordered && h->exact && lv.strategy != 4 && lv.W >= 4 && !getenv("AMGB200_GS_STRATEGY") && !(getenv("AMGB200_NO_XC") && atoi(getenv("AMGB200_NO_XC")))) {
+        ClusterStreamLayout SL;
+        const double tl = now_s();
+        build_stream_cluster(Amat, S, XC_CTAS, SL);
+        t_layout += now_s() - tl;
+        const int cap = (SL.max_width + 1) & ~1;        // every CTA holds the whole wavefront (x3)
+        const long long avail = (long long)h->max_dyn_smem - 256 - 3LL * cap * 8 - 128;
+        if ((long long)SL.max_block * 2 <= avail) {
+            lv.strategy = 5;
+            lv.xc_cap = cap;
+            lv.xc_ring = (int)(std::min<long long>(avail, std::max<long long>(8LL * SL.max_block, 65536)) & ~15LL);
+            const double mean_local = (double)S.n / lv.W / XC_CTAS;
+            lv.xc_S = 1;
+            while (lv.xc_S < 32 && lv.xc_S < SL.max_local) lv.xc_S *= 2;
+            lv.xc_F = std::max(1, std::min(XC_G, (int)((1.5 * mean_local + 31) / 32)));
+            lv.xc_P = (double)Amat.num_nnzs / std::max(1, Amat.num_rows) <= 96.0 ? 8 : 32;      // lanes per row in the product pass
+            if (getenv("AMGB200_XC_P")) lv.xc_P = atoi(getenv("AMGB200_XC_P")) >= 32 ? 32 : 8;
+            if (getenv("AMGB200_XC_F")) lv.xc_F = std::max(1, std::min(XC_G, atoi(getenv("AMGB200_XC_F"))));
+            if (getenv("AMGB200_XC_S")) { int v = std::max(1, std::min(32, atoi(getenv("AMGB200_XC_S")))); lv.xc_S = 1; while (lv.xc_S < v) lv.xc_S *= 2; }
+            if (lv.d_stream) { dev_free(lv.d_stream); dev_free(lv.d_blk_ptr); }
+            lv.d_stream = dev_upload(SL.data);
+            lv.d_blk_ptr = dev_upload(SL.blk_ptr);
+            lv.d_wf_row_ptr = dev_upload(S.wf_row_ptr);
+            if (h->opt.verbose >= 2) printf("      streaming cluster smoother: %d CTAs, %d folding warps/group x %d row slots, ring %d B, block mean %lld B max %d B, rows per CTA per wavefront <= %d, stream %.1f MB\n",
+                                            XC_CTAS, lv.xc_F, lv.xc_S, lv.xc_ring, SL.mean_block, SL.max_block, SL.max_local, SL.data.size() / 1e6);
+        }
+    }
     };
 
     for (int l = 0; l < nl; ++l) {
@@ -979,7 +1045,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         CUDA_CHECK(cudaMemset(lv.b, 0, (size_t)lv.n * sizeof(double)));
         lv.pattern_symmetric = S.pattern_symmetric;
         if (lv.smoothed) {
-            setup_smoother(lv, lay, S);
+            setup_smoother(lv, lay, S, c.A);
             if (natural[l]) {
                 // backward sweeps: own schedule, layout and vectors; d_fb maps its numbering into this level's
                 lv.natural = true;
@@ -995,7 +1061,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                 max_items = std::max(max_items, lb.nitems());
                 bk->x = dev_alloc<double>(lv.n);
                 bk->b = dev_alloc<double>(lv.n + 2);
-                setup_smoother(*bk, lb, B);
+                setup_smoother(*bk, lb, B, c.A);
                 std::vector<int> fb((size_t)lv.n);
                 for (int k = 0; k < lv.n; ++k) fb[k] = S.pos[B.order[k]];
                 lv.d_fb = dev_upload(fb);
@@ -1040,11 +1106,11 @@ void amgb200_free(amgb200_hier *h) {
     for (Level &lv : h->L) {
         lv.A.release(); lv.Asp.release(); lv.P.release(); lv.R.release();
         dev_free(lv.d_order); dev_free(lv.x); dev_free(lv.b); dev_free(lv.wp);
-        dev_free(lv.d_item_wf); dev_free(lv.d_wf_item_ptr); dev_free(lv.d_cnt); dev_free(lv.d_fb); dev_free(lv.d_stream); dev_free(lv.d_blk_ptr);
+        dev_free(lv.d_item_wf); dev_free(lv.d_wf_item_ptr); dev_free(lv.d_cnt); dev_free(lv.d_fb); dev_free(lv.d_stream); dev_free(lv.d_blk_ptr); dev_free(lv.d_wf_row_ptr);
         if (lv.bk) {
             lv.bk->A.release();
             dev_free(lv.bk->x); dev_free(lv.bk->b);
-            dev_free(lv.bk->d_item_wf); dev_free(lv.bk->d_wf_item_ptr); dev_free(lv.bk->d_cnt); dev_free(lv.bk->d_stream); dev_free(lv.bk->d_blk_ptr);
+            dev_free(lv.bk->d_item_wf); dev_free(lv.bk->d_wf_item_ptr); dev_free(lv.bk->d_cnt); dev_free(lv.bk->d_stream); dev_free(lv.bk->d_blk_ptr); dev_free(lv.bk->d_wf_row_ptr);
             delete lv.bk;
         }
     }
@@ -1113,7 +1179,7 @@ const char *amgb200_level_kernel(const amgb200_hier *h, int level) {
     check_level(h, level);
     const Level &lv = h->L[level];
     if (!lv.smoothed) return "none";
-    static const char *names[5] = {"gs_pass_kernel", "gs_ordered_grid_kernel", "gs_ordered_cta_kernel", "gs_ordered_cluster_kernel", "gs_stream_cta_kernel"};
+    static const char *names[6] = {"gs_pass_kernel", "gs_ordered_grid_kernel", "gs_ordered_cta_kernel", "gs_ordered_cluster_kernel", "gs_stream_cta_kernel", "gs_stream_cluster_kernel"};
     return names[lv.strategy];
 }
 

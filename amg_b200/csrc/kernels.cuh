@@ -1045,16 +1045,284 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
     for (int i = threadIdx.x; i < n; i += blockDim.x) xg[i] = x[i];
 }
 
+// ------------------------------------------------------------------------------------------
+// Streaming ordered sweeps on a 16-CTA cluster (levels too wide / too large for one SM).
+//
+// Same division of labour as gs_stream_cta_kernel -- loader warp with a bulk-async ring, product lanes, folding warps with
+// row slots, two alternating groups -- in every CTA of the cluster; row i of a wavefront belongs to CTA i % 16.  What
+// crosses SMs never goes through a release fence on the dependency path:
+//   * a finished x_k is PUSHED into the exchange buffers of all 16 CTAs with st.async (8 bytes, completion counted on the
+//     receiving CTA's mbarrier WF[g%3] by complete_tx): data and notification travel together.  Every CTA therefore holds
+//     the x of the last three wavefronts in its own shared memory, and entries at wavefront distance 1 or 2 ("late",
+//     flagged by the host) are ordinary local shared-memory reads after the wait;
+//   * x in GLOBAL memory only serves entries at distance >= 3: a PUBLISHER warp per CTA copies its share of each complete
+//     wavefront from the exchange buffer to global memory, fences at GPU scope (the ~1 us that used to sit between two
+//     wavefronts) and arrives on GV[g%4] of every CTA; the product pass of wavefront g waits for GV(g-3), long complete.
+// Dynamic shared memory: [full[4] empty[4] | WF[3] | GV[4] | ring offsets | zeros : 256 B][3 x xb_cap doubles][ring]
+// ------------------------------------------------------------------------------------------
+constexpr int CLUSTER_CTAS = 16;
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+constexpr int XC_CTAS = CLUSTER_CTAS;
+constexpr int XC_G = 4;                        // product warps per group
+constexpr int XC_WARPS = 2 * XC_G + 2;         // + loader + publisher
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(unsigned raddr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// 8 bytes into another CTA's shared memory; the receiving CTA's mbarrier counts them (complete_tx) when they have landed
+__device__ __forceinline__ void st_async_f64(unsigned raddr, double v, unsigned rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr), "l"(__double_as_longlong(v)), "r"(rbar) : "memory");
+}
+// x of one late entry: from the exchange buffer of the wavefront that produced it (distance d = 1 or 2 before wavefront g),
+// or -- for the first wavefronts of a launch, whose predecessors belong to the previous launch -- from global memory
+__device__ __forceinline__ double xc_late_x(int g, int src, int col, unsigned xb_a, int xb_cap, const double *x) {
+    const int d = (src & 1) + 1;
+    double v;
+    if (g - d < 0) asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(x + col) : "memory");
+    else v = lds_f64(xb_a + 8u * ((unsigned)((g - d) % 3) * (unsigned)xb_cap + ((unsigned)src >> 1)));
+    return v;
+}
+
+__global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
+    const unsigned char *__restrict__ stream, const int *__restrict__ blk_ptr, const int *__restrict__ wf_row_ptr,
+    const double *__restrict__ b, double *x, int W, int nsweeps, int F, int S, int P, int ring_bytes, int xb_cap, int recip, long long *dbg) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);      // full[0..4) empty[4..8) WF[8..11) GV[11..15)
+    volatile int *stage_off = reinterpret_cast<volatile int *>(smem_raw + 160);
+    const unsigned zeros_a = smem_u32(smem_raw + 192);
+    double *xb = reinterpret_cast<double *>(smem_raw + 256);
+    const unsigned xb_a = smem_u32(xb);
+    unsigned char *ring = smem_raw + 256 + (size_t)3 * xb_cap * 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int totalw = W * nsweeps;
+    const int C = XC_CTAS, G = XC_G;
+    const unsigned cta = cluster_ctarank();
+#ifdef AMGB200_TIMELINE
+    long long tl[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tl_prev = clock64();
+#define XC_MARK(i) { const long long c_ = clock64(); tl[i] += c_ - tl_prev; tl_prev = c_; }
+#else
+#define XC_MARK(i)
+#endif
+    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + 4), wf0 = smem_u32(bars + 8), gv0 = smem_u32(bars + 11);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 4; ++s) { mbar_init(full0 + 8u * s, 1); mbar_init(empty0 + 8u * s, 1); mbar_init(gv0 + 8u * s, C); }
+        for (int s = 0; s < 3; ++s) mbar_init(wf0 + 8u * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 8) reinterpret_cast<double *>(smem_raw + 192)[threadIdx.x] = 0.0;
+    __syncthreads();
+    cluster_arrive(); cluster_wait();            // every CTA's barriers exist before anybody signals them remotely
+    if (warp < 2 * G) {
+        const int grp = warp / G, r = warp - grp * G;
+        const int f = (r - grp + G) % G;         // folding warps of a group: f < F (the two groups' folders on different sub-partitions)
+        const bool folder = f < F;
+        const int sub = 32 / S, slot = lane / sub;
+        const int lis = lane - slot * sub;       // lane in slot
+        const int FS = F * S;
+        const int RP = 32 / P, lr = lane % P, unit = r * RP + lane / P;      // product pass: P lanes per row, G*RP rows in flight per CTA
+        for (int g = grp; g < totalw; g += 2) {
+            const int s = g & 3;
+            XC_MARK(9)
+            mbar_wait(full0 + 8u * s, (g >> 2) & 1);
+            XC_MARK(0)
+            unsigned char *blk = ring + stage_off[s];
+            const int4 hd = *reinterpret_cast<const int4 *>(blk);                   // rows of this CTA, first row of the wavefront, its width, block bytes
+            const int *rec_off = reinterpret_cast<const int *>(blk + 16);
+            // this CTA expects the whole wavefront g (width x 8 bytes) in its exchange buffer g % 3: one arrival per phase
+            if (f == 0 && lane == 0) mbar_arrive_expect_tx(wf0 + 8u * (unsigned)(g % 3), (unsigned)hd.z * 8u);
+            // right-hand side of my first-round row: requested now, used after the product pass
+            double b0 = 0.0;
+            if (folder && slot * F + f < hd.x) b0 = __ldg(b + hd.y + (int)cta + (slot * F + f) * C);
+            if (g >= 3) mbar_wait_cluster(gv0 + 8u * ((g - 3) & 3), ((g - 3) >> 2) & 1);      // global x visible through wavefront g-3
+            XC_MARK(1)
+            // ---- before the wavefront barrier: products of every entry (late ones are redone below).  P lanes per row, all
+            // row groups of the warp walk in lockstep (a diverged warp would serialise the L2 round trips of its row groups)
+            for (int rbase = 0; rbase < hd.x; rbase += G * RP) {
+                const int ri = rbase + unit;
+                unsigned val_a = 0, col_a = 0;
+                int len_pad = 0;
+                if (ri < hd.x) {
+                    unsigned char *rec = blk + rec_off[ri];
+                    len_pad = reinterpret_cast<const int *>(rec)[2];
+                    val_a = smem_u32(rec + 32); col_a = val_a + 8u * (unsigned)len_pad;
+                }
+                const int maxlen = __reduce_max_sync(FULL, len_pad);
+                for (int p0 = 0; p0 < maxlen; p0 += 8 * P) {
+                    int j[8];
+                    double v[8], xv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const int p = p0 + u * P + lr; j[u] = -1; if (p < len_pad) j[u] = lds_s32(col_a + 4u * (unsigned)p); }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int p = p0 + u * P + lr;
+                        v[u] = 0.0; xv[u] = 0.0;
+                        if (j[u] >= 0) {
+                            v[u] = lds_f64(val_a + 8u * (unsigned)p);
+                            asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(xv[u]) : "l"(x + j[u]) : "memory");
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const int p = p0 + u * P + lr; if (j[u] >= 0) sts_f64(val_a + 8u * (unsigned)p, __dmul_rn(v[u], xv[u])); }
+                }
+            }
+            XC_MARK(2)
+            asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");      // all products of my CTA's rows are in place
+            XC_MARK(3)
+            if (folder) {
+                // ... and the prefix chains; the state of the first round stays in registers (c_*)
+                bool c_mine = false;
+                unsigned c_suf = 0, c_late = 0, c_val = 0;
+                int c_cnt = 0, c_maxc = 0, c_row = 0, c_nlate = 0, c_li = 0;
+                double c_t = 0.0, c_d = 0.0;
+                for (int base = 0; base < hd.x; base += FS) {
+                    const int ri = base + slot * F + f;
+                    const bool mine = ri < hd.x;
+                    unsigned char *rec = blk + (mine ? rec_off[ri] : rec_off[0]);
+                    const int4 rh = *reinterpret_cast<const int4 *>(rec);               // row, prefix_pad, len_pad, nlate
+                    const int cnt = mine ? rh.y : 0;
+                    const int maxc = __reduce_max_sync(FULL, cnt);
+                    const double t0 = base == 0 ? b0 : (mine ? __ldg(b + rh.x) : 0.0);
+                    const double t = chain_fold_slots(t0, smem_u32(rec + 32), cnt, maxc, zeros_a);
+                    if (base == 0) {
+                        c_mine = mine; c_row = rh.x; c_t = t; c_d = reinterpret_cast<const double *>(rec)[2]; c_li = ri;
+                        c_val = smem_u32(rec + 32);
+                        c_suf = c_val + 8u * (unsigned)rh.y;
+                        c_cnt = mine ? rh.z - rh.y : 0;
+                        c_maxc = __reduce_max_sync(FULL, c_cnt);
+                        c_nlate = mine ? rh.w : 0;
+                        c_late = c_val + 12u * (unsigned)rh.z;
+                    } else if (mine && lis == 0) reinterpret_cast<double *>(rec)[3] = t;
+                }
+                __syncwarp();
+                XC_MARK(4)
+                if (g > 1) mbar_wait_cluster(wf0 + 8u * ((g - 2) % 3), ((g - 2) / 3) & 1);
+                if (g > 0) mbar_wait_cluster(wf0 + 8u * ((g - 1) % 3), ((g - 1) / 3) & 1);
+                XC_MARK(5)
+                // ---- after the barrier: late products (x from the exchange buffers), suffix chains, x_k pushed to every CTA
+                const unsigned xb_g = xb_a + 8u * (unsigned)(g % 3) * (unsigned)xb_cap, wf_g = wf0 + 8u * (unsigned)(g % 3);
+                for (int base = 0; base < hd.x; base += FS) {
+                    bool mine; unsigned val_a, suf_a, late_a; int cnt, maxc, row, nlate, li; double t, dg;
+                    if (base == 0) { mine = c_mine; val_a = c_val; suf_a = c_suf; late_a = c_late; cnt = c_cnt; maxc = c_maxc; row = c_row; nlate = c_nlate; li = c_li; t = c_t; dg = c_d; }
+                    else {
+                        li = base + slot * F + f;
+                        mine = li < hd.x;
+                        unsigned char *rec = blk + (mine ? rec_off[li] : rec_off[0]);
+                        const int4 rh = *reinterpret_cast<const int4 *>(rec);
+                        val_a = smem_u32(rec + 32); suf_a = val_a + 8u * (unsigned)rh.y; late_a = val_a + 12u * (unsigned)rh.z;
+                        cnt = mine ? rh.z - rh.y : 0; maxc = __reduce_max_sync(FULL, cnt); row = rh.x; nlate = mine ? rh.w : 0;
+                        const double2 dt = *reinterpret_cast<const double2 *>(rec + 16);
+                        dg = dt.x; t = dt.y;
+                    }
+                    for (int i0 = lis; i0 < nlate; i0 += 4 * sub) {                  // four late entries per lane at a time
+                        double lv[4], xv[4];
+                        int lp[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u * sub;
+                            lp[u] = -1;
+                            if (i < nlate) {
+                                const unsigned a = late_a + 24u * (unsigned)i;
+                                lv[u] = lds_f64(a); lp[u] = lds_s32(a + 8u);
+                                xv[u] = xc_late_x(g, lds_s32(a + 16u), lds_s32(a + 12u), xb_a, xb_cap, x);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) if (lp[u] >= 0) sts_f64(val_a + 8u * (unsigned)lp[u], __dmul_rn(lv[u], xv[u]));
+                    }
+                    __syncwarp();
+                    XC_MARK(6)
+                    t = chain_fold_slots(t, suf_a, cnt, maxc, zeros_a);
+#ifdef AMGB200_TIMELINE
+                    if (t == 1.2345e300) tl[11] = 1;
+                    XC_MARK(7)
+#endif
+                    double xn = 0.0;
+                    if (mine && lis == 0) {
+                        if (fabs(dg) > GS_TINY) xn = gs_quotient(t, dg, recip);
+                        else asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(xn) : "l"(x + row) : "memory");     // row without a diagonal: x_k unchanged (never speculated)
+                    }
+                    xn = __shfl_sync(FULL, xn, slot * sub);
+                    XC_MARK(8)
+                    // the sub lanes of the slot share the 16 destinations
+                    if (mine) {
+                        const unsigned idx = (unsigned)(li * C) + cta;               // index of the row within its wavefront
+                        for (int c2 = lis; c2 < C; c2 += sub) st_async_f64(mapa_u32(xb_g + 8u * idx, (unsigned)c2), xn, mapa_u32(wf_g, (unsigned)c2));
+                    }
+                }
+                XC_MARK(10)
+            }
+            // every warp's generic writes to the block precede its reuse by the async proxy: fence, group barrier, release
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");
+            if (f == 0 && lane == 0) mbar_arrive(empty0 + 8u * s);
+        }
+#ifdef AMGB200_TIMELINE
+        if (dbg && lane == 0 && f == 0 && cta == 0) for (int i = 0; i < 12; ++i) dbg[grp * 16 + i] = tl[i];
+#endif
+    } else if (warp == 2 * G) {
+        if (lane == 0) {
+            // ---- loader (see gs_stream_cta_kernel); block of (wavefront wl, this CTA)
+            int head = 0, tail = 0, inflight = 0, g_old = 0, wl = 0;
+            for (int g = 0; g < totalw; ++g) {
+                const int s = g & 3;
+                const int o0 = blk_ptr[wl * C + (int)cta], o1 = blk_ptr[wl * C + (int)cta + 1];
+                const int need = (o1 - o0) * 16;
+                for (;;) {
+                    if (inflight == 0) { head = tail = 0; break; }
+                    if (inflight < 4) {
+                        if (head >= tail) {
+                            if (head + need <= ring_bytes) break;
+                            if (need < tail) { head = 0; break; }
+                        } else if (head + need < tail) break;
+                    }
+                    mbar_wait_sleep(empty0 + 8u * (g_old & 3), (g_old >> 2) & 1);
+                    ++g_old; --inflight;
+                    tail = inflight ? stage_off[g_old & 3] : head;
+                }
+                stage_off[s] = head;
+                mbar_arrive_expect_tx(full0 + 8u * s, (unsigned)need);
+                bulk_g2s(smem_u32(ring + head), stream + (size_t)o0 * 16, (unsigned)need, full0 + 8u * s);
+                head += need; ++inflight;
+                if (++wl == W) wl = 0;
+            }
+        }
+    } else {
+        // ---- publisher: my share of each complete wavefront, exchange buffer -> global x, GPU-scope fence, GV(g) on every CTA
+        int wl = 0;
+        for (int g = 0; g < totalw; ++g) {
+            const int start = wf_row_ptr[wl], width = wf_row_ptr[wl + 1] - start;
+            mbar_wait_cluster(wf0 + 8u * (unsigned)(g % 3), (g / 3) & 1);
+            const double *xb_g = xb + (size_t)(g % 3) * xb_cap;
+            for (int i = (int)cta + C * lane; i < width; i += C * 32) x[start + i] = xb_g[i];
+            __threadfence();
+            __syncwarp();
+            if (lane < C) mbar_arrive_remote(mapa_u32(gv0 + 8u * (unsigned)(g & 3), (unsigned)lane));
+            if (++wl == W) wl = 0;
+        }
+    }
+    __syncwarp();
+    cluster_arrive(); cluster_wait();            // nobody leaves while its exchange buffers / barriers may still be addressed remotely
+}
+
 // Ordered sweeps inside ONE thread-block cluster (16 CTAs = 16 SMs on one die): the wavefronts of the
 // level are walked in order, the items of a wavefront are spread over all warps of the cluster, and
 // consecutive wavefronts are separated by the hardware cluster barrier (barrier.cluster, ~0.2 us)
 // instead of a round trip through L2 atomics (~2-5 us for a grid-wide counter).  The barrier is split:
 // after its last store a warp *arrives*, then prefetches the matrix entries of its next item, then
 // *waits*.  x lives in global memory and is read at L2 (ld.cg) after the acquire.
-constexpr int CLUSTER_CTAS = 16;
-__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 constexpr int CLUSTER_WARPS_SELL = 8, CLUSTER_WARPS_CSR = 16;
 template <int KIND, bool EXACT>

@@ -51,7 +51,7 @@ def test_wavefront_schedule_properties(case):
 
 
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("kind", [0, 1, 2])      # SELL-32 | CSR | packed per-wavefront blocks of the streaming smoother (two-phase rows)
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])   # SELL-32 | CSR | packed per-wavefront blocks of the streaming smoother (two-phase rows) | per-(wavefront, CTA) blocks of the cluster streaming smoother
 def test_wavefront_execution_is_bit_identical_to_sequential_sweep(case, kind, oracle):
     hier = HostHierarchy(generate(*case), tol=1e-8)
     for l in range(hier.num_levels - 1):
@@ -84,7 +84,7 @@ def test_nonsymmetric_pattern_keeps_read_old_value_order(oracle):
     assert cnt[2] == 0                                         # pattern reported as non-symmetric
     x0 = np.array([1.0, 2.0, 3.0, 4.0]); b = np.array([1.0, 1.0, 1.0, 1.0])
     want = oracle.gs_cf(mat, mark, x0, b, 3, 1)
-    for kind in (0, 1, 2):
+    for kind in (0, 1, 2, 3):
         x = x0.copy()
         L.amgb200_debug_gs_walk(C.byref(mat), capi.iptr(mark), kind, 3, capi.dptr(x), capi.dptr(b))
         assert x.tobytes() == want.tobytes()
