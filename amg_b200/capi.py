@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(ROOT, "amg_b200", "libamgb200.so")
+LIB_PATH = os.environ.get("AMGB200_LIB") or os.path.join(ROOT, "amg_b200", "libamgb200.so")   # AMGB200_LIB: developer builds (e.g. -DAMGB200_TIMELINE)
 
 c_int_p = C.POINTER(C.c_int)
 c_double_p = C.POINTER(C.c_double)

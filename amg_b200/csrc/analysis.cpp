@@ -242,7 +242,7 @@ void build_stream(const DevLayout &L, StreamLayout &S) {
     }
 }
 
-void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, ClusterStreamLayout &SL) {
+void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, ClusterStreamLayout &SL, long long smem_budget) {
     const int n = S.n, W = S.wf_count[0] + S.wf_count[1];
     const std::vector<int> &wrp = S.wf_row_ptr;
     auto r8 = [](int v) { return (v + 7) & ~7; };
@@ -279,8 +279,12 @@ void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, Cluste
             SL.max_width = std::max(SL.max_width, width);
         }
     }
-    SL.data.resize((size_t)SL.blk_ptr[(size_t)W * C] * 16);
     SL.mean_block = W ? (long long)SL.blk_ptr[(size_t)W * C] * 16 / ((long long)W * C) : 0;
+    // sizes are known: give up before the (expensive) fill when two of the largest blocks plus the three exchange
+    // buffers cannot fit in one CTA's shared memory
+    SL.filled = !(smem_budget >= 0 && 2LL * SL.max_block > smem_budget - 24LL * ((SL.max_width + 1) & ~1));
+    if (!SL.filled) return;
+    SL.data.resize((size_t)SL.blk_ptr[(size_t)W * C] * 16);
 #pragma omp parallel for schedule(dynamic, 8)
     for (int w = 0; w < W; ++w) {
         const int width = wrp[w + 1] - wrp[w];

@@ -102,8 +102,10 @@ struct ClusterStreamLayout {
     long long mean_block = 0;
     int max_local = 0;             // largest number of rows one CTA gets from one wavefront
     int max_width = 0;             // widest wavefront (rows)
+    bool filled = false;           // false: the sizing pass showed the blocks cannot fit (data left empty)
 };
-void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, ClusterStreamLayout &SL);
+// smem_budget >= 0: shared memory available for 3 exchange buffers + a ring of two blocks; the fill is skipped when it cannot fit
+void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, ClusterStreamLayout &SL, long long smem_budget = -1);
 
 // mark == nullptr: single pass over all rows in natural order (no C/F ordering).
 void build_schedule(const amgb200_mat &A, const int *mark, Schedule &S);

@@ -988,11 +988,11 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     if (lv.ordered && h->exact && lv.strategy != 4 && lv.W >= 4 && !getenv("AMGB200_GS_STRATEGY") && !(getenv("AMGB200_NO_XC") && atoi(getenv("AMGB200_NO_XC")))) {
         ClusterStreamLayout SL;
         const double tl = now_s();
-        build_stream_cluster(Amat, S, XC_CTAS, SL);
+        build_stream_cluster(Amat, S, XC_CTAS, SL, (long long)h->max_dyn_smem - 256 - 128);
         t_layout += now_s() - tl;
         const int cap = (SL.max_width + 1) & ~1;        // every CTA holds the whole wavefront (x3)
         const long long avail = (long long)h->max_dyn_smem - 256 - 3LL * cap * 8 - 128;
-        if ((long long)SL.max_block * 2 <= avail) {
+        if (SL.filled && (long long)SL.max_block * 2 <= avail) {
             lv.strategy = 5;
             lv.xc_cap = cap;
             lv.xc_ring = (int)(std::min<long long>(avail, std::max<long long>(8LL * SL.max_block, 65536)) & ~15LL);

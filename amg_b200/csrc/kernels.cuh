@@ -900,7 +900,11 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
             const int *rec_off = reinterpret_cast<const int *>(blk + 16);
             const double *bseg = reinterpret_cast<const double *>(blk + hd.w);
             // ---- before the barrier: products of every entry (late ones are redone below) ...
+#if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 13
+            for (int ri = r; ri < 0; ri += G) {
+#else
             for (int ri = r; ri < hd.x; ri += G) {                                   // all 32 lanes on one row at a time
+#endif
                 unsigned char *rec = blk + rec_off[ri];
                 const int len_pad = reinterpret_cast<const int *>(rec)[2];
                 // explicit shared-space accesses in program order (volatile asm): 8 column loads, then the 16 value /
@@ -938,16 +942,28 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
                     const bool mine = ri < hd.x;
                     unsigned char *rec = blk + (mine ? rec_off[ri] : rec_off[0]);
                     const int4 rh = *reinterpret_cast<const int4 *>(rec);               // row, prefix_pad, len_pad, nlate
+#if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 14
+                    const int cnt = 0;
+#else
                     const int cnt = mine ? rh.y : 0;
+#endif
                     const int maxc = __reduce_max_sync(FULL, cnt);
                     const double t = chain_fold_slots(mine ? bseg[rh.x - hd.y] : 0.0, smem_u32(rec + 32), cnt, maxc, zeros_a);
                     if (base == 0) {
                         c_mine = mine; c_row = rh.x; c_t = t; c_d = reinterpret_cast<const double *>(rec)[2];
                         c_val = smem_u32(rec + 32);
                         c_suf = c_val + 8u * (unsigned)rh.y;
+#if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 15
+                        c_cnt = 0;
+#else
                         c_cnt = mine ? rh.z - rh.y : 0;
+#endif
                         c_maxc = __reduce_max_sync(FULL, c_cnt);
+#if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 12
+                        c_nlate = 0;
+#else
                         c_nlate = mine ? rh.w : 0;
+#endif
                         c_late = c_val + 12u * (unsigned)rh.z;
                         if (lis < c_nlate) c_e = *reinterpret_cast<const StreamLateDev *>(rec + 32 + 12 * rh.z + 16 * lis);
                     } else if (mine && leader) reinterpret_cast<double *>(rec)[3] = t;
@@ -975,7 +991,11 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
                     SL_MARK(5)
                     tl[9] += c_maxc;
 #endif
+#if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 11
+                    if (c_mine && leader && fabs(c_d) > GS_TINY) sts_f64(x_a + 8u * (unsigned)c_row, __dmul_rn(t, c_d));
+#else
                     if (c_mine && leader && fabs(c_d) > GS_TINY) sts_f64(x_a + 8u * (unsigned)c_row, gs_quotient(t, c_d, recip));
+#endif
                     SL_MARK(6)
                 }
                 for (int base = S; base < hd.x; base += S) {                             // wavefront wider than S rows: further rounds

@@ -281,20 +281,30 @@ def main():
           "spmv_gbs": dev.bytes(0, 4) / dev.time_op(0, 4, 20) / 1e6}
     l0_frac = {k.replace("_gbs", "_frac_of_hbm"): v / hbm for k, v in l0.items()}
     vcycle_bytes = dev.bytes(0, 5)
+    device_bytes = dev.device_bytes()
+    analysis_s, upload_s = dev.upload_seconds()
 
-    # ---- e2e through the reference-facing call with host buffers
+    # ---- e2e through the reference-facing call with host buffers: every call analyses and uploads the host
+    # hierarchy, solves and copies x back; one untimed warm-up call (device memory pool, pinned staging buffers --
+    # the same once-per-process costs the warm-up steps of the device-timed leg absorb), then the mean of E2E_CALLS
     os.environ["AMGB200_VERBOSE"] = "0"
-    t0 = time.perf_counter()
+    dev.close()                                            # the resident copy is not part of the e2e path
+    E2E_CALLS = 3
+    e2e_times = []
     with open(os.devnull, "w") as devnull:
         saved = os.dup(1); sys.stdout.flush(); os.dup2(devnull.fileno(), 1)
         try:
-            rtn_e2e, x_e2e = solve_dropin(hier, np.ones(n), np.ones(n))
+            for rep in range(1 + E2E_CALLS):
+                x_host, b_host = np.ones(n), np.ones(n)
+                t0 = time.perf_counter()
+                rtn_e2e, x_e2e = solve_dropin(hier, x_host, b_host)
+                if rep:
+                    e2e_times.append(1e3 * (time.perf_counter() - t0))
         finally:
             os.dup2(saved, 1); os.close(saved)
-    e2e_ms = 1e3 * (time.perf_counter() - t0)
-    h2d = dev.device_bytes() + 2 * 8 * n
+    e2e_ms = sum(e2e_times) / len(e2e_times)
+    h2d = device_bytes + 2 * 8 * n
     d2h = 8 * n + 8 * (rtn_e2e.nits + 1)
-    analysis_s, upload_s = dev.upload_seconds()
 
     # ---- CPU baseline: the reference's own CPU path on this box, one full solve
     cpu = None
@@ -316,7 +326,8 @@ def main():
             "level0": dict(l0, **l0_frac),
             "clocks": clocks,
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "analysis_ms": 1e3 * analysis_s, "analysis_plus_upload_ms": 1e3 * upload_s, "vcycles": rtn_e2e.nits},
+                    "calls": E2E_CALLS, "warmup_calls": 1, "min_ms": min(e2e_times), "max_ms": max(e2e_times),
+                    "analysis_ms": 1e3 * analysis_s, "analysis_plus_upload_ms_first_upload": 1e3 * upload_s, "vcycles": rtn_e2e.nits},
             "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "kernels": kernels[:6],
             "phase_ms_per_solve": {"gs": phase[0], "residual": phase[1], "restrict": phase[2], "prolong": phase[3],
