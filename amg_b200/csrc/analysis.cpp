@@ -118,15 +118,18 @@ void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos
             for (int w = 0; w < W; ++w) for (int k = (*breaks)[w]; k < (*breaks)[w + 1]; ++k) wf_of[k] = w;
             L.split.resize((size_t)n);
             L.late.assign(((size_t)L.nnz + 31) / 32 + 1, 0u);
+            L.late2.assign(W >= 4 ? ((size_t)L.nnz + 31) / 32 + 1 : 0, 0u);
             for (int k = 0; k < n; ++k) {              // (bit writes of neighbouring rows share words: keep this loop serial)
                 const int prev = wf_of[k] == 0 ? W - 1 : wf_of[k] - 1;
+                const int prev2 = W >= 4 ? (wf_of[k] + W - 2) % W : -1;
                 int sp = L.rptr[k + 1] - L.rptr[k];
                 for (int q = L.rptr[k]; q < L.rptr[k + 1]; ++q) {
                     const int c = L.col[q];
-                    if (c != k && c < n && wf_of[c] == prev) {
+                    if (c == k || c >= n) continue;
+                    if (wf_of[c] == prev) {
                         if (q - L.rptr[k] < sp) sp = q - L.rptr[k];
                         L.late[(size_t)q >> 5] |= 1u << (q & 31);
-                    }
+                    } else if (wf_of[c] == prev2) L.late2[(size_t)q >> 5] |= 1u << (q & 31);
                 }
                 L.split[k] = sp;
             }
@@ -183,15 +186,19 @@ void build_stream(const DevLayout &L, StreamLayout &S) {
     const std::vector<int> &wip = L.wf_item_ptr;
     auto r8 = [](int v) { return (v + 7) & ~7; };
     auto late_bit = [&](int q) { return (L.late[(size_t)q >> 5] >> (q & 31)) & 1u; };
+    const bool have2 = !L.late2.empty();
+    auto late2_bit = [&](int q) { return have2 ? (L.late2[(size_t)q >> 5] >> (q & 31)) & 1u : 0u; };
     // per-row record size
     std::vector<int> rec_bytes((size_t)L.nrows);
 #pragma omp parallel for schedule(static)
     for (int k = 0; k < L.nrows; ++k) {
         const int p0 = L.rptr[k], len = L.rptr[k + 1] - p0, sp = L.split[k];
-        int nlate = 0;
+        int nlate = 0, nlate2 = 0;
         for (int q = p0 + sp; q < p0 + len; ++q) nlate += late_bit(q);
+        for (int q = p0; q < p0 + len; ++q) nlate2 += late2_bit(q);
+        if (nlate > 0xffff || nlate2 > 0x7fff) { fprintf(stderr, "libamgb200: build_stream: late list of a row exceeds the record format\n"); abort(); }
         const int len_pad = r8(sp) + r8(len - sp);
-        rec_bytes[k] = 32 + len_pad * 12 + nlate * 16;
+        rec_bytes[k] = 32 + len_pad * 12 + (nlate + nlate2) * 16;
     }
     S.blk_ptr.assign((size_t)W + 1, 0);
     S.max_block = 0;
@@ -227,7 +234,7 @@ void build_stream(const DevLayout &L, StreamLayout &S) {
             StreamLate *lt = reinterpret_cast<StreamLate *>(col + len_pad);
             for (int i = 0; i < len_pad; ++i) { val[i] = 0.0; col[i] = -1; }
             double diag = 0.0;
-            int nlate = 0;
+            int nlate = 0, nlate2 = 0;
             for (int i = 0; i < len; ++i) {
                 const int q = p0 + i, pos = i < sp ? i : pre_pad + (i - sp);
                 const int c = L.col[q];
@@ -235,7 +242,12 @@ void build_stream(const DevLayout &L, StreamLayout &S) {
                 val[pos] = L.val[q]; col[pos] = c;
                 if (late_bit(q)) { lt[nlate].val = L.val[q]; lt[nlate].pos = pos; lt[nlate].col = c; ++nlate; }
             }
-            rh[0] = k; rh[1] = pre_pad; rh[2] = len_pad; rh[3] = nlate;
+            StreamLate *lt2 = lt + nlate;
+            for (int i = 0; i < len; ++i) {
+                const int q = p0 + i, pos = i < sp ? i : pre_pad + (i - sp);
+                if (late2_bit(q)) { lt2[nlate2].val = L.val[q]; lt2[nlate2].pos = pos; lt2[nlate2].col = L.col[q]; ++nlate2; }
+            }
+            rh[0] = k; rh[1] = pre_pad; rh[2] = len_pad; rh[3] = nlate | (nlate2 << 16);
             rd[2] = diag; rd[3] = 0.0;
             off += rec_bytes[k];
         }

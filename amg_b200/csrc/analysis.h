@@ -62,6 +62,7 @@ struct DevLayout {
     std::vector<int> split;        // CSR + wavefronts: per row, index of the first entry whose column lies in the
                                    // cyclically preceding wavefront (row length if none)
     std::vector<unsigned> late;    // CSR + wavefronts: one bit per entry, set when its column lies in that preceding wavefront
+    std::vector<unsigned> late2;   // ... when it lies in the wavefront before that one (cyclic distance 2; empty when W < 4)
     int nitems() const { return kind == KIND_SELL ? (int)slice_row.size() - 1 : nrows; }
 };
 
@@ -74,7 +75,10 @@ struct DevLayout {
 //   record : int32 row, int32 prefix_pad, int32 len_pad, int32 nlate, double diag, double scratch     (32 bytes)
 //            double val[len_pad]   prefix entries, zero padding to a multiple of 8, suffix entries, padding to 8
 //            int32  col[len_pad]   (-1 for padding and for the diagonal entry, whose value moves to `diag`)
-//            {double val; int32 pos; int32 col} late[nlate]   entries whose column lies in the preceding wavefront
+//            {double val; int32 pos; int32 col} late[n1]    entries whose column lies in the preceding wavefront
+//            {double val; int32 pos; int32 col} late2[n2]   entries whose column lies in the wavefront before that one
+//            with nlate = n1 | n2 << 16: three wavefronts are in flight in the kernel, so the product pass of wavefront
+//            g only sees x through wavefront g-3; distance-2 entries are redone after g-2, distance-1 entries after g-1
 // The storage order of a row is untouched: padding only inserts exact no-ops (+0.0 products).
 struct StreamLayout {
     RawBuf<unsigned char> data;

@@ -92,16 +92,17 @@ void amgb200_debug_gs_walk(const amgb200_mat *A, const int *mark, int kind, int 
         return;
     }
     if (kind == 2) {
-        // the streaming smoother's algorithm on its packed blocks (kernels.cuh, gs_stream_cta_kernel), in the least
-        // favourable legal interleaving: the pre-barrier half of wavefront g+1 runs entirely BEFORE the post-barrier
-        // half of wavefront g
+        // the streaming smoother's algorithm on its packed blocks (kernels.cuh, gs_stream_cta_kernel) with three wavefronts
+        // in flight, in the least favourable legal interleaving: the product pass of wavefront g+2 and the late2 patch +
+        // prefix fold of wavefront g+1 run entirely BEFORE the post-barrier half of wavefront g (W >= 4; otherwise two in flight)
         StreamLayout SL;
         build_stream(L, SL);
         const int total = W * nsweeps;
-        std::vector<std::vector<unsigned char>> live(2);
-        auto pre = [&](int g) {
+        const int D = W >= 4 ? 3 : 2;
+        std::vector<std::vector<unsigned char>> live(3);
+        auto prod = [&](int g) {
             const int w = g % W;
-            std::vector<unsigned char> &blk = live[g & 1];
+            std::vector<unsigned char> &blk = live[g % 3];
             blk.assign(SL.data.data() + (size_t)SL.blk_ptr[w] * 16, SL.data.data() + (size_t)SL.blk_ptr[w + 1] * 16);
             const int *hd = reinterpret_cast<const int *>(blk.data());
             for (int ri = 0; ri < hd[0]; ++ri) {
@@ -110,30 +111,52 @@ void amgb200_debug_gs_walk(const amgb200_mat *A, const int *mark, int kind, int 
                 double *val = reinterpret_cast<double *>(rec + 32);
                 const int *col = reinterpret_cast<const int *>(val + rh[2]);
                 for (int p = 0; p < rh[2]; ++p) if (col[p] >= 0) val[p] = val[p] * xs[col[p]];
+            }
+        };
+        auto mid = [&](int g) {
+            std::vector<unsigned char> &blk = live[g % 3];
+            const int *hd = reinterpret_cast<const int *>(blk.data());
+            for (int ri = 0; ri < hd[0]; ++ri) {
+                unsigned char *rec = blk.data() + hd[4 + ri];
+                const int *rh = reinterpret_cast<const int *>(rec);
+                double *val = reinterpret_cast<double *>(rec + 32);
+                const StreamLate *lt2 = reinterpret_cast<const StreamLate *>(reinterpret_cast<const int *>(val + rh[2]) + rh[2]) + (rh[3] & 0xffff);
+                for (int i = 0; i < (rh[3] >> 16); ++i) val[lt2[i].pos] = lt2[i].val * xs[lt2[i].col];
                 double t = bs[rh[0]];
                 for (int p = 0; p < rh[1]; ++p) t -= val[p];
                 reinterpret_cast<double *>(rec)[3] = t;
             }
         };
         auto post = [&](int g) {
-            std::vector<unsigned char> &blk = live[g & 1];
+            std::vector<unsigned char> &blk = live[g % 3];
             const int *hd = reinterpret_cast<const int *>(blk.data());
             for (int ri = hd[0] - 1; ri >= 0; --ri) {
                 unsigned char *rec = blk.data() + hd[4 + ri];
                 const int *rh = reinterpret_cast<const int *>(rec);
                 double *val = reinterpret_cast<double *>(rec + 32);
                 const StreamLate *lt = reinterpret_cast<const StreamLate *>(reinterpret_cast<const int *>(val + rh[2]) + rh[2]);
-                for (int i = 0; i < rh[3]; ++i) val[lt[i].pos] = lt[i].val * xs[lt[i].col];
+                for (int i = 0; i < (rh[3] & 0xffff); ++i) val[lt[i].pos] = lt[i].val * xs[lt[i].col];
                 double t = reinterpret_cast<double *>(rec)[3];
                 for (int p = rh[1]; p < rh[2]; ++p) t -= val[p];
                 const double d = reinterpret_cast<double *>(rec)[2];
                 if (fabs(d) > 1e-20) xs[rh[0]] = t / d;
             }
         };
-        if (total > 0) pre(0);
-        for (int g = 0; g < total; ++g) {
-            if (g + 1 < total) pre(g + 1);
-            post(g);
+        if (D == 3) {
+            if (total > 0) prod(0);
+            if (total > 1) prod(1);
+            if (total > 0) mid(0);
+            for (int g = 0; g < total; ++g) {
+                if (g + 2 < total) prod(g + 2);      // needs done(g-1)
+                if (g + 1 < total) mid(g + 1);       // needs done(g-1)
+                post(g);
+            }
+        } else {
+            if (total > 0) { prod(0); mid(0); }
+            for (int g = 0; g < total; ++g) {
+                if (g + 1 < total) { prod(g + 1); mid(g + 1); }
+                post(g);
+            }
         }
         for (int k = 0; k < n; ++k) x[S.order[k]] = xs[k];
         return;

@@ -179,7 +179,7 @@ struct Level {
     int cta_cap = 0;                   // strategy 2, two-phase rows: parked suffix products per warp (0 = stream the suffix)
     unsigned char *d_stream = nullptr; // strategy 4 (streaming single CTA): per-wavefront blocks (analysis.h, StreamLayout)
     int *d_blk_ptr = nullptr;
-    int stream_G = 1, stream_S = 1, stream_ring = 0;   // consumer warps per group, row slots per warp
+    int stream_G = 1, stream_S = 1, stream_D = 2, stream_ring = 0;   // consumer warps per group, row slots per warp, groups (wavefronts in flight)
     int xc_F = 1, xc_S = 1, xc_P = 32, xc_ring = 0, xc_cap = 0;   // strategy 5 (streaming cluster): folding warps per group, row slots, ring bytes, exchange-buffer doubles
     int dsmem_sh = 0;                  // strategy 3: x distributed over the cluster's shared memory, 2^sh rows per CTA (0 = x in global memory)
     bool natural = false;              // natural-order Gauss-Seidel (cf_order = 0 or no cfmark): forward sweeps use this level's
@@ -331,22 +331,22 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
             attr_set = true;
         }
         const size_t xb = ((size_t)lv.n * 8 + 15) & ~(size_t)15;
-        const size_t smem = 256 + xb + (size_t)lv.stream_ring + 128;
-        gs_stream_cta_kernel<<<1, 32 * (2 * lv.stream_G + 1), smem, h->stream>>>(lv.d_stream, lv.d_blk_ptr, lv.d_wf_item_ptr, lv.b, lv.x, lv.n, lv.W, nsweeps,
-                                                                            lv.stream_G, lv.stream_S, lv.stream_ring, lv.A.v.recip, h->d_dbg);
+        const size_t smem = STREAM_HDR + xb + (size_t)lv.stream_ring + 128;
+        gs_stream_cta_kernel<<<1, 32 * (lv.stream_D * lv.stream_G + 1), smem, h->stream>>>(lv.d_stream, lv.d_blk_ptr, lv.d_wf_item_ptr, lv.b, lv.x, lv.n, lv.W, nsweeps,
+                                                                            lv.stream_G, lv.stream_S, lv.stream_D, lv.stream_ring, lv.A.v.recip, h->d_dbg);
         ++g_launches;
 #ifdef AMGB200_TIMELINE
         if (h->d_dbg) {
             long long hd[32];
             CUDA_CHECK(cudaStreamSynchronize(h->stream));
             CUDA_CHECK(cudaMemcpy(hd, h->d_dbg, sizeof(hd), cudaMemcpyDeviceToHost));
-            const char *nm[9] = {"wait block", "products", "prefix fold", "bar.sync(prev wavefront)", "patch late", "suffix fold", "div+store", "group barrier", "arrive+release"};
-            const int iters = (lv.W * nsweeps + 1) / 2;
+            const char *nm[11] = {"wait block", "products", "prefix fold", "wait done(g-1)", "patch late", "suffix fold", "div+store", "group barrier", "arrive+release", "wait done(g-2)", "patch late2"};
+            const int iters = (lv.W * nsweeps + lv.stream_D - 1) / lv.stream_D;
             for (int g2 = 0; g2 < 2; ++g2) {
                 printf("   stream timeline group %d warp r=0 (cycles per wavefront, %d wavefronts, G=%d):", g2, iters, lv.stream_G);
                 long long tot = 0;
-                for (int i = 0; i < 9; ++i) { printf("  %s %lld", nm[i], hd[g2 * 16 + i] / iters); tot += hd[g2 * 16 + i]; }
-                printf("  | total %lld | suffix terms folded per wavefront %lld\n", tot / iters, hd[g2 * 16 + 9] / iters);
+                for (int i = 0; i < 11; ++i) { printf("  %s %lld", nm[i], hd[g2 * 16 + i] / iters); tot += hd[g2 * 16 + i]; }
+                printf("  | total %lld (D=%d groups)\n", tot / iters, lv.stream_D);
             }
         }
 #endif
@@ -962,7 +962,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     // largest wavefront blocks fit in shared memory
     if (lv.ordered && lay.kind == KIND_CSR && h->exact && !getenv("AMGB200_GS_STRATEGY") && (double)wip[lv.W] / lv.W <= stream_max_avg) {
         const size_t xb = ((size_t)lv.n * 8 + 15) & ~(size_t)15;
-        const long long ring = (long long)h->max_dyn_smem - 256 - (long long)xb - 128;
+        const long long ring = (long long)h->max_dyn_smem - STREAM_HDR - (long long)xb - 128;
         if (ring >= 4096) {
             StreamLayout SL;
             const double tl = now_s();
@@ -978,9 +978,14 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                 lv.stream_S = 1;
                 while (lv.stream_S < 32 && lv.stream_S < lv.max_width) lv.stream_S *= 2;
                 if (getenv("AMGB200_STREAM_S")) { int v = std::max(1, std::min(32, atoi(getenv("AMGB200_STREAM_S")))); lv.stream_S = 1; while (lv.stream_S < v) lv.stream_S *= 2; }
+                // three wavefronts in flight (the late2 lists exist for W >= 4); a ring that cannot hold three of the largest
+                // blocks only serialises the affected wavefronts (every block is released in order)
+                lv.stream_D = lv.W >= 4 ? 3 : 2;
+                if (getenv("AMGB200_STREAM_D")) { const int d = atoi(getenv("AMGB200_STREAM_D")); if (d == 2 || (lv.W >= 4 && d == 3)) lv.stream_D = d; }
+                if (lv.stream_D * lv.stream_G > 16) lv.stream_G = 4;
                 lv.d_stream = dev_upload(SL.data);
                 lv.d_blk_ptr = dev_upload(SL.blk_ptr);
-                if (h->opt.verbose >= 2) printf("      streaming CTA smoother: 2 groups of %d product warps, %d row slots in the folding warp, ring %d B, wavefront block mean %lld B max %d B, stream %.1f MB\n", lv.stream_G, lv.stream_S, lv.stream_ring, SL.mean_block, SL.max_block, SL.data.size() / 1e6);
+                if (h->opt.verbose >= 2) printf("      streaming CTA smoother: %d groups of %d product warps, %d row slots in the folding warp, ring %d B, wavefront block mean %lld B max %d B, stream %.1f MB\n", lv.stream_D, lv.stream_G, lv.stream_S, lv.stream_ring, SL.mean_block, SL.max_block, SL.data.size() / 1e6);
             }
         }
     }
@@ -1439,6 +1444,19 @@ void amgb200_cycle_from(amgb200_hier *h, int level) {
 }
 void amgb200_vec_to_schedule(amgb200_hier *h, int level, const double *d_nat, double *d_sched) { check_level(h, level); to_schedule(h, level, d_nat, d_sched); }
 void amgb200_vec_to_natural(amgb200_hier *h, int level, const double *d_sched, double *d_nat) { check_level(h, level); to_natural(h, level, d_sched, d_nat); }
+// test hook (not part of the documented ABI): number of operand pairs for which the precomputed-reciprocal quotient of the
+// ordered smoothers differs from __ddiv_rn
+__attribute__((visibility("default"))) long long amgb200_debug_quotient_check(long long n, unsigned long long seed, int mode) {
+    unsigned long long *d_bad = nullptr, bad = 0;
+    CUDA_CHECK(cudaMalloc(&d_bad, sizeof(bad)));
+    CUDA_CHECK(cudaMemset(d_bad, 0, sizeof(bad)));
+    quotient_check_kernel<<<1184, BLOCK>>>(n, seed, mode, d_bad);
+    ++g_launches;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaFree(d_bad));
+    return (long long)bad;
+}
 void amgb200_sync(amgb200_hier *h) { CUDA_CHECK(cudaStreamSynchronize(h->stream)); }
 
 }  // extern "C"

@@ -51,6 +51,35 @@ __device__ __forceinline__ double gs_quotient(double t, double d, int recip) {
     return recip ? __dmul_rn(t, __ddiv_rn(1.0, d)) : __ddiv_rn(t, d);
 }
 
+// The same quotient with everything that depends only on d taken off the dependency path: y = RN(1/d) (an IEEE division,
+// done while the row still waits for its inputs) and `dsafe` (d in a range where nothing below can over/underflow).
+// t/d is then q2 of  q0 = RN(t y), r0 = t - q0 d (exact, FMA), q1 = RN(q0 + r0 y), r1 = t - q1 d, q2 = RN(q1 + r1 y):
+// q1 is within 1 ulp of t/d (|t/d - (q0 + r0 y)| = |t/d - q0| |1 - d y| <= 1.5 ulp * 2^-53), and one Markstein correction
+// step from a faithful q with y = RN(1/d) and an exact remainder yields the correctly rounded quotient (Markstein 1990;
+// Muller et al., Handbook of Floating-Point Arithmetic, "Newton-Raphson-based division with an FMA") -- the same
+// last step __ddiv_rn itself ends with.  5 dependent fp64 operations (~40 cycles) instead of MUFU.RCP64H + 9 (~200 measured).
+// Outside the guarded range (|t| tiny/huge/zero/non-finite) it falls back to __ddiv_rn.  Checked bit for bit against
+// __ddiv_rn on the device by tests/test_gpu_parity.py::test_quotient_fast_path (amgb200_debug_quotient_check).
+__device__ __forceinline__ bool gs_quotient_dsafe(double d) {
+    const double ad = fabs(d);
+    const long long m = __double_as_longlong(d) & 0x000fffffffffffffLL;
+    return ad > 0x1p-200 && ad < 0x1p200 && m != 0x000fffffffffffffLL;
+}
+// (a separate, never-inlined function: inlined, ptxas if-converts the guard and runs the whole IEEE division next to the
+// fast path on every call)
+__device__ __noinline__ double gs_quotient_slow(double t, double d) { return __ddiv_rn(t, d); }
+__device__ __forceinline__ double gs_quotient_pre(double t, double d, double y, bool dsafe, int recip, bool need = true) {
+    if (recip) return __dmul_rn(t, y);                                         // SSS_smooth.c:112-118: x = t * (1/d)
+    const double q0 = __dmul_rn(t, y);
+    const double r0 = __fma_rn(-q0, d, t);
+    const double q1 = __fma_rn(r0, y, q0);
+    const double r1 = __fma_rn(-q1, d, t);
+    double q2 = __fma_rn(r1, y, q1);
+    const double at = fabs(t);
+    if (need && !(dsafe && at > 0x1p-700 && at < 0x1p700)) q2 = gs_quotient_slow(t, d);
+    return q2;
+}
+
 // where the x vector of a level lives during a launch
 template <bool COH>
 struct GlobalX {                       // global memory (or this CTA's shared memory: generic addressing)
@@ -788,7 +817,9 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
 // recompute the few "late" products, fold the suffix, divide and store: that chain is the whole critical path.
 // Dynamic shared memory: [mbarriers full[NS], empty[NS] | ring offsets | 64 B of zeros : 256 B][x : n doubles][ring]
 // ------------------------------------------------------------------------------------------
-constexpr int STREAM_NS = 4;                  // wavefront blocks in flight (ring descriptors)
+constexpr int STREAM_NS = 8;                  // wavefront blocks in flight (ring descriptors)
+constexpr int STREAM_HDR = 384;               // bytes of barriers / descriptors in front of x
+constexpr int STREAM_MAX_WARPS = 17;          // D groups of G warps + the loader (D*G <= 16)
 constexpr int STREAM_MAX_G = 8;               // product warps per group (1, 2, 4 or 8)
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -798,6 +829,13 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     unsigned ok;
     do {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// busy polling (test_wait never suspends the thread): lowest wake-up latency, for the waits on the dependency path
+__device__ __forceinline__ void mbar_wait_spin(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
 __device__ __forceinline__ void mbar_wait_sleep(unsigned bar, unsigned parity) {
@@ -853,44 +891,54 @@ __device__ __forceinline__ double chain_fold_slots(double t, unsigned sp, int cn
     return t;
 }
 
-__global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_kernel(
+__global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
     const unsigned char *__restrict__ stream, const int *__restrict__ blk_ptr, const int *__restrict__ wf_row_ptr,
-    const double *__restrict__ b, double *xg, int n, int W, int nsweeps, int G, int S, int ring_bytes, int recip, long long *dbg) {
+    const double *__restrict__ b, double *xg, int n, int W, int nsweeps, int G, int S, int D, int ring_bytes, int recip, long long *dbg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);      // full[0..NS), empty[0..NS)
-    volatile int *stage_off = reinterpret_cast<volatile int *>(smem_raw + 64);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);      // full[0..NS), empty[NS..2NS); done[8] at +256
+    volatile int *stage_off = reinterpret_cast<volatile int *>(smem_raw + 192);
     const unsigned zeros_a = smem_u32(smem_raw + 128);
-    double *x = reinterpret_cast<double *>(smem_raw + 256);
-    unsigned char *ring = smem_raw + 256 + (((size_t)n * 8 + 15) & ~(size_t)15);
+    const unsigned done0 = smem_u32(smem_raw + 256);
+    double *x = reinterpret_cast<double *>(smem_raw + STREAM_HDR);
+    unsigned char *ring = smem_raw + STREAM_HDR + (((size_t)n * 8 + 15) & ~(size_t)15);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int totalw = W * nsweeps;
     const unsigned x_a = smem_u32(x);
 #ifdef AMGB200_TIMELINE
-    long long tl[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tl[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tl_prev = clock64();
+#if AMGB200_TIMELINE == 2          // only two clock reads per wavefront: [8] = done(g-1) observed -> done(g) announced, [3] = everything else
+#define SL_MARK(i) { if ((i) == 3 || (i) == 8) { const long long c_ = clock64(); tl[i] += c_ - tl_prev; tl_prev = c_; } }
+#else
 #define SL_MARK(i) { const long long c_ = clock64(); tl[i] += c_ - tl_prev; tl_prev = c_; }
+#endif
 #else
 #define SL_MARK(i)
 #endif
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STREAM_NS; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + STREAM_NS + s), 1); }
+        for (int s = 0; s < STREAM_NS; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + STREAM_NS + s), 1); mbar_init(done0 + 8u * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 8) reinterpret_cast<double *>(smem_raw + 128)[threadIdx.x] = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = xg[i];
     __syncthreads();
-    if (warp < 2 * G) {
-        // warps [0,G) = group 0, [G,2G) = group 1.  All G warps of a group multiply (one row at a time, rows dealt round-robin);
-        // ONE warp per group folds: its lanes are split into S row slots, so a single warp-wide DSUB advances every row
-        // of the wavefront, and the two folding warps sit on different SM sub-partitions (a warp-wide DADD occupies a
-        // sub-partition's fp64 pipe for 4 cycles: two chains on one pipe slow each other down, measured 8.6 -> 11 cycles
-        // per term).  G is 1, 2 or 4.
+    if (warp < D * G) {
+        // warps [d*G, (d+1)*G) = group d; group d walks the wavefronts g = d, d+D, ...  All G warps of a group multiply (one
+        // row at a time, rows dealt round-robin); ONE warp per group folds: its lanes are split into S row slots, so a single
+        // warp-wide DSUB advances every row of the wavefront, and the folding warps sit on different SM sub-partitions (a
+        // warp-wide DADD occupies a sub-partition's fp64 pipe for 4 cycles: two chains on one pipe slow each other down,
+        // measured 8.6 -> 11 cycles per term).  G is 1, 2 or 4 (8 with two groups).
+        //
+        // D wavefronts are in flight.  x_k of wavefront g is announced on the mbarrier done[g & 7].  With D = 3 the product
+        // pass of wavefront g starts when g-3 is complete: entries whose column lies in wavefront g-2 ("late2", host-flagged) are
+        // redone after done(g-2), before the prefix fold; entries in g-1 ("late") after done(g-1), before the suffix fold.
+        // The pre-barrier work of a wavefront (products + prefix fold) thereby has TWO post-barrier periods to hide in.
         const int grp = warp / G, r = warp - grp * G;
-        const bool folder = r == (G > 1 ? grp : 0);
+        const bool folder = r == (G > 1 ? grp % G : 0);
         const int sub = 32 / S, slot = lane / sub;
         const int lis = lane - slot * sub;       // lane in slot
         const bool leader = lis == 0;
-        for (int g = grp; g < totalw; g += 2) {
+        for (int g = grp; g < totalw; g += D) {
             const int s = g & (STREAM_NS - 1);
             SL_MARK(7)
             mbar_wait(smem_u32(bars + s), (g / STREAM_NS) & 1);
@@ -899,7 +947,7 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
             const int4 hd = *reinterpret_cast<const int4 *>(blk);                   // nrows, first row & ~1, rhs count, block bytes
             const int *rec_off = reinterpret_cast<const int *>(blk + 16);
             const double *bseg = reinterpret_cast<const double *>(blk + hd.w);
-            // ---- before the barrier: products of every entry (late ones are redone below) ...
+            // ---- products of every entry (late / late2 ones are redone below) ...
 #if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 13
             for (int ri = r; ri < 0; ri += G) {
 #else
@@ -929,19 +977,42 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
             if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");      // all products of the wavefront are in place
             else __syncwarp();
             if (folder) {
-                // ... and the prefix chains.  Everything the post-barrier half of the FIRST round needs is kept in
+                // ---- after done(g-2): the late2 products of every row
+                if (D > 2) {
+                    if (g >= 2) mbar_wait(done0 + 8u * (unsigned)((g - 2) & 7), ((g - 2) >> 3) & 1);
+                    SL_MARK(9)
+                    for (int base = 0; base < hd.x; base += S) {
+                        const int ri = base + slot;
+                        if (ri < hd.x) {
+                            unsigned char *rec = blk + rec_off[ri];
+                            const int4 rh = *reinterpret_cast<const int4 *>(rec);
+                            const unsigned val_a = smem_u32(rec + 32), l2_a = val_a + 12u * (unsigned)rh.z + 16u * (unsigned)(rh.w & 0xffff);
+                            const int n2 = rh.w >> 16;
+                            for (int i = lis; i < n2; i += sub) {
+                                const double lv = lds_f64(l2_a + 16u * (unsigned)i);
+                                const int lp = lds_s32(l2_a + 16u * (unsigned)i + 8u), lc = lds_s32(l2_a + 16u * (unsigned)i + 12u);
+                                sts_f64(val_a + 8u * (unsigned)lp, __dmul_rn(lv, lds_f64(x_a + 8u * (unsigned)lc)));
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    SL_MARK(10)
+                }
+                // ---- the prefix chains.  Everything the post-barrier half of the FIRST round needs is kept in
                 // registers (c_*): its dependent path is x of the late entries -> product -> store -> suffix chain ->
                 // divide -> store.
                 bool c_mine = false;
                 unsigned c_suf = 0, c_late = 0, c_val = 0;       // shared-space addresses: suffix products, late list, products
                 int c_cnt = 0, c_maxc = 0, c_row = 0, c_nlate = 0;
-                double c_t = 0.0, c_d = 0.0;
-                StreamLateDev c_e = {0.0, 0, 0};
+                double c_t = 0.0, c_d = 0.0, c_y = 0.0;
+                bool c_dsafe = false, c_store = false;
+                unsigned c_xaddr = 0;
+                StreamLateDev c_e = {0.0, 0, 0}, c_e2 = {0.0, 0, 0};
                 for (int base = 0; base < hd.x; base += S) {
                     const int ri = base + slot;
                     const bool mine = ri < hd.x;
                     unsigned char *rec = blk + (mine ? rec_off[ri] : rec_off[0]);
-                    const int4 rh = *reinterpret_cast<const int4 *>(rec);               // row, prefix_pad, len_pad, nlate
+                    const int4 rh = *reinterpret_cast<const int4 *>(rec);               // row, prefix_pad, len_pad, nlate | nlate2 << 16
 #if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 14
                     const int cnt = 0;
 #else
@@ -951,6 +1022,10 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
                     const double t = chain_fold_slots(mine ? bseg[rh.x - hd.y] : 0.0, smem_u32(rec + 32), cnt, maxc, zeros_a);
                     if (base == 0) {
                         c_mine = mine; c_row = rh.x; c_t = t; c_d = reinterpret_cast<const double *>(rec)[2];
+                        c_y = __ddiv_rn(1.0, c_d); c_dsafe = gs_quotient_dsafe(c_d);
+                        c_store = mine && leader && fabs(c_d) > GS_TINY;
+                        c_xaddr = x_a + 8u * (unsigned)rh.x;
+                        asm volatile("" : "+r"(c_xaddr));            // keep the address in a register (ptxas otherwise rebuilds it from SR_CgaCtaId after the chain)
                         c_val = smem_u32(rec + 32);
                         c_suf = c_val + 8u * (unsigned)rh.y;
 #if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 15
@@ -962,23 +1037,28 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
 #if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 12
                         c_nlate = 0;
 #else
-                        c_nlate = mine ? rh.w : 0;
+                        c_nlate = mine ? (rh.w & 0xffff) : 0;
 #endif
                         c_late = c_val + 12u * (unsigned)rh.z;
                         if (lis < c_nlate) c_e = *reinterpret_cast<const StreamLateDev *>(rec + 32 + 12 * rh.z + 16 * lis);
+                        if (lis + sub < c_nlate) c_e2 = *reinterpret_cast<const StreamLateDev *>(rec + 32 + 12 * rh.z + 16 * (lis + sub));
                     } else if (mine && leader) reinterpret_cast<double *>(rec)[3] = t;
 #ifdef AMGB200_TIMELINE
-                    if (t == 1.2345e300) tl[9] = 1;
+                    if (t == 1.2345e300) tl[11] = 1;
 #endif
                 }
                 SL_MARK(2)
                 __syncwarp();
-                if (g > 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + ((g - 1) & 7)), "r"(64) : "memory");
+                if (g > 0) mbar_wait_spin(done0 + 8u * (unsigned)((g - 1) & 7), ((g - 1) >> 3) & 1);
                 SL_MARK(3)
-                // ---- after the barrier: late products, suffix chains, x_k
+                // ---- after done(g-1): late products (the first two per lane from registers), suffix chains, x_k
                 {
-                    if (lis < c_nlate) sts_f64(c_val + 8u * (unsigned)c_e.pos, __dmul_rn(c_e.val, lds_f64(x_a + 8u * (unsigned)c_e.col)));
-                    for (int i = lis + sub; i < c_nlate; i += sub) {
+                    {
+                        const double x1 = lds_f64(x_a + 8u * (unsigned)c_e.col), x2 = lds_f64(x_a + 8u * (unsigned)c_e2.col);
+                        if (lis < c_nlate) sts_f64(c_val + 8u * (unsigned)c_e.pos, __dmul_rn(c_e.val, x1));
+                        if (lis + sub < c_nlate) sts_f64(c_val + 8u * (unsigned)c_e2.pos, __dmul_rn(c_e2.val, x2));
+                    }
+                    for (int i = lis + 2 * sub; i < c_nlate; i += sub) {
                         const double lv = lds_f64(c_late + 16u * (unsigned)i);
                         const int lp = lds_s32(c_late + 16u * (unsigned)i + 8u), lc = lds_s32(c_late + 16u * (unsigned)i + 12u);
                         sts_f64(c_val + 8u * (unsigned)lp, __dmul_rn(lv, lds_f64(x_a + 8u * (unsigned)lc)));
@@ -986,15 +1066,17 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
                     __syncwarp();
                     SL_MARK(4)
                     const double t = chain_fold_slots(c_t, c_suf, c_cnt, c_maxc, zeros_a);
-#ifdef AMGB200_TIMELINE
-                    if (t == 1.2345e300) tl[9] = 1;
+#if defined(AMGB200_TIMELINE) && AMGB200_TIMELINE != 2
+                    if (t == 1.2345e300) tl[11] = 1;
                     SL_MARK(5)
-                    tl[9] += c_maxc;
 #endif
 #if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 11
                     if (c_mine && leader && fabs(c_d) > GS_TINY) sts_f64(x_a + 8u * (unsigned)c_row, __dmul_rn(t, c_d));
 #else
-                    if (c_mine && leader && fabs(c_d) > GS_TINY) sts_f64(x_a + 8u * (unsigned)c_row, gs_quotient(t, c_d, recip));
+                    {
+                        const double xn = gs_quotient_pre(t, c_d, c_y, c_dsafe, recip, c_store);
+                        if (c_store) sts_f64(c_xaddr, xn);
+                    }
 #endif
                     SL_MARK(6)
                 }
@@ -1006,7 +1088,7 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
                     double *val = reinterpret_cast<double *>(rec + 32);
                     if (mine) {
                         const StreamLateDev *lt = reinterpret_cast<const StreamLateDev *>(reinterpret_cast<const int *>(val + rh.z) + rh.z);
-                        for (int i = lis; i < rh.w; i += sub) { const StreamLateDev e = lt[i]; val[e.pos] = __dmul_rn(e.val, lds_f64(x_a + 8u * (unsigned)e.col)); }
+                        for (int i = lis; i < (rh.w & 0xffff); i += sub) { const StreamLateDev e = lt[i]; val[e.pos] = __dmul_rn(e.val, lds_f64(x_a + 8u * (unsigned)e.col)); }
                     }
                     __syncwarp();
                     const double2 dt = *reinterpret_cast<const double2 *>(rec + 16);    // diag, prefix accumulator
@@ -1015,9 +1097,10 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
                     const double t = chain_fold_slots(dt.y, smem_u32(val + rh.y), cnt, maxc, zeros_a);
                     if (mine && leader && fabs(dt.x) > GS_TINY) sts_f64(x_a + 8u * (unsigned)rh.x, gs_quotient(t, dt.x, recip));
                 }
-                // bar.arrive orders this thread's prior shared-memory stores before the consumer's bar.sync (PTX ISA, bar:
-                // producer/consumer example)
-                if (g + 1 < totalw) asm volatile("bar.arrive %0, %1;" ::"r"(1 + (g & 7)), "r"(64) : "memory");
+                // the leaders' x stores are ordered before lane 0's arrive by the warp barrier (memory ordering among its
+                // participants); mbarrier.arrive has release, the waiters' try_wait acquire semantics at CTA scope
+                __syncwarp();
+                if (lane == 0 && g + 1 < totalw) mbar_arrive(done0 + 8u * (unsigned)(g & 7));
                 SL_MARK(8)
             }
             // every warp's generic writes to the block precede its reuse by the async proxy: fence, group barrier, release
@@ -1027,9 +1110,9 @@ __global__ void __launch_bounds__(32 * (2 * STREAM_MAX_G + 1)) gs_stream_cta_ker
             if (folder && lane == 0) mbar_arrive(smem_u32(bars + STREAM_NS + s));
         }
 #ifdef AMGB200_TIMELINE
-        if (dbg && lane == 0 && folder) for (int i = 0; i < 10; ++i) dbg[grp * 16 + i] = tl[i];
+        if (dbg && lane == 0 && folder && grp < 2) for (int i = 0; i < 12; ++i) dbg[grp * 16 + i] = tl[i];
 #endif
-    } else if (lane == 0) {
+    } else if (warp == D * G && lane == 0) {
         // ---- loader: in-order ring allocation; a block is released when its group's folding warp has arrived on empty[s]
         int head = 0, tail = 0, inflight = 0, g_old = 0, wl = 0;
         for (int g = 0; g < totalw; ++g) {
@@ -1206,7 +1289,8 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
                 bool c_mine = false;
                 unsigned c_suf = 0, c_late = 0, c_val = 0;
                 int c_cnt = 0, c_maxc = 0, c_row = 0, c_nlate = 0, c_li = 0;
-                double c_t = 0.0, c_d = 0.0;
+                double c_t = 0.0, c_d = 0.0, c_y = 0.0;
+                bool c_dsafe = false;
                 for (int base = 0; base < hd.x; base += FS) {
                     const int ri = base + slot * F + f;
                     const bool mine = ri < hd.x;
@@ -1218,6 +1302,7 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
                     const double t = chain_fold_slots(t0, smem_u32(rec + 32), cnt, maxc, zeros_a);
                     if (base == 0) {
                         c_mine = mine; c_row = rh.x; c_t = t; c_d = reinterpret_cast<const double *>(rec)[2]; c_li = ri;
+                        c_y = __ddiv_rn(1.0, c_d); c_dsafe = gs_quotient_dsafe(c_d);
                         c_val = smem_u32(rec + 32);
                         c_suf = c_val + 8u * (unsigned)rh.y;
                         c_cnt = mine ? rh.z - rh.y : 0;
@@ -1271,7 +1356,7 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
 #endif
                     double xn = 0.0;
                     if (mine && lis == 0) {
-                        if (fabs(dg) > GS_TINY) xn = gs_quotient(t, dg, recip);
+                        if (fabs(dg) > GS_TINY) xn = base == 0 ? gs_quotient_pre(t, dg, c_y, c_dsafe, recip) : gs_quotient(t, dg, recip);
                         else asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(xn) : "l"(x + row) : "memory");     // row without a diagonal: x_k unchanged (never speculated)
                     }
                     xn = __shfl_sync(FULL, xn, slot * sub);
@@ -1625,6 +1710,42 @@ __global__ void __launch_bounds__(BLOCK) dot_tree_kernel(int n, const double *__
 }
 
 // permutations between natural and schedule numbering
+// test hook: gs_quotient_pre against __ddiv_rn, bit for bit, on generated operand pairs (mode 0: random significands,
+// moderate exponents; 1: raw 64-bit patterns; 2: t within a few ulps of q*d for random q -- quotients next to
+// representable numbers and rounding midpoints; 3: divisors next to powers of two and with saturated significands)
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long &s) {
+    unsigned long long z = (s += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(BLOCK) quotient_check_kernel(long long n, unsigned long long seed, int mode, unsigned long long *mismatch) {
+    unsigned long long bad = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long s = seed + 0x632be59bd9b4e019ULL * (unsigned long long)(i + 1);
+        const unsigned long long a = splitmix64(s), b = splitmix64(s), c = splitmix64(s);
+        double t, d;
+        auto mk = [](unsigned long long bits, int e) { return __longlong_as_double((long long)((bits & 0x800fffffffffffffULL) | ((unsigned long long)(1023 + e) << 52))); };
+        if (mode == 0) { t = mk(a, (int)(c % 121) - 60); d = mk(b, (int)((c >> 8) % 41) - 20); }
+        else if (mode == 1) { t = __longlong_as_double((long long)a); d = __longlong_as_double((long long)b); }
+        else if (mode == 2) {
+            const double q = mk(a, (int)(c % 61) - 30);
+            d = mk(b, (int)((c >> 8) % 41) - 20);
+            t = __dmul_rn(q, d);
+            t = __longlong_as_double(__double_as_longlong(t) + (long long)((c >> 20) % 5) - 2);
+        } else {
+            const unsigned long long lowbits = (c >> 12) % 3 == 0 ? 0ULL : ((c >> 12) % 3 == 1 ? 0x000fffffffffffffULL : 0x000ffffffffffff0ULL);
+            d = mk((b & 0x8000000000000000ULL) | ((lowbits + (c & 7)) & 0x000fffffffffffffULL), (int)((c >> 8) % 41) - 20);
+            t = mk(a, (int)(c % 121) - 60);
+        }
+        const double ref = __ddiv_rn(t, d);
+        const double got = gs_quotient_pre(t, d, __ddiv_rn(1.0, d), gs_quotient_dsafe(d), 0);
+        const bool same = __double_as_longlong(ref) == __double_as_longlong(got) || (ref != ref && got != got);
+        if (!same) ++bad;
+    }
+    if (bad) atomicAdd(mismatch, bad);
+}
+
 __global__ void __launch_bounds__(BLOCK) gather_kernel(int n, const int *__restrict__ order, const double *__restrict__ in, double *out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) out[k] = in[order[k]];

@@ -327,3 +327,18 @@ def test_linearity_of_spmv_property():
     rhs = 2.5 * dev.spmv(0, "A", x) + dev.spmv(0, "A", y)
     assert rel_err(lhs, rhs) <= 1e-13
     dev.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_quotient_fast_path(mode):
+    """the ordered smoothers' quotient with the reciprocal taken off the dependency path (kernels.cuh: gs_quotient_pre)
+    is bit-identical to IEEE division (SSS_smooth.c:32) on 2^26 generated operand pairs per mode: random operands, raw bit
+    patterns (incl. zeros, subnormals, infinities, NaNs), quotients within 2 ulps of representable numbers / midpoints,
+    divisors next to powers of two and with saturated significands"""
+    import ctypes as C
+    L = capi.lib()
+    L.amgb200_debug_quotient_check.restype = C.c_longlong
+    L.amgb200_debug_quotient_check.argtypes = [C.c_longlong, C.c_ulonglong, C.c_int]
+    for seed in (1, 2026):
+        assert L.amgb200_debug_quotient_check(1 << 26, seed, mode) == 0
