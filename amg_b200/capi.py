@@ -73,7 +73,7 @@ EXPORTS = [
     "amgb200_algorithmic_bytes", "amgb200_time_op", "amgb200_launch_count", "amgb200_last_phase_ms",
     "amgb200_version", "amgb200_generate", "amgb200_mat_free", "amgb200_setup", "amgb200_amg_destroy",
     "amgb200_default_pars", "amgb200_last_level_ms", "amgb200_set_profile", "amgb200_upload_seconds",
-    "amgb200_device_bytes", "amgb200_level_kernel", "amgb200_bench_solve",
+    "amgb200_device_bytes", "amgb200_level_kernel", "amgb200_level_chain_terms", "amgb200_bench_solve",
     "amgb200_set_stream", "amgb200_level_vec", "amgb200_level_order", "amgb200_l0_shape", "amgb200_l0_gs_pass",
     "amgb200_l0_residual", "amgb200_l0_prolong", "amgb200_restrict_from", "amgb200_cycle_from",
     "amgb200_vec_to_schedule", "amgb200_vec_to_natural", "amgb200_sync",
@@ -133,6 +133,8 @@ def lib():
         L.amgb200_upload_seconds.argtypes = [C.c_void_p, c_double_p]
         L.amgb200_device_bytes.restype = C.c_longlong
         L.amgb200_device_bytes.argtypes = [C.c_void_p]
+        L.amgb200_level_chain_terms.restype = C.c_longlong
+        L.amgb200_level_chain_terms.argtypes = [C.c_void_p, C.c_int]
         L.amgb200_level_kernel.restype = C.c_char_p
         L.amgb200_level_kernel.argtypes = [C.c_void_p, C.c_int]
         L.amgb200_bench_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

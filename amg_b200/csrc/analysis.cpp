@@ -185,10 +185,15 @@ void build_stream(const DevLayout &L, StreamLayout &S) {
     const int W = (int)L.wf_item_ptr.size() - 1;
     const std::vector<int> &wip = L.wf_item_ptr;
     auto r8 = [](int v) { return (v + 7) & ~7; };
+    auto r16 = [](int v) { return (v + 15) & ~15; };
     auto late_bit = [&](int q) { return (L.late[(size_t)q >> 5] >> (q & 31)) & 1u; };
     const bool have2 = !L.late2.empty();
     auto late2_bit = [&](int q) { return have2 ? (L.late2[(size_t)q >> 5] >> (q & 31)) & 1u : 0u; };
-    // per-row record size
+    // Bank alignment: the folding warp's lanes read 16 bytes each from DIFFERENT rows in lockstep (same term index in every
+    // row slot).  Blocks start on 128-byte boundaries of shared memory, the product array of row i of a wavefront starts in
+    // 16-byte bank group i % 8, and the prefix is padded to a multiple of 16 terms (128 bytes) so that the suffix starts in
+    // the same group: 32 row slots then hit every bank group exactly 4 times (no conflicts beyond the 512 bytes moved).
+    // per-row record size (before alignment padding)
     std::vector<int> rec_bytes((size_t)L.nrows);
 #pragma omp parallel for schedule(static)
     for (int k = 0; k < L.nrows; ++k) {
@@ -197,36 +202,43 @@ void build_stream(const DevLayout &L, StreamLayout &S) {
         for (int q = p0 + sp; q < p0 + len; ++q) nlate += late_bit(q);
         for (int q = p0; q < p0 + len; ++q) nlate2 += late2_bit(q);
         if (nlate > 0xffff || nlate2 > 0x7fff) { fprintf(stderr, "libamgb200: build_stream: late list of a row exceeds the record format\n"); abort(); }
-        const int len_pad = r8(sp) + r8(len - sp);
+        const int len_pad = r16(sp) + r8(len - sp);
         rec_bytes[k] = 32 + len_pad * 12 + (nlate + nlate2) * 16;
     }
+    auto place = [](int off, int ri) {           // first offset >= off whose product array (off + 32) lies in bank group ri % 8
+        while ((((off + 32) >> 4) & 7) != (ri & 7)) off += 16;
+        return off;
+    };
     S.blk_ptr.assign((size_t)W + 1, 0);
     S.max_block = 0;
     for (int w = 0; w < W; ++w) {
         const int nr = wip[w + 1] - wip[w];
-        long long bytes = 16 + (long long)((nr + 3) & ~3) * 4;
-        for (int k = wip[w]; k < wip[w + 1]; ++k) bytes += rec_bytes[k];
+        int off = 16 + ((nr + 3) & ~3) * 4;
+        for (int k = wip[w]; k < wip[w + 1]; ++k) off = place(off, k - wip[w]) + rec_bytes[k];
+        const long long bytes = (off + 127) & ~127;
         const int i0a = wip[w] & ~1, bcnt = (wip[w + 1] - i0a + 1) & ~1;
         S.blk_ptr[w + 1] = S.blk_ptr[w] + (int)(bytes / 16);
-        S.max_block = (int)std::max<long long>(S.max_block, bytes + (long long)bcnt * 8);
+        S.max_block = (int)std::max<long long>(S.max_block, ((bytes + (long long)bcnt * 8) + 127) & ~127LL);
     }
     S.data.resize((size_t)S.blk_ptr[W] * 16);
     S.mean_block = W ? (long long)S.blk_ptr[W] * 16 / W : 0;
 #pragma omp parallel for schedule(dynamic, 8)
     for (int w = 0; w < W; ++w) {
         unsigned char *blk = S.data.data() + (size_t)S.blk_ptr[w] * 16;
+        const int blk_bytes = (S.blk_ptr[w + 1] - S.blk_ptr[w]) * 16;
+        memset(blk, 0, (size_t)blk_bytes);
         const int nr = wip[w + 1] - wip[w];
         int *hd = reinterpret_cast<int *>(blk);
         const int i0a = wip[w] & ~1;
-        hd[0] = nr; hd[1] = i0a; hd[2] = (wip[w + 1] - i0a + 1) & ~1; hd[3] = (S.blk_ptr[w + 1] - S.blk_ptr[w]) * 16;
+        hd[0] = nr; hd[1] = i0a; hd[2] = (wip[w + 1] - i0a + 1) & ~1; hd[3] = blk_bytes;
         int *rec_off = hd + 4;
         int off = 16 + ((nr + 3) & ~3) * 4;
-        for (int i = nr; i < ((nr + 3) & ~3); ++i) rec_off[i] = 0;
         for (int k = wip[w]; k < wip[w + 1]; ++k) {
+            off = place(off, k - wip[w]);
             rec_off[k - wip[w]] = off;
             unsigned char *rec = blk + off;
             const int p0 = L.rptr[k], len = L.rptr[k + 1] - p0, sp = L.split[k];
-            const int pre_pad = r8(sp), len_pad = pre_pad + r8(len - sp);
+            const int pre_pad = r16(sp), len_pad = pre_pad + r8(len - sp);
             int *rh = reinterpret_cast<int *>(rec);
             double *rd = reinterpret_cast<double *>(rec);
             double *val = rd + 4;
@@ -274,7 +286,7 @@ void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, Cluste
             if (c != k && dist(wf_of[k], c) <= 2) { if (q < sp) sp = q; ++nl; }
         }
         split[k] = sp; nlate[k] = nl;
-        rec_bytes[k] = 32 + (r8(sp) + r8(len - sp)) * 12 + nl * 24;
+        rec_bytes[k] = 32 + (r8(sp) + r8(len - sp)) * 12;
         rec_bytes[k] = (rec_bytes[k] + 15) & ~15;
     }
     SL.blk_ptr.assign((size_t)W * C + 1, 0);
@@ -283,8 +295,10 @@ void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, Cluste
         const int width = wrp[w + 1] - wrp[w];
         for (int c = 0; c < C; ++c) {
             const int nr = width > c ? (width - c + C - 1) / C : 0;
-            long long bytes = 16 + (long long)((nr + 3) & ~3) * 4;
-            for (int li = 0; li < nr; ++li) bytes += rec_bytes[wrp[w] + c + li * C];
+            long long bytes = 32 + (long long)((nr + 3) & ~3) * 4;
+            long long nflat = 0;
+            for (int li = 0; li < nr; ++li) { bytes += rec_bytes[wrp[w] + c + li * C]; nflat += nlate[wrp[w] + c + li * C]; }
+            bytes += ((nflat * 24 + 15) & ~15LL);
             SL.blk_ptr[(size_t)w * C + c + 1] = SL.blk_ptr[(size_t)w * C + c] + (int)(bytes / 16);
             SL.max_block = (int)std::max<long long>(SL.max_block, bytes);
             SL.max_local = std::max(SL.max_local, nr);
@@ -304,10 +318,16 @@ void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, Cluste
             unsigned char *blk = SL.data.data() + (size_t)SL.blk_ptr[(size_t)w * C + c] * 16;
             const int nr = width > c ? (width - c + C - 1) / C : 0;
             int *hd = reinterpret_cast<int *>(blk);
-            hd[0] = nr; hd[1] = wrp[w]; hd[2] = width; hd[3] = (SL.blk_ptr[(size_t)w * C + c + 1] - SL.blk_ptr[(size_t)w * C + c]) * 16;
-            int *rec_off = hd + 4;
-            int off = 16 + ((nr + 3) & ~3) * 4;
+            const int blk_bytes = (SL.blk_ptr[(size_t)w * C + c + 1] - SL.blk_ptr[(size_t)w * C + c]) * 16;
+            hd[0] = nr; hd[1] = wrp[w]; hd[2] = width; hd[3] = blk_bytes;
+            int *rec_off = hd + 8;
+            int off = 32 + ((nr + 3) & ~3) * 4;
             for (int li = nr; li < ((nr + 3) & ~3); ++li) rec_off[li] = 0;
+            int flat_off = off;
+            for (int li = 0; li < nr; ++li) flat_off += rec_bytes[wrp[w] + c + li * C];
+            unsigned char *flat = blk + flat_off;
+            memset(flat, 0, (size_t)(blk_bytes - flat_off));
+            int nflat = 0;
             for (int li = 0; li < nr; ++li) {
                 const int k = wrp[w] + c + li * C, i = S.order[k];
                 rec_off[li] = off;
@@ -318,7 +338,6 @@ void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, Cluste
                 double *rd = reinterpret_cast<double *>(rec);
                 double *val = rd + 4;
                 int *col = reinterpret_cast<int *>(val + len_pad);
-                unsigned char *lt = reinterpret_cast<unsigned char *>(col + len_pad);
                 memset(rec, 0, (size_t)rec_bytes[k]);
                 for (int q = 0; q < len_pad; ++q) col[q] = -1;
                 double diag = 0.0;
@@ -333,15 +352,16 @@ void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, Cluste
                     if (d <= 2) {
                         const int ii = cc - wrp[wf_of[cc]];
                         StreamLateC e;
-                        e.val = v; e.pos = pos; e.col = cc; e.src = (d - 1) | (ii << 1); e.pad = 0;
-                        memcpy(lt + (size_t)nl * 24, &e, 24);
-                        ++nl;
+                        e.val = v; e.pos = off + 32 + 8 * pos; e.col = cc; e.src = (d - 1) | (ii << 1); e.pad = 0;
+                        memcpy(flat + (size_t)nflat * 24, &e, 24);
+                        ++nflat; ++nl;
                     }
                 }
                 rh[0] = k; rh[1] = pre_pad; rh[2] = len_pad; rh[3] = nl;
                 rd[2] = diag; rd[3] = 0.0;
                 off += rec_bytes[k];
             }
+            hd[4] = nflat; hd[5] = flat_off; hd[6] = 0; hd[7] = 0;
         }
     }
 }

@@ -93,10 +93,14 @@ void build_stream(const DevLayout &L, StreamLayout &S);
 // (i = schedule row - first row of the wavefront) belongs to CTA i % C of a C-CTA cluster, local index i / C; block
 // (w, c) = blk_ptr[w*C + c] holds CTA c's rows of wavefront w.  x stays in global memory for entries at cyclic
 // wavefront distance >= 3; entries at distance 1 or 2 ("late") are read from the exchange buffers in
-// shared memory (every CTA receives every x of the last three wavefronts): late record = {double val; int32 pos;
-// int32 col; int32 src; int32 0} with src = (distance-1) | index within its wavefront << 1.  Block header: rows of
-// this CTA, first row of the wavefront, width of the wavefront, block bytes.  Record header and val/col arrays as in StreamLayout;
-// the prefix ends at the first late entry.
+// shared memory (every CTA receives every x of the last three wavefronts).
+//   block  : int32 rows of this CTA, first row of the wavefront, width of the wavefront, block bytes,
+//            int32 nflat, flat_off (bytes), 0, 0                                                       (32 bytes)
+//            int32 rec_off[rows] (padded to a multiple of 4), records (header and val/col arrays as in StreamLayout, no
+//            per-row late lists; the prefix ends at the first late entry),
+//            flat late list: {double val; int32 dst; int32 col; int32 src; int32 0} for ALL late entries of the block,
+//            dst = byte offset of the product inside the block, src = (distance-1) | index within its wavefront << 1 --
+//            one flat list so that all lanes of a consumer group share the post-barrier patching evenly
 struct StreamLateC { double val; int pos; int col; int src; int pad; };
 struct ClusterStreamLayout {
     RawBuf<unsigned char> data;

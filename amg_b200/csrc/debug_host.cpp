@@ -60,8 +60,11 @@ void amgb200_debug_gs_walk(const amgb200_mat *A, const int *mark, int kind, int 
                                                SL.data.data() + (size_t)SL.blk_ptr[(size_t)w * Cc + c + 1] * 16);
                 const int *hd = reinterpret_cast<const int *>(blk.data());
                 exb[g][c].assign(hd[0], 0.0);
+                // product pass and prefix folds of every row, then ALL late products of the block from its flat list, then the
+                // suffix folds
+                std::vector<double> tacc(hd[0], 0.0);
                 for (int li = hd[0] - 1; li >= 0; --li) {
-                    unsigned char *rec = blk.data() + hd[4 + li];
+                    unsigned char *rec = blk.data() + hd[8 + li];
                     const int *rh = reinterpret_cast<const int *>(rec);
                     double *val = reinterpret_cast<double *>(rec + 32);
                     const int *col = reinterpret_cast<const int *>(val + rh[2]);
@@ -69,14 +72,21 @@ void amgb200_debug_gs_walk(const amgb200_mat *A, const int *mark, int kind, int 
                     for (int p = 0; p < rh[2]; ++p) if (col[p] >= 0) val[p] = val[p] * vis[col[p]];
                     double t = bs[rh[0]];
                     for (int p = 0; p < rh[1]; ++p) t -= val[p];
-                    const unsigned char *lt = reinterpret_cast<const unsigned char *>(col + rh[2]);
-                    for (int i = 0; i < rh[3]; ++i) {
-                        StreamLateC e;
-                        memcpy(&e, lt + (size_t)i * 24, 24);
-                        const int d = (e.src & 1) + 1, ii = e.src >> 1;
-                        const double xv = g - d >= 0 ? exb[g - d][ii % Cc][ii / Cc] : vis[e.col];
-                        val[e.pos] = e.val * xv;
-                    }
+                    tacc[li] = t;
+                }
+                const unsigned char *lt = blk.data() + hd[5];
+                for (int i = 0; i < hd[4]; ++i) {
+                    StreamLateC e;
+                    memcpy(&e, lt + (size_t)i * 24, 24);
+                    const int d = (e.src & 1) + 1, ii = e.src >> 1;
+                    const double xv = g - d >= 0 ? exb[g - d][ii % Cc][ii / Cc] : vis[e.col];
+                    *reinterpret_cast<double *>(blk.data() + e.pos) = e.val * xv;
+                }
+                for (int li = hd[0] - 1; li >= 0; --li) {
+                    unsigned char *rec = blk.data() + hd[8 + li];
+                    const int *rh = reinterpret_cast<const int *>(rec);
+                    const double *val = reinterpret_cast<const double *>(rec + 32);
+                    double t = tacc[li];
                     for (int p = rh[1]; p < rh[2]; ++p) t -= val[p];
                     const double d = reinterpret_cast<double *>(rec)[2];
                     double xn = xs[rh[0]];

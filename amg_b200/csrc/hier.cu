@@ -180,6 +180,8 @@ struct Level {
     unsigned char *d_stream = nullptr; // strategy 4 (streaming single CTA): per-wavefront blocks (analysis.h, StreamLayout)
     int *d_blk_ptr = nullptr;
     int stream_G = 1, stream_S = 1, stream_D = 2, stream_ring = 0;   // consumer warps per group, row slots per warp, groups (wavefronts in flight)
+    long long chain_terms = 0;                                    // ordered levels: sum over wavefronts of the longest post-barrier chain (terms per sweep)
+    int xc_D = 2;                                                 // strategy 5: consumer groups (wavefronts in flight)
     int xc_F = 1, xc_S = 1, xc_P = 32, xc_ring = 0, xc_cap = 0;   // strategy 5 (streaming cluster): folding warps per group, row slots, ring bytes, exchange-buffer doubles
     int dsmem_sh = 0;                  // strategy 3: x distributed over the cluster's shared memory, 2^sh rows per CTA (0 = x in global memory)
     bool natural = false;              // natural-order Gauss-Seidel (cf_order = 0 or no cfmark): forward sweeps use this level's
@@ -296,8 +298,8 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(XC_CTAS);
-        cfg.blockDim = dim3(32 * XC_WARPS);
-        cfg.dynamicSmemBytes = 256 + (size_t)3 * lv.xc_cap * 8 + (size_t)lv.xc_ring + 128;
+        cfg.blockDim = dim3(32 * (lv.xc_D * XC_G + 2));
+        cfg.dynamicSmemBytes = XC_HDR + (size_t)3 * lv.xc_cap * 8 + (size_t)lv.xc_ring + 128;
         cfg.stream = h->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
@@ -305,7 +307,7 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         cfg.attrs = at;
         cfg.numAttrs = 1;
         CUDA_CHECK(cudaLaunchKernelEx(&cfg, gs_stream_cluster_kernel, (const unsigned char *)lv.d_stream, (const int *)lv.d_blk_ptr, (const int *)lv.d_wf_row_ptr,
-                                      (const double *)lv.b, lv.x, lv.W, nsweeps, lv.xc_F, lv.xc_S, lv.xc_P, lv.xc_ring, lv.xc_cap, lv.A.v.recip, h->d_dbg));
+                                      (const double *)lv.b, lv.x, lv.W, nsweeps, lv.xc_F, lv.xc_S, lv.xc_P, lv.xc_D, lv.xc_ring, lv.xc_cap, lv.A.v.recip, h->d_dbg));
         ++g_launches;
 #ifdef AMGB200_TIMELINE
         if (h->d_dbg) {
@@ -313,7 +315,7 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
             CUDA_CHECK(cudaStreamSynchronize(h->stream));
             CUDA_CHECK(cudaMemcpy(hd, h->d_dbg, sizeof(hd), cudaMemcpyDeviceToHost));
             const char *nm[11] = {"wait block", "wait GV(g-3)", "products", "group barrier", "prefix fold", "wait WF(g-1)", "late patch", "suffix fold", "quotient", "loop top", "push x"};
-            const int iters = (lv.W * nsweeps + 1) / 2;
+            const int iters = (lv.W * nsweeps + lv.xc_D - 1) / lv.xc_D;
             for (int g2 = 0; g2 < 2; ++g2) {
                 printf("   cluster stream timeline CTA 0 group %d folder (cycles per wavefront, %d wavefronts, F=%d S=%d):", g2, iters, lv.xc_F, lv.xc_S);
                 long long tot = 0;
@@ -330,7 +332,7 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
             CUDA_CHECK(cudaFuncSetAttribute(gs_stream_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
             attr_set = true;
         }
-        const size_t xb = ((size_t)lv.n * 8 + 15) & ~(size_t)15;
+        const size_t xb = ((size_t)lv.n * 8 + 127) & ~(size_t)127;
         const size_t smem = STREAM_HDR + xb + (size_t)lv.stream_ring + 128;
         gs_stream_cta_kernel<<<1, 32 * (lv.stream_D * lv.stream_G + 1), smem, h->stream>>>(lv.d_stream, lv.d_blk_ptr, lv.d_wf_item_ptr, lv.b, lv.x, lv.n, lv.W, nsweeps,
                                                                             lv.stream_G, lv.stream_S, lv.stream_D, lv.stream_ring, lv.A.v.recip, h->d_dbg);
@@ -439,6 +441,14 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         at[0].val.clusterDim.x = CLUSTER_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
+        if (KIND == 0 && lv.A.v.max_row <= 20) {
+            static bool attr_set1 = false;
+            if (!attr_set1) {
+                CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cluster_kernel<KIND, EXACT, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                attr_set1 = true;
+            }
+            CUDA_CHECK(cudaLaunchKernelEx(&cfg, gs_ordered_cluster_kernel<KIND, EXACT, true>, lv.A.v, (const double *)lv.b, lv.x, (const int *)lv.d_wf_item_ptr, lv.W, nsweeps, h->d_dbg));
+        } else
         CUDA_CHECK(cudaLaunchKernelEx(&cfg, gs_ordered_cluster_kernel<KIND, EXACT>, lv.A.v, (const double *)lv.b, lv.x, (const int *)lv.d_wf_item_ptr, lv.W, nsweeps, h->d_dbg));
         ++g_launches;
         if (h->d_dbg) {
@@ -922,6 +932,20 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     }
     lv.d_item_wf = dev_upload(item_wf);
     lv.d_wf_item_ptr = dev_upload(wip);
+    // the dependency-chain floor of one sweep: per wavefront the longest in-order chain that can only start when the
+    // previous wavefront is complete (warp-per-row layouts: the row suffix from its first entry in that wavefront; thread-
+    // per-row SELL slices: the whole padded row), one dependent fp64 subtraction (8.1 cycles measured) per term
+    lv.chain_terms = 0;
+    if (lv.ordered) {
+        for (int w = 0; w < lv.W; ++w) {
+            int longest = 0;
+            for (int it = wip[w]; it < wip[w + 1]; ++it) {
+                if (lay.kind == KIND_CSR) longest = std::max(longest, lay.rptr[it + 1] - lay.rptr[it] - (lay.split.empty() ? 0 : lay.split[it]));
+                else longest = std::max(longest, (int)((lay.slice_ptr[it + 1] - lay.slice_ptr[it]) / 32));
+            }
+            lv.chain_terms += longest;
+        }
+    }
     // 0 parallel passes | 2 one CTA (narrow wavefronts) | 3 one 16-CTA cluster | 1 cooperative grid (fallback)
     if (!lv.ordered) lv.strategy = 0;
     else lv.strategy = ((double)wip[lv.W] / lv.W <= cta_max_avg) ? 2 : 3;
@@ -961,7 +985,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     // streaming single-CTA smoother: warp-per-row EXACT levels whose x vector plus a ring of at least two of the
     // largest wavefront blocks fit in shared memory
     if (lv.ordered && lay.kind == KIND_CSR && h->exact && !getenv("AMGB200_GS_STRATEGY") && (double)wip[lv.W] / lv.W <= stream_max_avg) {
-        const size_t xb = ((size_t)lv.n * 8 + 15) & ~(size_t)15;
+        const size_t xb = ((size_t)lv.n * 8 + 127) & ~(size_t)127;
         const long long ring = (long long)h->max_dyn_smem - STREAM_HDR - (long long)xb - 128;
         if (ring >= 4096) {
             StreamLayout SL;
@@ -970,19 +994,22 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             t_layout += now_s() - tl;
             if ((long long)SL.max_block * 2 <= ring) {
                 lv.strategy = 4;
-                lv.stream_ring = (int)(ring & ~15LL);
+                lv.stream_ring = (int)(ring & ~127LL);
                 // product warps per group (1, 2 or 4) and row slots of the folding warp (the widest wavefront in one
                 // round if possible: unused slots cost nothing)
-                lv.stream_G = lv.max_width >= 3 ? 4 : lv.max_width;
-                if (getenv("AMGB200_STREAM_G")) { const int g = atoi(getenv("AMGB200_STREAM_G")); lv.stream_G = g >= 8 ? 8 : g >= 4 ? 4 : g >= 2 ? 2 : 1; }
+                // measured (128^3, three wavefronts in flight): with narrow wavefronts the folding warp alone keeps up with the
+                // products, and every additional product warp only disturbs the chains of the other wavefronts in flight
+                // (level 5: 3.62 -> 3.39 ms per sweep, level 6: 4.50 -> 4.31 with one warp per group instead of four)
+                lv.stream_G = (double)wip[lv.W] / lv.W <= 6.0 ? 1 : 4;
+                if (getenv("AMGB200_STREAM_G")) { const int g = atoi(getenv("AMGB200_STREAM_G")); lv.stream_G = g >= 4 ? 4 : g >= 2 ? 2 : 1; }
                 lv.stream_S = 1;
-                while (lv.stream_S < 32 && lv.stream_S < lv.max_width) lv.stream_S *= 2;
+                while (lv.stream_S < 16 && lv.stream_S < lv.max_width) lv.stream_S *= 2;      // (16 slots + a rare second round beat 32 slots: fewer distinct shared-memory addresses per chain load)
                 if (getenv("AMGB200_STREAM_S")) { int v = std::max(1, std::min(32, atoi(getenv("AMGB200_STREAM_S")))); lv.stream_S = 1; while (lv.stream_S < v) lv.stream_S *= 2; }
                 // three wavefronts in flight (the late2 lists exist for W >= 4); a ring that cannot hold three of the largest
                 // blocks only serialises the affected wavefronts (every block is released in order)
                 lv.stream_D = lv.W >= 4 ? 3 : 2;
                 if (getenv("AMGB200_STREAM_D")) { const int d = atoi(getenv("AMGB200_STREAM_D")); if (d == 2 || (lv.W >= 4 && d == 3)) lv.stream_D = d; }
-                if (lv.stream_D * lv.stream_G > 16) lv.stream_G = 4;
+                if (lv.stream_D * lv.stream_G > 12) lv.stream_G = 4;
                 lv.d_stream = dev_upload(SL.data);
                 lv.d_blk_ptr = dev_upload(SL.blk_ptr);
                 if (h->opt.verbose >= 2) printf("      streaming CTA smoother: %d groups of %d product warps, %d row slots in the folding warp, ring %d B, wavefront block mean %lld B max %d B, stream %.1f MB\n", lv.stream_D, lv.stream_G, lv.stream_S, lv.stream_ring, SL.mean_block, SL.max_block, SL.data.size() / 1e6);
@@ -993,10 +1020,10 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     if (lv.ordered && h->exact && lv.strategy != 4 && lv.W >= 4 && !getenv("AMGB200_GS_STRATEGY") && !(getenv("AMGB200_NO_XC") && atoi(getenv("AMGB200_NO_XC")))) {
         ClusterStreamLayout SL;
         const double tl = now_s();
-        build_stream_cluster(Amat, S, XC_CTAS, SL, (long long)h->max_dyn_smem - 256 - 128);
+        build_stream_cluster(Amat, S, XC_CTAS, SL, (long long)h->max_dyn_smem - XC_HDR - 128);
         t_layout += now_s() - tl;
         const int cap = (SL.max_width + 1) & ~1;        // every CTA holds the whole wavefront (x3)
-        const long long avail = (long long)h->max_dyn_smem - 256 - 3LL * cap * 8 - 128;
+        const long long avail = (long long)h->max_dyn_smem - XC_HDR - 3LL * cap * 8 - 128;
         if (SL.filled && (long long)SL.max_block * 2 <= avail) {
             lv.strategy = 5;
             lv.xc_cap = cap;
@@ -1006,6 +1033,8 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             while (lv.xc_S < 32 && lv.xc_S < SL.max_local) lv.xc_S *= 2;
             lv.xc_F = std::max(1, std::min(XC_G, (int)((1.5 * mean_local + 31) / 32)));
             lv.xc_P = (double)Amat.num_nnzs / std::max(1, Amat.num_rows) <= 96.0 ? 8 : 32;      // lanes per row in the product pass
+            lv.xc_D = 3;
+            if (getenv("AMGB200_XC_D")) lv.xc_D = atoi(getenv("AMGB200_XC_D")) >= 3 ? 3 : 2;
             if (getenv("AMGB200_XC_P")) lv.xc_P = atoi(getenv("AMGB200_XC_P")) >= 32 ? 32 : 8;
             if (getenv("AMGB200_XC_F")) lv.xc_F = std::max(1, std::min(XC_G, atoi(getenv("AMGB200_XC_F"))));
             if (getenv("AMGB200_XC_S")) { int v = std::max(1, std::min(32, atoi(getenv("AMGB200_XC_S")))); lv.xc_S = 1; while (lv.xc_S < v) lv.xc_S *= 2; }
@@ -1179,6 +1208,10 @@ long long amgb200_device_bytes(const amgb200_hier *h) {
         tot += (long long)lv.n * (3 * 8 + 4);
     }
     return tot;
+}
+long long amgb200_level_chain_terms(const amgb200_hier *h, int level) {
+    check_level(h, level);
+    return h->L[level].chain_terms;
 }
 const char *amgb200_level_kernel(const amgb200_hier *h, int level) {
     check_level(h, level);

@@ -819,8 +819,8 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
 // ------------------------------------------------------------------------------------------
 constexpr int STREAM_NS = 8;                  // wavefront blocks in flight (ring descriptors)
 constexpr int STREAM_HDR = 384;               // bytes of barriers / descriptors in front of x
-constexpr int STREAM_MAX_WARPS = 17;          // D groups of G warps + the loader (D*G <= 16)
-constexpr int STREAM_MAX_G = 8;               // product warps per group (1, 2, 4 or 8)
+constexpr int STREAM_MAX_WARPS = 13;          // D groups of G warps + the loader (D*G <= 12: up to 157 registers per thread)
+constexpr int STREAM_MAX_G = 4;               // product warps per group (1, 2 or 4)
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
@@ -900,7 +900,7 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
     const unsigned zeros_a = smem_u32(smem_raw + 128);
     const unsigned done0 = smem_u32(smem_raw + 256);
     double *x = reinterpret_cast<double *>(smem_raw + STREAM_HDR);
-    unsigned char *ring = smem_raw + STREAM_HDR + (((size_t)n * 8 + 15) & ~(size_t)15);
+    unsigned char *ring = smem_raw + STREAM_HDR + (((size_t)n * 8 + 127) & ~(size_t)127);       // (128-byte aligned: see analysis.cpp, bank alignment)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int totalw = W * nsweeps;
     const unsigned x_a = smem_u32(x);
@@ -909,6 +909,8 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
     long long tl_prev = clock64();
 #if AMGB200_TIMELINE == 2          // only two clock reads per wavefront: [8] = done(g-1) observed -> done(g) announced, [3] = everything else
 #define SL_MARK(i) { if ((i) == 3 || (i) == 8) { const long long c_ = clock64(); tl[i] += c_ - tl_prev; tl_prev = c_; } }
+#elif AMGB200_TIMELINE == 3        // post path in three pieces: [4] late patch, [6] suffix chain + quotient + store, [8] announce; [3] = everything else
+#define SL_MARK(i) { if ((i) == 3 || (i) == 4 || (i) == 6 || (i) == 8) { const long long c_ = clock64(); tl[i] += c_ - tl_prev; tl_prev = c_; } }
 #else
 #define SL_MARK(i) { const long long c_ = clock64(); tl[i] += c_ - tl_prev; tl_prev = c_; }
 #endif
@@ -1066,9 +1068,12 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
                     __syncwarp();
                     SL_MARK(4)
                     const double t = chain_fold_slots(c_t, c_suf, c_cnt, c_maxc, zeros_a);
-#if defined(AMGB200_TIMELINE) && AMGB200_TIMELINE != 2
+#if defined(AMGB200_TIMELINE) && AMGB200_TIMELINE == 1
                     if (t == 1.2345e300) tl[11] = 1;
                     SL_MARK(5)
+#endif
+#if defined(AMGB200_TIMELINE)
+                    tl[5] += c_maxc;
 #endif
 #if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 11
                     if (c_mine && leader && fabs(c_d) > GS_TINY) sts_f64(x_a + 8u * (unsigned)c_row, __dmul_rn(t, c_d));
@@ -1119,7 +1124,7 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
             const int s = g & (STREAM_NS - 1);
             const int o0 = blk_ptr[wl], o1 = blk_ptr[wl + 1];
             const int i0a = wf_row_ptr[wl] & ~1, bcnt = (wf_row_ptr[wl + 1] - i0a + 1) & ~1;
-            const int bytes = (o1 - o0) * 16, need = bytes + bcnt * 8;
+            const int bytes = (o1 - o0) * 16, need = (bytes + bcnt * 8 + 127) & ~127;     // blocks stay 128-byte aligned in the ring
             for (;;) {
                 if (inflight == 0) { head = tail = 0; break; }
                 if (inflight < STREAM_NS) {
@@ -1136,7 +1141,7 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
             }
             stage_off[s] = head;
             const unsigned full = smem_u32(bars + s);
-            mbar_arrive_expect_tx(full, (unsigned)need);
+            mbar_arrive_expect_tx(full, (unsigned)(bytes + bcnt * 8));
             bulk_g2s(smem_u32(ring + head), stream + (size_t)o0 * 16, (unsigned)bytes, full);
             bulk_g2s(smem_u32(ring + head + bytes), b + i0a, (unsigned)(bcnt * 8), full);
             head += need; ++inflight;
@@ -1169,7 +1174,10 @@ __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 constexpr int XC_CTAS = CLUSTER_CTAS;
 constexpr int XC_G = 4;                        // product warps per group
-constexpr int XC_WARPS = 2 * XC_G + 2;         // + loader + publisher
+constexpr int XC_MAX_D = 3;                    // consumer groups (wavefronts in flight)
+constexpr int XC_WARPS = XC_MAX_D * XC_G + 2;  // + loader + publisher
+constexpr int XC_NS = 8;                       // ring descriptors
+constexpr int XC_HDR = 384;                    // barriers, descriptors and the block of zeros in front of the exchange buffers
 __device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
     unsigned r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
@@ -1200,14 +1208,14 @@ __device__ __forceinline__ double xc_late_x(int g, int src, int col, unsigned xb
 
 __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
     const unsigned char *__restrict__ stream, const int *__restrict__ blk_ptr, const int *__restrict__ wf_row_ptr,
-    const double *__restrict__ b, double *x, int W, int nsweeps, int F, int S, int P, int ring_bytes, int xb_cap, int recip, long long *dbg) {
+    const double *__restrict__ b, double *x, int W, int nsweeps, int F, int S, int P, int D, int ring_bytes, int xb_cap, int recip, long long *dbg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);      // full[0..4) empty[4..8) WF[8..11) GV[11..15)
-    volatile int *stage_off = reinterpret_cast<volatile int *>(smem_raw + 160);
-    const unsigned zeros_a = smem_u32(smem_raw + 192);
-    double *xb = reinterpret_cast<double *>(smem_raw + 256);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);      // full[0..8) empty[8..16) WF[16..19) GV[19..23)
+    volatile int *stage_off = reinterpret_cast<volatile int *>(smem_raw + 192);
+    const unsigned zeros_a = smem_u32(smem_raw + 256);
+    double *xb = reinterpret_cast<double *>(smem_raw + XC_HDR);
     const unsigned xb_a = smem_u32(xb);
-    unsigned char *ring = smem_raw + 256 + (size_t)3 * xb_cap * 8;
+    unsigned char *ring = smem_raw + XC_HDR + (size_t)3 * xb_cap * 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int totalw = W * nsweeps;
     const int C = XC_CTAS, G = XC_G;
@@ -1219,37 +1227,42 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
 #else
 #define XC_MARK(i)
 #endif
-    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + 4), wf0 = smem_u32(bars + 8), gv0 = smem_u32(bars + 11);
+    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + XC_NS), wf0 = smem_u32(bars + 2 * XC_NS), gv0 = smem_u32(bars + 2 * XC_NS + 3);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 4; ++s) { mbar_init(full0 + 8u * s, 1); mbar_init(empty0 + 8u * s, 1); mbar_init(gv0 + 8u * s, C); }
+        for (int s = 0; s < XC_NS; ++s) { mbar_init(full0 + 8u * s, 1); mbar_init(empty0 + 8u * s, 1); }
+        for (int s = 0; s < 4; ++s) mbar_init(gv0 + 8u * s, C);
         for (int s = 0; s < 3; ++s) mbar_init(wf0 + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 8) reinterpret_cast<double *>(smem_raw + 192)[threadIdx.x] = 0.0;
+    if (threadIdx.x < 8) reinterpret_cast<double *>(smem_raw + 256)[threadIdx.x] = 0.0;
     __syncthreads();
     cluster_arrive(); cluster_wait();            // every CTA's barriers exist before anybody signals them remotely
-    if (warp < 2 * G) {
+    if (warp < D * G) {
+        // D groups of G warps; group d walks the wavefronts g = d, d+D, ...  The product pass of wavefront g needs global x
+        // through wavefront g-3 only (GV), so up to three wavefronts can be in flight.
         const int grp = warp / G, r = warp - grp * G;
-        const int f = (r - grp + G) % G;         // folding warps of a group: f < F (the two groups' folders on different sub-partitions)
+        const int f = (r - grp % G + G) % G;     // folding warps of a group: f < F (the groups' first folders on different sub-partitions)
         const bool folder = f < F;
         const int sub = 32 / S, slot = lane / sub;
         const int lis = lane - slot * sub;       // lane in slot
         const int FS = F * S;
         const int RP = 32 / P, lr = lane % P, unit = r * RP + lane / P;      // product pass: P lanes per row, G*RP rows in flight per CTA
-        for (int g = grp; g < totalw; g += 2) {
-            const int s = g & 3;
+        for (int g = grp; g < totalw; g += D) {
+            const int s = g & (XC_NS - 1);
             XC_MARK(9)
-            mbar_wait(full0 + 8u * s, (g >> 2) & 1);
+            mbar_wait(full0 + 8u * s, (g / XC_NS) & 1);
             XC_MARK(0)
             unsigned char *blk = ring + stage_off[s];
             const int4 hd = *reinterpret_cast<const int4 *>(blk);                   // rows of this CTA, first row of the wavefront, its width, block bytes
-            const int *rec_off = reinterpret_cast<const int *>(blk + 16);
-            // this CTA expects the whole wavefront g (width x 8 bytes) in its exchange buffer g % 3: one arrival per phase
-            if (f == 0 && lane == 0) mbar_arrive_expect_tx(wf0 + 8u * (unsigned)(g % 3), (unsigned)hd.z * 8u);
+            const int2 hf = *reinterpret_cast<const int2 *>(blk + 16);              // late entries of the block, byte offset of their list
+            const int *rec_off = reinterpret_cast<const int *>(blk + 32);
             // right-hand side of my first-round row: requested now, used after the product pass
             double b0 = 0.0;
             if (folder && slot * F + f < hd.x) b0 = __ldg(b + hd.y + (int)cta + (slot * F + f) * C);
-            if (g >= 3) mbar_wait_cluster(gv0 + 8u * ((g - 3) & 3), ((g - 3) >> 2) & 1);      // global x visible through wavefront g-3
+            // global x visible through wavefront g-3 (this also means: the previous use of WF[g % 3], by wavefront g-3, is over)
+            if (g >= 3) mbar_wait_cluster(gv0 + 8u * ((g - 3) & 3), ((g - 3) >> 2) & 1);
+            // this CTA expects the whole wavefront g (width x 8 bytes) in its exchange buffer g % 3: one arrival per phase
+            if (f == 0 && lane == 0) mbar_arrive_expect_tx(wf0 + 8u * (unsigned)(g % 3), (unsigned)hd.z * 8u);
             XC_MARK(1)
             // ---- before the wavefront barrier: products of every entry (late ones are redone below).  P lanes per row, all
             // row groups of the warp walk in lockstep (a diverged warp would serialise the L2 round trips of its row groups)
@@ -1284,13 +1297,13 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
             XC_MARK(2)
             asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");      // all products of my CTA's rows are in place
             XC_MARK(3)
+            // ... and the prefix chains; the state of the first round stays in registers (c_*)
+            bool c_mine = false;
+            unsigned c_suf = 0;
+            int c_cnt = 0, c_maxc = 0, c_row = 0, c_li = 0;
+            double c_t = 0.0, c_d = 0.0, c_y = 0.0;
+            bool c_dsafe = false;
             if (folder) {
-                // ... and the prefix chains; the state of the first round stays in registers (c_*)
-                bool c_mine = false;
-                unsigned c_suf = 0, c_late = 0, c_val = 0;
-                int c_cnt = 0, c_maxc = 0, c_row = 0, c_nlate = 0, c_li = 0;
-                double c_t = 0.0, c_d = 0.0, c_y = 0.0;
-                bool c_dsafe = false;
                 for (int base = 0; base < hd.x; base += FS) {
                     const int ri = base + slot * F + f;
                     const bool mine = ri < hd.x;
@@ -1303,52 +1316,49 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
                     if (base == 0) {
                         c_mine = mine; c_row = rh.x; c_t = t; c_d = reinterpret_cast<const double *>(rec)[2]; c_li = ri;
                         c_y = __ddiv_rn(1.0, c_d); c_dsafe = gs_quotient_dsafe(c_d);
-                        c_val = smem_u32(rec + 32);
-                        c_suf = c_val + 8u * (unsigned)rh.y;
+                        c_suf = smem_u32(rec + 32) + 8u * (unsigned)rh.y;
                         c_cnt = mine ? rh.z - rh.y : 0;
                         c_maxc = __reduce_max_sync(FULL, c_cnt);
-                        c_nlate = mine ? rh.w : 0;
-                        c_late = c_val + 12u * (unsigned)rh.z;
                     } else if (mine && lis == 0) reinterpret_cast<double *>(rec)[3] = t;
                 }
                 __syncwarp();
-                XC_MARK(4)
-                if (g > 1) mbar_wait_cluster(wf0 + 8u * ((g - 2) % 3), ((g - 2) / 3) & 1);
-                if (g > 0) mbar_wait_cluster(wf0 + 8u * ((g - 1) % 3), ((g - 1) / 3) & 1);
-                XC_MARK(5)
-                // ---- after the barrier: late products (x from the exchange buffers), suffix chains, x_k pushed to every CTA
+            }
+            XC_MARK(4)
+            if (g > 1) mbar_wait_cluster(wf0 + 8u * ((g - 2) % 3), ((g - 2) / 3) & 1);
+            if (g > 0) mbar_wait_cluster(wf0 + 8u * ((g - 1) % 3), ((g - 1) / 3) & 1);
+            XC_MARK(5)
+            // ---- after the barrier: ALL late products of the block (x from the exchange buffers), shared evenly by the lanes of the
+            // group; then the suffix chains, and x_k pushed to every CTA
+            {
+                const unsigned flat_a = smem_u32(blk + hf.y), blk_a = smem_u32(blk);
+                for (int i0 = r * 32 + lane; i0 < hf.x; i0 += 2 * G * 32) {               // two entries per lane at a time
+                    const int i1 = i0 + G * 32;
+                    const unsigned a0 = flat_a + 24u * (unsigned)i0, a1 = flat_a + 24u * (unsigned)(i1 < hf.x ? i1 : i0);
+                    const double v0 = lds_f64(a0), v1 = lds_f64(a1);
+                    const int d0 = lds_s32(a0 + 8u), d1 = lds_s32(a1 + 8u);
+                    const double x0 = xc_late_x(g, lds_s32(a0 + 16u), lds_s32(a0 + 12u), xb_a, xb_cap, x);
+                    const double x1 = xc_late_x(g, lds_s32(a1 + 16u), lds_s32(a1 + 12u), xb_a, xb_cap, x);
+                    sts_f64(blk_a + (unsigned)d0, __dmul_rn(v0, x0));
+                    if (i1 < hf.x) sts_f64(blk_a + (unsigned)d1, __dmul_rn(v1, x1));
+                }
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");      // all late products are in place
+            XC_MARK(6)
+            if (folder) {
                 const unsigned xb_g = xb_a + 8u * (unsigned)(g % 3) * (unsigned)xb_cap, wf_g = wf0 + 8u * (unsigned)(g % 3);
                 for (int base = 0; base < hd.x; base += FS) {
-                    bool mine; unsigned val_a, suf_a, late_a; int cnt, maxc, row, nlate, li; double t, dg;
-                    if (base == 0) { mine = c_mine; val_a = c_val; suf_a = c_suf; late_a = c_late; cnt = c_cnt; maxc = c_maxc; row = c_row; nlate = c_nlate; li = c_li; t = c_t; dg = c_d; }
+                    bool mine; unsigned suf_a; int cnt, maxc, row, li; double t, dg;
+                    if (base == 0) { mine = c_mine; suf_a = c_suf; cnt = c_cnt; maxc = c_maxc; row = c_row; li = c_li; t = c_t; dg = c_d; }
                     else {
                         li = base + slot * F + f;
                         mine = li < hd.x;
                         unsigned char *rec = blk + (mine ? rec_off[li] : rec_off[0]);
                         const int4 rh = *reinterpret_cast<const int4 *>(rec);
-                        val_a = smem_u32(rec + 32); suf_a = val_a + 8u * (unsigned)rh.y; late_a = val_a + 12u * (unsigned)rh.z;
-                        cnt = mine ? rh.z - rh.y : 0; maxc = __reduce_max_sync(FULL, cnt); row = rh.x; nlate = mine ? rh.w : 0;
+                        suf_a = smem_u32(rec + 32) + 8u * (unsigned)rh.y;
+                        cnt = mine ? rh.z - rh.y : 0; maxc = __reduce_max_sync(FULL, cnt); row = rh.x;
                         const double2 dt = *reinterpret_cast<const double2 *>(rec + 16);
                         dg = dt.x; t = dt.y;
                     }
-                    for (int i0 = lis; i0 < nlate; i0 += 4 * sub) {                  // four late entries per lane at a time
-                        double lv[4], xv[4];
-                        int lp[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int i = i0 + u * sub;
-                            lp[u] = -1;
-                            if (i < nlate) {
-                                const unsigned a = late_a + 24u * (unsigned)i;
-                                lv[u] = lds_f64(a); lp[u] = lds_s32(a + 8u);
-                                xv[u] = xc_late_x(g, lds_s32(a + 16u), lds_s32(a + 12u), xb_a, xb_cap, x);
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) if (lp[u] >= 0) sts_f64(val_a + 8u * (unsigned)lp[u], __dmul_rn(lv[u], xv[u]));
-                    }
-                    __syncwarp();
-                    XC_MARK(6)
                     t = chain_fold_slots(t, suf_a, cnt, maxc, zeros_a);
 #ifdef AMGB200_TIMELINE
                     if (t == 1.2345e300) tl[11] = 1;
@@ -1359,12 +1369,14 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
                         if (fabs(dg) > GS_TINY) xn = base == 0 ? gs_quotient_pre(t, dg, c_y, c_dsafe, recip) : gs_quotient(t, dg, recip);
                         else asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(xn) : "l"(x + row) : "memory");     // row without a diagonal: x_k unchanged (never speculated)
                     }
-                    xn = __shfl_sync(FULL, xn, slot * sub);
                     XC_MARK(8)
-                    // the sub lanes of the slot share the 16 destinations
-                    if (mine) {
-                        const unsigned idx = (unsigned)(li * C) + cta;               // index of the row within its wavefront
-                        for (int c2 = lis; c2 < C; c2 += sub) st_async_f64(mapa_u32(xb_g + 8u * idx, (unsigned)c2), xn, mapa_u32(wf_g, (unsigned)c2));
+                    // the 16 destinations of every finished row, spread over all lanes of the warp: item = (slot, destination)
+                    const int nslots = min(S, (hd.x - base - f + F - 1) / F);            // slots of this round that hold a row
+                    for (int it0 = 0; it0 < nslots * C; it0 += 32) {
+                        const int it = it0 + lane, sl = min(it / C, S - 1), c2 = it % C;
+                        const double xv = __shfl_sync(FULL, xn, sl * sub);
+                        const unsigned idx = (unsigned)((base + sl * F + f) * C) + cta;   // index of the row within its wavefront
+                        if (it < nslots * C) st_async_f64(mapa_u32(xb_g + 8u * idx, (unsigned)c2), xv, mapa_u32(wf_g, (unsigned)c2));
                     }
                 }
                 XC_MARK(10)
@@ -1375,27 +1387,27 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
             if (f == 0 && lane == 0) mbar_arrive(empty0 + 8u * s);
         }
 #ifdef AMGB200_TIMELINE
-        if (dbg && lane == 0 && f == 0 && cta == 0) for (int i = 0; i < 12; ++i) dbg[grp * 16 + i] = tl[i];
+        if (dbg && lane == 0 && f == 0 && cta == 0 && grp < 2) for (int i = 0; i < 12; ++i) dbg[grp * 16 + i] = tl[i];
 #endif
-    } else if (warp == 2 * G) {
+    } else if (warp == D * G) {
         if (lane == 0) {
             // ---- loader (see gs_stream_cta_kernel); block of (wavefront wl, this CTA)
             int head = 0, tail = 0, inflight = 0, g_old = 0, wl = 0;
             for (int g = 0; g < totalw; ++g) {
-                const int s = g & 3;
+                const int s = g & (XC_NS - 1);
                 const int o0 = blk_ptr[wl * C + (int)cta], o1 = blk_ptr[wl * C + (int)cta + 1];
                 const int need = (o1 - o0) * 16;
                 for (;;) {
                     if (inflight == 0) { head = tail = 0; break; }
-                    if (inflight < 4) {
+                    if (inflight < XC_NS) {
                         if (head >= tail) {
                             if (head + need <= ring_bytes) break;
                             if (need < tail) { head = 0; break; }
                         } else if (head + need < tail) break;
                     }
-                    mbar_wait_sleep(empty0 + 8u * (g_old & 3), (g_old >> 2) & 1);
+                    mbar_wait_sleep(empty0 + 8u * (g_old & (XC_NS - 1)), (g_old / XC_NS) & 1);
                     ++g_old; --inflight;
-                    tail = inflight ? stage_off[g_old & 3] : head;
+                    tail = inflight ? stage_off[g_old & (XC_NS - 1)] : head;
                 }
                 stage_off[s] = head;
                 mbar_arrive_expect_tx(full0 + 8u * s, (unsigned)need);
@@ -1404,7 +1416,7 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
                 if (++wl == W) wl = 0;
             }
         }
-    } else {
+    } else if (warp == D * G + 1) {
         // ---- publisher: my share of each complete wavefront, exchange buffer -> global x, GPU-scope fence, GV(g) on every CTA
         int wl = 0;
         for (int g = 0; g < totalw; ++g) {
@@ -1430,7 +1442,9 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
 // *waits*.  x lives in global memory and is read at L2 (ld.cg) after the acquire.
 
 constexpr int CLUSTER_WARPS_SELL = 8, CLUSTER_WARPS_CSR = 16;
-template <int KIND, bool EXACT>
+// ONE (SELL only): every row fits in one register chunk (max row length <= 20): no next-chunk registers, which leaves room
+// for a second register-resident item -- my item of the NEXT wavefront, requested before this wavefront's rows are finished
+template <int KIND, bool EXACT, bool ONE = false>
 __global__ void __launch_bounds__(KIND == 0 ? 32 * CLUSTER_WARPS_SELL : 32 * CLUSTER_WARPS_CSR) gs_ordered_cluster_kernel(
     DMat A, const double *__restrict__ b, double *x, const int *__restrict__ wf_item_ptr, int W, int nsweeps, long long *dbg) {
     __shared__ double sprod[KIND == 1 ? CLUSTER_WARPS_CSR * STAGE : 1];
@@ -1446,8 +1460,11 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CLUSTER_WARPS_SELL : 32 * CLU
     const int totalw = W * nsweeps;
     double *sp = sprod + (KIND == 1 ? warp * STAGE : 0);
     auto finish = [&](Item &w) {
-        if constexpr (KIND == 0) gs_finish_sell<true>(w, x); else gs_finish_csr<true, EXACT>(A, w, x, lane, sp);
+        if constexpr (KIND == 0 && ONE) gs_finish_sell_one<true>(w, x);
+        else if constexpr (KIND == 0) gs_finish_sell<true>(w, x);
+        else gs_finish_csr<true, EXACT>(A, w, x, lane, sp);
     };
+    constexpr bool DB = KIND == 0 && ONE;
     // Look-ahead pipeline over the (static) schedule, one stage per wavefront step, so that no dependent
     // load chain (wavefront table -> item descriptor -> matrix entries) is exposed between two barriers:
     //   (a0,a1) item range of wavefront g     cur : entries of my item in g     (loaded during step g-1)
@@ -1457,24 +1474,31 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CLUSTER_WARPS_SELL : 32 * CLU
     int a0 = wf_item_ptr[0], a1 = wf_item_ptr[1];
     int b0 = wf_item_ptr[1 % W], b1 = wf_item_ptr[1 % W + 1];
     int c0 = wf_item_ptr[wl2], c1 = wf_item_ptr[wl2 + 1];
-    Item cur;
+    Item cur, nxt;
     Desc dn = {};
-    bool have = a0 + gw < a1, have_n = b0 + gw < b1;
+    bool have = a0 + gw < a1, have_n = totalw > 1 && b0 + gw < b1;
     if (have) cur.prologue(A, a0 + gw, lane, b);
     if (have_n) dn = Item::load_desc(A, b0 + gw);
 #ifdef AMGB200_TIMING
     long long tf = 0, tf2 = 0, ta = 0, tpre = 0, tw = 0, nit = 0;
 #endif
-    for (int g = 0; g < totalw; ++g) {
+    // one wavefront step; `c` holds my item of wavefront g, `n` receives my item of wavefront g+1 (the loop below alternates
+    // two register-resident items instead of copying one into the other)
+    auto step = [&](Item &c, Item &n, int g) {
 #ifdef AMGB200_TIMING
         long long k0 = clock64(), k1 = k0;
 #endif
+        // the matrix entries of my item in wavefront g+1 are requested BEFORE this wavefront's rows are finished (their
+        // descriptor arrived during step g-1): they travel during the x gathers of finish() and the release fence of the
+        // barrier.  Requested after the arrive they used to sit on the critical path (measured 1 825 cycles per wavefront
+        // on level 1 of 128^3: memory instructions behind barrier.cluster.arrive.release wait for its fence).
+        if constexpr (DB) { if (have_n) n.load_entries(A, dn, lane, b); }
         if (have) {
-            finish(cur);
+            finish(c);
 #ifdef AMGB200_TIMING
             ++nit; k1 = clock64();
 #endif
-            for (int it = a0 + gw + TW; it < a1; it += TW) { cur.prologue(A, it, lane, b); finish(cur); }   // wider than the cluster
+            for (int it = a0 + gw + TW; it < a1; it += TW) { c.prologue(A, it, lane, b); finish(c); }   // wider than the cluster
         }
 #ifdef AMGB200_TIMING
         long long k2 = clock64(); tf += k1 - k0; tf2 += k2 - k1;
@@ -1484,9 +1508,9 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CLUSTER_WARPS_SELL : 32 * CLU
 #ifdef AMGB200_TIMING
             long long k3 = clock64(); ta += k3 - k2;
 #endif
+            if constexpr (!DB) { if (have_n) n.load_entries(A, dn, lane, b); }   // descriptor arrived during the previous step
             a0 = b0; a1 = b1; have = have_n;
-            if (have) cur.load_entries(A, dn, lane, b);                 // descriptor arrived during the previous step
-            b0 = c0; b1 = c1; have_n = b0 + gw < b1;
+            b0 = c0; b1 = c1; have_n = g + 2 < totalw && b0 + gw < b1;
             if (have_n) dn = Item::load_desc(A, b0 + gw);
             if (++wl2 == W) wl2 = 0;
             c0 = wf_item_ptr[wl2]; c1 = wf_item_ptr[wl2 + 1];
@@ -1498,6 +1522,14 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CLUSTER_WARPS_SELL : 32 * CLU
             tw += clock64() - k4;
 #endif
         }
+    };
+    if constexpr (DB) {
+        for (int g = 0; g < totalw; g += 2) {
+            step(cur, nxt, g);
+            if (g + 1 < totalw) step(nxt, cur, g + 1);
+        }
+    } else {
+        for (int g = 0; g < totalw; ++g) step(cur, cur, g);        // one item: its entries are requested after the arrive
     }
 #ifdef AMGB200_TIMING
     if (dbg && lane == 0 && (gw < 4 || gw == TW - 1)) {

@@ -254,6 +254,9 @@ class DeviceHierarchy:
     def device_bytes(self):
         return self._lib.amgb200_device_bytes(self.h)
 
+    def chain_terms(self, l):
+        return self._lib.amgb200_level_chain_terms(self.h, l)
+
     def gs_kernel(self, l):
         return self._lib.amgb200_level_kernel(self.h, l).decode()
 

@@ -199,6 +199,11 @@ void amgb200_upload_seconds(const amgb200_hier *h, double s[2]);
 long long amgb200_device_bytes(const amgb200_hier *h);
 /* name of the Gauss-Seidel kernel chosen for that level */
 const char *amgb200_level_kernel(const amgb200_hier *h, int level);
+/* ordered (row-order Gauss-Seidel) levels: sum over the dependency wavefronts of one sweep of the longest in-order chain that can
+ * only start once the previous wavefront is complete, in terms (one dependent fp64 subtraction each): the latency floor of a
+ * sweep under the reference's rounding order (Solve/SSS_smooth.c:22-29) is this many terms x the fp64 add latency; 0 for
+ * levels whose passes are one wavefront */
+long long amgb200_level_chain_terms(const amgb200_hier *h, int level);
 /* `warmup` untimed + `steps` timed solves from d_x0 (device arrays, natural numbering), timed with
  * CUDA events on the library's stream; *ms_total = milliseconds for the `steps` solves */
 void amgb200_bench_solve(amgb200_hier *h, const double *d_x0, const double *d_b, double *d_x, int warmup, int steps,
