@@ -119,7 +119,8 @@ void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos
             L.split.resize((size_t)n);
             L.late.assign(((size_t)L.nnz + 31) / 32 + 1, 0u);
             L.late2.assign(W >= 4 ? ((size_t)L.nnz + 31) / 32 + 1 : 0, 0u);
-            for (int k = 0; k < n; ++k) {              // (bit writes of neighbouring rows share words: keep this loop serial)
+#pragma omp parallel for schedule(static)
+            for (int k = 0; k < n; ++k) {              // (bit writes of neighbouring rows share words: atomic OR)
                 const int prev = wf_of[k] == 0 ? W - 1 : wf_of[k] - 1;
                 const int prev2 = W >= 4 ? (wf_of[k] + W - 2) % W : -1;
                 int sp = L.rptr[k + 1] - L.rptr[k];
@@ -128,8 +129,8 @@ void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos
                     if (c == k || c >= n) continue;
                     if (wf_of[c] == prev) {
                         if (q - L.rptr[k] < sp) sp = q - L.rptr[k];
-                        L.late[(size_t)q >> 5] |= 1u << (q & 31);
-                    } else if (wf_of[c] == prev2) L.late2[(size_t)q >> 5] |= 1u << (q & 31);
+                        __atomic_fetch_or(&L.late[(size_t)q >> 5], 1u << (q & 31), __ATOMIC_RELAXED);
+                    } else if (wf_of[c] == prev2) __atomic_fetch_or(&L.late2[(size_t)q >> 5], 1u << (q & 31), __ATOMIC_RELAXED);
                 }
                 L.split[k] = sp;
             }
@@ -138,6 +139,47 @@ void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos
     }
 
     // SELL-32
+    build_sell_structure(M, row_order, breaks, L);
+    const int ns = (int)L.slice_row.size() - 1;
+    const size_t total = (size_t)L.slice_ptr[ns];
+    L.col.resize(total);          // every slot is written below (entries or padding): no separate fill pass
+    L.val.resize(total);
+#pragma omp parallel for schedule(static)
+    for (int s = 0; s < ns; ++s) {
+        const long long base = L.slice_ptr[s];
+        const int nr = L.slice_row[s + 1] - L.slice_row[s];
+        const int width = (int)((L.slice_ptr[s + 1] - base) / 32);
+        for (int lane = 0; lane < 32; ++lane) {
+            long long w = base + lane;
+            int filled = 0;
+            if (lane < nr) {
+                const int i = nat(L.slice_row[s] + lane);
+                for (int q = M.row_ptr[i]; q < M.row_ptr[i + 1]; ++q, w += 32, ++filled) {
+                    const int j = M.col_idx[q];
+                    L.col[(size_t)w] = col_pos ? col_pos[j] : j;
+                    L.val[(size_t)w] = M.val[q];
+                }
+            }
+            for (; filled < width; ++filled, w += 32) { L.col[(size_t)w] = -1; L.val[(size_t)w] = 0.0; }
+        }
+    }
+}
+
+// The O(rows) part of a SELL-32 layout: slices (never straddling a `breaks` boundary), their widths and offsets.  col/val stay
+// empty: hier.cu fills them on the device from the raw CSR arrays (sell_fill_kernel), the host only when asked (build_layout).
+void build_sell_structure(const amgb200_mat &M, const int *row_order, const std::vector<int> *breaks, DevLayout &L) {
+    L.~DevLayout();
+    new (&L) DevLayout();
+    L.kind = KIND_SELL;
+    const int n = M.num_rows;
+    L.nrows = n;
+    L.ncols = M.num_cols;
+    L.nnz = M.row_ptr[n];
+    auto nat = [&](int k) { return row_order ? row_order[k] : k; };
+    int maxlen = 0;
+#pragma omp parallel for reduction(max : maxlen) schedule(static)
+    for (int i = 0; i < n; ++i) maxlen = std::max(maxlen, M.row_ptr[i + 1] - M.row_ptr[i]);
+    L.max_row = maxlen;
     std::vector<int> seg;
     if (breaks) seg = *breaks; else seg = {0, n};
     L.slice_row.clear();
@@ -158,27 +200,6 @@ void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos
         width[s] = w;
     }
     for (int s = 0; s < ns; ++s) L.slice_ptr[s + 1] = L.slice_ptr[s] + 32LL * width[s];
-    const size_t total = (size_t)L.slice_ptr[ns];
-    L.col.resize(total);          // every slot is written below (entries or padding): no separate fill pass
-    L.val.resize(total);
-#pragma omp parallel for schedule(static)
-    for (int s = 0; s < ns; ++s) {
-        const long long base = L.slice_ptr[s];
-        const int nr = L.slice_row[s + 1] - L.slice_row[s];
-        for (int lane = 0; lane < 32; ++lane) {
-            long long w = base + lane;
-            int filled = 0;
-            if (lane < nr) {
-                const int i = nat(L.slice_row[s] + lane);
-                for (int q = M.row_ptr[i]; q < M.row_ptr[i + 1]; ++q, w += 32, ++filled) {
-                    const int j = M.col_idx[q];
-                    L.col[(size_t)w] = col_pos ? col_pos[j] : j;
-                    L.val[(size_t)w] = M.val[q];
-                }
-            }
-            for (; filled < width[s]; ++filled, w += 32) { L.col[(size_t)w] = -1; L.val[(size_t)w] = 0.0; }
-        }
-    }
 }
 
 void build_stream(const DevLayout &L, StreamLayout &S) {
@@ -275,6 +296,10 @@ void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, Cluste
     // cyclic distance from the wavefront of column c back to wavefront w (1 = the wavefront just before)
     auto dist = [&](int w, int c) { const int d = w - wf_of[c]; return d > 0 ? d : d + W; };
     SL.C = C;
+    SL.max_width = 0;
+    for (int w = 0; w < W; ++w) SL.max_width = std::max(SL.max_width, wrp[w + 1] - wrp[w]);
+    // the three exchange buffers alone (every CTA holds the whole of the last three wavefronts) must leave room for a ring
+    if (smem_budget >= 0 && 24LL * ((SL.max_width + 1) & ~1) + 8192 > smem_budget) { SL.filled = false; return; }
     std::vector<int> rec_bytes((size_t)n), split((size_t)n), nlate((size_t)n);
 #pragma omp parallel for schedule(static)
     for (int k = 0; k < n; ++k) {

@@ -125,6 +125,9 @@ void identity_schedule(int n, Schedule &S);
 void build_layout(const amgb200_mat &M, const int *row_order, const int *col_pos, int kind,
                   const std::vector<int> *breaks, DevLayout &L);
 
+// structure only (slices, widths, offsets, wavefront item table) of the SELL-32 layout; col/val are left empty
+void build_sell_structure(const amgb200_mat &M, const int *row_order, const std::vector<int> *breaks, DevLayout &L);
+
 int choose_kind(const amgb200_mat &M, double sell_max_mean);
 
 }  // namespace amgb200

@@ -151,6 +151,31 @@ struct DevMatOwner {
         v.val = dev_upload(L.val);
         nnz = L.nnz; padded = (long long)L.col.size(); max_row = L.max_row; valid = true;
     }
+    // SELL layout filled on the device: L carries the slice structure only (build_sell_structure); the raw CSR arrays of M are
+    // copied as they are and permuted / padded by sell_fill_kernel.  The temporaries are appended to `temps` and must stay
+    // alive until the stream has been synchronised.
+    void upload_sell(const DevLayout &L, const amgb200_mat &M, const int *d_order, const int *d_colpos, cudaStream_t stream, std::vector<void *> &temps) {
+        const double t0 = now_s();
+        v.kind = KIND_SELL; v.nrows = L.nrows; v.ncols = L.ncols; v.nitems = L.nitems(); v.max_row = L.max_row; v.recip = 0;
+        v.rptr = nullptr; v.split = nullptr; v.late = nullptr;
+        v.slice_row = dev_upload(L.slice_row); v.slice_ptr = dev_upload(L.slice_ptr);
+        const size_t total = (size_t)L.slice_ptr.back();
+        int *d_col = dev_alloc<int>(total);
+        double *d_val = dev_alloc<double>(total);
+        v.col = d_col; v.val = d_val;
+        if (total) {
+            const size_t nz = (size_t)M.row_ptr[M.num_rows];
+            int *d_rp = dev_upload_raw(M.row_ptr, (size_t)M.num_rows + 1);
+            int *d_ci = dev_upload_raw(M.col_idx, nz);
+            double *d_va = dev_upload_raw(M.val, nz);
+            temps.push_back(d_rp); temps.push_back(d_ci); temps.push_back(d_va);
+            const int ns = L.nitems();
+            LAUNCH(sell_fill_kernel, std::max(1, std::min((ns + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 148 * 16)), BLOCK, stream,
+                   ns, v.slice_row, v.slice_ptr, d_order, d_colpos, (const int *)d_rp, (const int *)d_ci, (const double *)d_va, d_col, d_val);
+        }
+        nnz = L.nnz; padded = (long long)total; max_row = L.max_row; valid = true;
+        t_upload() += now_s() - t0;
+    }
     void release() {
         if (!valid) return;
         dev_free(v.slice_row); dev_free(v.slice_ptr); dev_free(v.rptr); dev_free(v.split); dev_free(v.late);
@@ -839,11 +864,16 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     CUDA_CHECK(cudaEventCreate(&h->ev1));
     int dev = 0;
     CUDA_CHECK(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
-    h->num_sms = prop.multiProcessorCount;
-    h->max_dyn_smem = (int)prop.sharedMemPerBlockOptin - 1024;
-    if (!prop.cooperativeLaunch) { fprintf(stderr, "libamgb200: device lacks cooperative launch\n"); exit(70); }
+    {
+        // (three attribute queries instead of cudaGetDeviceProperties, which costs milliseconds on every upload)
+        int sms = 0, smem_optin = 0, coop = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_CHECK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        h->num_sms = sms;
+        h->max_dyn_smem = smem_optin - 1024;
+        if (!coop) { fprintf(stderr, "libamgb200: device lacks cooperative launch\n"); exit(70); }
+    }
     if (getenv("AMGB200_GS_BLOCK")) h->gs_block = std::max(32, std::min(BLOCK, atoi(getenv("AMGB200_GS_BLOCK")) / 32 * 32));
     h->exact = !opt.fast;
     int per_sm = 0;
@@ -912,6 +942,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     h->analysis_s = now_s() - t0;
     DevMatOwner::t_upload() = 0;
     double t_layout = 0;
+    auto tl_note = [&](const char *what, int l, double dt) { t_layout += dt; if (opt.verbose >= 3) printf("      [layout] level %d %-8s %.1f ms\n", l, what, 1e3 * dt); };
 
     int max_items = 1;
     // wavefront tables and launch strategy of one level's smoother (used for the level itself and, in natural
@@ -991,7 +1022,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             StreamLayout SL;
             const double tl = now_s();
             build_stream(lay, SL);
-            t_layout += now_s() - tl;
+            tl_note("stream", lv.n, now_s() - tl);
             if ((long long)SL.max_block * 2 <= ring) {
                 lv.strategy = 4;
                 lv.stream_ring = (int)(ring & ~127LL);
@@ -1021,7 +1052,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         ClusterStreamLayout SL;
         const double tl = now_s();
         build_stream_cluster(Amat, S, XC_CTAS, SL, (long long)h->max_dyn_smem - XC_HDR - 128);
-        t_layout += now_s() - tl;
+        tl_note("xcluster", lv.n, now_s() - tl);
         const int cap = (SL.max_width + 1) & ~1;        // every CTA holds the whole wavefront (x3)
         const long long avail = (long long)h->max_dyn_smem - XC_HDR - 3LL * cap * 8 - 128;
         if (SL.filled && (long long)SL.max_block * 2 <= avail) {
@@ -1048,6 +1079,32 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     }
     };
 
+    // SELL layouts are permuted and padded on the device from the raw CSR arrays (sell_fill_kernel); the host only builds their
+    // O(rows) slice tables.  AMGB200_HOST_LAYOUT=1 restores the host fill (debugging).
+    const bool dev_fill = !(getenv("AMGB200_HOST_LAYOUT") && atoi(getenv("AMGB200_HOST_LAYOUT")));
+    std::vector<void *> temps;
+    std::vector<int *> d_pos(nl, nullptr);
+    for (int l = 0; l < nl; ++l) {
+        h->L[l].d_order = dev_upload(sched[l].order);
+        if (dev_fill) { d_pos[l] = dev_upload(sched[l].pos); temps.push_back(d_pos[l]); }
+    }
+    // one matrix: host layout + copy, or slice table + device fill
+    auto put_matrix = [&](DevMatOwner &dst, DevLayout &lay, const amgb200_mat &M, const Schedule &rowS, const int *d_row_order, const Schedule *colS,
+                          const int *d_col_pos, int kind, const std::vector<int> *breaks, const char *what, int l) {
+        const double tl = now_s();
+        if (kind == KIND_SELL && dev_fill) {
+            build_sell_structure(M, rowS.order.data(), breaks, lay);
+            tl_note(what, l, now_s() - tl);
+            // (legacy default stream: ordered after the cudaMemcpy's of small pageable arrays, whose DMA may still be in flight
+            // when the call returns; the library's own stream is non-blocking and would not wait for them)
+            dst.upload_sell(lay, M, d_row_order, d_col_pos, (cudaStream_t)0, temps);
+        } else {
+            build_layout(M, rowS.order.data(), colS ? colS->pos.data() : nullptr, kind, breaks, lay);
+            tl_note(what, l, now_s() - tl);
+            dst.upload(lay);
+        }
+    };
+
     for (int l = 0; l < nl; ++l) {
         const amgb200_comp &c = mg->cg[l];
         Level &lv = h->L[l];
@@ -1062,16 +1119,13 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         int gs_kind = kind_of(c.A);
         const double mean_len = (double)c.A.num_nnzs / std::max(1, c.A.num_rows);
         if (is_ordered && h->exact && mean_len > ordered_csr_min) gs_kind = KIND_CSR;
-        { const double tl = now_s(); build_layout(c.A, S.order.data(), S.pos.data(), gs_kind, lv.smoothed ? &S.wf_row_ptr : nullptr, lay); t_layout += now_s() - tl; }
-        lv.A.upload(lay);
+        put_matrix(lv.A, lay, c.A, S, lv.d_order, &S, d_pos[l], gs_kind, lv.smoothed ? &S.wf_row_ptr : nullptr, "A", l);
         max_items = std::max(max_items, lay.nitems());
         if (gs_kind != kind_of(c.A)) {
             DevLayout lsp;
-            { const double tl = now_s(); build_layout(c.A, S.order.data(), S.pos.data(), kind_of(c.A), nullptr, lsp); t_layout += now_s() - tl; }
-            lv.Asp.upload(lsp);
+            put_matrix(lv.Asp, lsp, c.A, S, lv.d_order, &S, d_pos[l], kind_of(c.A), nullptr, "A(spmv)", l);
             max_items = std::max(max_items, lsp.nitems());
         }
-        lv.d_order = dev_upload(S.order);
         lv.x = dev_alloc<double>(lv.n);
         lv.b = dev_alloc<double>(lv.n + 2);               // (+2: the streaming smoother fetches 16-byte aligned segments of b)
         lv.wp = dev_alloc<double>(lv.n);
@@ -1089,8 +1143,14 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                 lv.bk = bk;
                 bk->n = lv.n; bk->smoothed = true; bk->natural = true;
                 DevLayout lb;
-                { const double tl = now_s(); build_layout(c.A, B.order.data(), B.pos.data(), gs_kind, &B.wf_row_ptr, lb); t_layout += now_s() - tl; }
-                bk->A.upload(lb);
+                {
+                    int *d_border = nullptr, *d_bpos = nullptr;
+                    if (gs_kind == KIND_SELL && dev_fill) {
+                        d_border = dev_upload(B.order); d_bpos = dev_upload(B.pos);
+                        temps.push_back(d_border); temps.push_back(d_bpos);
+                    }
+                    put_matrix(bk->A, lb, c.A, B, d_border, &B, d_bpos, gs_kind, &B.wf_row_ptr, "A(back)", l);
+                }
                 bk->A.v.recip = 1;
                 max_items = std::max(max_items, lb.nitems());
                 bk->x = dev_alloc<double>(lv.n);
@@ -1102,11 +1162,9 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             }
             // transfers: P_l rows in this level's schedule, columns in the next level's; R_l the other way round
             DevLayout lp, lr;
-            { const double tl = now_s(); build_layout(c.P, S.order.data(), sched[l + 1].pos.data(), kind_of(c.P), nullptr, lp); t_layout += now_s() - tl; }
-            lv.P.upload(lp);
+            put_matrix(lv.P, lp, c.P, S, lv.d_order, &sched[l + 1], d_pos[l + 1], kind_of(c.P), nullptr, "P", l);
             max_items = std::max(max_items, lp.nitems());
-            { const double tl = now_s(); build_layout(c.R, sched[l + 1].order.data(), S.pos.data(), kind_of(c.R), nullptr, lr); t_layout += now_s() - tl; }
-            lv.R.upload(lr);
+            put_matrix(lv.R, lr, c.R, sched[l + 1], h->L[l + 1].d_order, &S, d_pos[l], kind_of(c.R), nullptr, "R", l);
             max_items = std::max(max_items, lr.nitems());
         }
     }
@@ -1118,6 +1176,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     h->d_xnat = dev_alloc<double>(maxn);
     h->d_bnat = dev_alloc<double>(maxn);
     CUDA_CHECK(cudaDeviceSynchronize());
+    for (void *p : temps) dev_free(p);                  // raw CSR copies and numbering tables of the device-side fills
     h->upload_s = now_s() - t0;
     if (opt.verbose >= 2) {
         printf("libamgb200: %d levels resident; schedule analysis %.3f s, layout build %.3f s, cudaMalloc+H2D %.3f s, total %.3f s\n", nl, h->analysis_s, t_layout, DevMatOwner::t_upload(), h->upload_s);

@@ -1778,6 +1778,34 @@ __global__ void __launch_bounds__(BLOCK) quotient_check_kernel(long long n, unsi
     if (bad) atomicAdd(mismatch, bad);
 }
 
+// Device-side construction of a SELL-32 layout from the raw CSR arrays of the host hierarchy (one warp per slice, lane = row):
+// rows taken in `order` (schedule position -> natural row, or identity), columns renumbered through `col_pos`, padding
+// col = -1 / val = +0.0, row-internal storage order untouched.  Writes are fully coalesced; the host only computes the O(rows)
+// slice table (analysis.cpp: build_sell_structure).
+__global__ void __launch_bounds__(BLOCK) sell_fill_kernel(int nslices, const int *__restrict__ slice_row, const long long *__restrict__ slice_ptr,
+                                                           const int *__restrict__ order, const int *__restrict__ col_pos,
+                                                           const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
+                                                           int *__restrict__ col, double *__restrict__ val) {
+    const int lane = threadIdx.x & 31;
+    for (int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); s < nslices; s += gridDim.x * WARPS_PER_BLOCK) {
+        const long long base = slice_ptr[s];
+        const int width = (int)((slice_ptr[s + 1] - base) >> 5);
+        const int r0 = slice_row[s], nr = slice_row[s + 1] - r0;
+        int p0 = 0, len = 0;
+        if (lane < nr) {
+            const int i = order ? order[r0 + lane] : r0 + lane;
+            p0 = rp[i]; len = rp[i + 1] - p0;
+        }
+        for (int e = 0; e < width; ++e) {
+            int j = -1;
+            double a = 0.0;
+            if (e < len) { j = ci[p0 + e]; a = va[p0 + e]; if (col_pos) j = col_pos[j]; }
+            col[base + 32LL * e + lane] = j;
+            val[base + 32LL * e + lane] = a;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(BLOCK) gather_kernel(int n, const int *__restrict__ order, const double *__restrict__ in, double *out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) out[k] = in[order[k]];

@@ -342,3 +342,28 @@ def test_quotient_fast_path(mode):
     L.amgb200_debug_quotient_check.argtypes = [C.c_longlong, C.c_ulonglong, C.c_int]
     for seed in (1, 2026):
         assert L.amgb200_debug_quotient_check(1 << 26, seed, mode) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["p3d16", "v27_12"])
+def test_host_and_device_sell_fill_agree(name, oracle, monkeypatch):
+    """SELL-32 layouts permuted/padded on the device (sell_fill_kernel, the default) and on the host
+    (AMGB200_HOST_LAYOUT=1, analysis.cpp build_layout) give bit-identical SpMV on every level and the same solve"""
+    A, hier, dev = case(name)
+    monkeypatch.setenv("AMGB200_HOST_LAYOUT", "1")
+    dev_h = DeviceHierarchy(hier)
+    monkeypatch.delenv("AMGB200_HOST_LAYOUT")
+    for l in range(dev.num_levels):
+        n = dev.info(l)["rows"]
+        x = rng_vec(n, 7 + l)
+        assert dev.spmv(l, "A", x).tobytes() == dev_h.spmv(l, "A", x).tobytes()
+        if l + 1 < dev.num_levels:
+            nc = dev.info(l + 1)["rows"]
+            xc = rng_vec(nc, 70 + l)
+            assert dev.spmv(l, "P", xc).tobytes() == dev_h.spmv(l, "P", xc).tobytes()
+            assert dev.spmv(l, "R", x).tobytes() == dev_h.spmv(l, "R", x).tobytes()
+    n0 = A.nrows
+    r1, x1, h1 = dev.solve(np.ones(n0), np.ones(n0))
+    r2, x2, h2 = dev_h.solve(np.ones(n0), np.ones(n0))
+    assert r1.nits == r2.nits and x1.tobytes() == x2.tobytes()
+    dev_h.close()
