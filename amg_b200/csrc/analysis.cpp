@@ -17,6 +17,8 @@
 #include <cstring>
 #include <new>
 
+#include <omp.h>
+
 namespace amgb200 {
 
 int choose_kind(const amgb200_mat &M, double sell_max_mean) {
@@ -42,27 +44,38 @@ void build_schedule(const amgb200_mat &A, const int *mark, Schedule &S) {
     std::vector<int> lvl(n, 0), pend(n, 0);
     std::vector<unsigned char> pass(n, 0);
     if (mark) for (int i = 0; i < n; ++i) pass[i] = mark[i] == 1 ? 1 : 0;
-    int depth[2] = {0, 0};
-    for (int i = 0; i < n; ++i) {
-        const int p = pass[i];
-        const int b = A.row_ptr[i], e = A.row_ptr[i + 1];
-        int L = 1;
-        bool diag = false;
-        for (int k = b; k < e; ++k) {
-            const int j = A.col_idx[k];
-            if (j == i) { diag = true; continue; }
-            if (j < i && pass[j] == p && lvl[j] + 1 > L) L = lvl[j] + 1;
+    // the two passes are independent recurrences over disjoint rows (only same-pass neighbours enter): one thread each
+    int depth[2] = {0, 0}, nodiag[2] = {0, 0}, rows[2] = {0, 0};
+    bool sym[2] = {true, true};
+#pragma omp parallel for schedule(static, 1) num_threads(2)
+    for (int p = 0; p < 2; ++p) {
+        int dmax = 0, nd = 0, nr = 0;
+        bool sy = true;
+        for (int i = 0; i < n; ++i) {
+            if (pass[i] != p) continue;
+            const int b = A.row_ptr[i], e = A.row_ptr[i + 1];
+            int L = 1;
+            bool diag = false;
+            for (int k = b; k < e; ++k) {
+                const int j = A.col_idx[k];
+                if (j == i) { diag = true; continue; }
+                if (j < i && pass[j] == p && lvl[j] + 1 > L) L = lvl[j] + 1;
+            }
+            if (pend[i] > L) { L = pend[i]; sy = false; }
+            lvl[i] = L;
+            if (!diag) ++nd;
+            for (int k = b; k < e; ++k) {
+                const int j = A.col_idx[k];
+                if (j > i && pass[j] == p && pend[j] < L + 1) pend[j] = L + 1;
+            }
+            if (L > dmax) dmax = L;
+            ++nr;
         }
-        if (pend[i] > L) { L = pend[i]; S.pattern_symmetric = false; }
-        lvl[i] = L;
-        if (!diag) S.rows_without_diag++;
-        for (int k = b; k < e; ++k) {
-            const int j = A.col_idx[k];
-            if (j > i && pass[j] == p && pend[j] < L + 1) pend[j] = L + 1;
-        }
-        if (L > depth[p]) depth[p] = L;
-        S.pass_rows[p]++;
+        depth[p] = dmax; nodiag[p] = nd; rows[p] = nr; sym[p] = sy;
     }
+    S.rows_without_diag = nodiag[0] + nodiag[1];
+    S.pass_rows[0] = rows[0]; S.pass_rows[1] = rows[1];
+    S.pattern_symmetric = sym[0] && sym[1];
     S.wf_count[0] = depth[0];
     S.wf_count[1] = depth[1];
     const int W = depth[0] + depth[1];
@@ -287,7 +300,7 @@ void build_stream(const DevLayout &L, StreamLayout &S) {
     }
 }
 
-void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, ClusterStreamLayout &SL, long long smem_budget) {
+void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, ClusterStreamLayout &SL, long long smem_budget, int late_dist) {
     const int n = S.n, W = S.wf_count[0] + S.wf_count[1];
     const std::vector<int> &wrp = S.wf_row_ptr;
     auto r8 = [](int v) { return (v + 7) & ~7; };
@@ -295,11 +308,13 @@ void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, Cluste
     for (int w = 0; w < W; ++w) for (int k = wrp[w]; k < wrp[w + 1]; ++k) wf_of[k] = w;
     // cyclic distance from the wavefront of column c back to wavefront w (1 = the wavefront just before)
     auto dist = [&](int w, int c) { const int d = w - wf_of[c]; return d > 0 ? d : d + W; };
+    const int LD = (late_dist >= 3 && W >= 6) ? 3 : 2;       // entries at cyclic wavefront distance <= LD come from the exchange buffers
     SL.C = C;
+    SL.late_dist = LD;
     SL.max_width = 0;
     for (int w = 0; w < W; ++w) SL.max_width = std::max(SL.max_width, wrp[w + 1] - wrp[w]);
     // the three exchange buffers alone (every CTA holds the whole of the last three wavefronts) must leave room for a ring
-    if (smem_budget >= 0 && 24LL * ((SL.max_width + 1) & ~1) + 8192 > smem_budget) { SL.filled = false; return; }
+    if (smem_budget >= 0 && 8LL * (LD + 1) * ((SL.max_width + 1) & ~1) + 8192 > smem_budget) { SL.filled = false; return; }
     std::vector<int> rec_bytes((size_t)n), split((size_t)n), nlate((size_t)n);
 #pragma omp parallel for schedule(static)
     for (int k = 0; k < n; ++k) {
@@ -308,7 +323,7 @@ void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, Cluste
         int sp = len, nl = 0;
         for (int q = 0; q < len; ++q) {
             const int c = S.pos[A.col_idx[p0 + q]];
-            if (c != k && dist(wf_of[k], c) <= 2) { if (q < sp) sp = q; ++nl; }
+            if (c != k && dist(wf_of[k], c) <= LD) { if (q < sp) sp = q; ++nl; }
         }
         split[k] = sp; nlate[k] = nl;
         rec_bytes[k] = 32 + (r8(sp) + r8(len - sp)) * 12;
@@ -333,7 +348,7 @@ void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, Cluste
     SL.mean_block = W ? (long long)SL.blk_ptr[(size_t)W * C] * 16 / ((long long)W * C) : 0;
     // sizes are known: give up before the (expensive) fill when two of the largest blocks plus the three exchange
     // buffers cannot fit in one CTA's shared memory
-    SL.filled = !(smem_budget >= 0 && 2LL * SL.max_block > smem_budget - 24LL * ((SL.max_width + 1) & ~1));
+    SL.filled = !(smem_budget >= 0 && 2LL * SL.max_block > smem_budget - 8LL * (LD + 1) * ((SL.max_width + 1) & ~1));
     if (!SL.filled) return;
     SL.data.resize((size_t)SL.blk_ptr[(size_t)W * C] * 16);
 #pragma omp parallel for schedule(dynamic, 8)
@@ -374,10 +389,10 @@ void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, Cluste
                     if (cc == k) { diag = v; continue; }
                     val[pos] = v; col[pos] = cc;
                     const int d = dist(w, cc);
-                    if (d <= 2) {
+                    if (d <= LD) {
                         const int ii = cc - wrp[wf_of[cc]];
                         StreamLateC e;
-                        e.val = v; e.pos = off + 32 + 8 * pos; e.col = cc; e.src = (d - 1) | (ii << 1); e.pad = 0;
+                        e.val = v; e.pos = off + 32 + 8 * pos; e.col = cc; e.src = (d - 1) | (ii << 2); e.pad = 0;
                         memcpy(flat + (size_t)nflat * 24, &e, 24);
                         ++nflat; ++nl;
                     }

@@ -92,14 +92,14 @@ void build_stream(const DevLayout &L, StreamLayout &S);
 // The same idea for levels that need several SMs (kernels.cuh, gs_stream_cluster_kernel): row i of a wavefront
 // (i = schedule row - first row of the wavefront) belongs to CTA i % C of a C-CTA cluster, local index i / C; block
 // (w, c) = blk_ptr[w*C + c] holds CTA c's rows of wavefront w.  x stays in global memory for entries at cyclic
-// wavefront distance >= 3; entries at distance 1 or 2 ("late") are read from the exchange buffers in
-// shared memory (every CTA receives every x of the last three wavefronts).
+// wavefront distance > late_dist (2 or 3); nearer entries ("late") are read from the exchange buffers in
+// shared memory (every CTA receives every x of the last late_dist + 1 wavefronts).
 //   block  : int32 rows of this CTA, first row of the wavefront, width of the wavefront, block bytes,
 //            int32 nflat, flat_off (bytes), 0, 0                                                       (32 bytes)
 //            int32 rec_off[rows] (padded to a multiple of 4), records (header and val/col arrays as in StreamLayout, no
 //            per-row late lists; the prefix ends at the first late entry),
 //            flat late list: {double val; int32 dst; int32 col; int32 src; int32 0} for ALL late entries of the block,
-//            dst = byte offset of the product inside the block, src = (distance-1) | index within its wavefront << 1 --
+//            dst = byte offset of the product inside the block, src = (distance-1) | index within its wavefront << 2 --
 //            one flat list so that all lanes of a consumer group share the post-barrier patching evenly
 struct StreamLateC { double val; int pos; int col; int src; int pad; };
 struct ClusterStreamLayout {
@@ -111,9 +111,11 @@ struct ClusterStreamLayout {
     int max_local = 0;             // largest number of rows one CTA gets from one wavefront
     int max_width = 0;             // widest wavefront (rows)
     bool filled = false;           // false: the sizing pass showed the blocks cannot fit (data left empty)
+    int late_dist = 2;             // 2 or 3: wavefront distance served from the exchange buffers (late_dist + 1 buffers per CTA)
 };
 // smem_budget >= 0: shared memory available for 3 exchange buffers + a ring of two blocks; the fill is skipped when it cannot fit
-void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, ClusterStreamLayout &SL, long long smem_budget = -1);
+// late_dist: entries at cyclic wavefront distance <= late_dist (2 or 3; 3 needs >= 6 wavefronts) are served from the exchange buffers
+void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, ClusterStreamLayout &SL, long long smem_budget = -1, int late_dist = 3);
 
 // mark == nullptr: single pass over all rows in natural order (no C/F ordering).
 void build_schedule(const amgb200_mat &A, const int *mark, Schedule &S);

@@ -47,12 +47,13 @@ void amgb200_debug_gs_walk(const amgb200_mat *A, const int *mark, int kind, int 
         const int Cc = 4;
         ClusterStreamLayout SL;
         build_stream_cluster(*A, S, Cc, SL);
+        const int NB = SL.late_dist + 1;                               // global x is visible to the product pass through wavefront g - NB
         const int total = W * nsweeps;
         std::vector<double> vis(xs);                                   // global x as visible to the product pass
         std::vector<std::vector<std::pair<int, double>>> pending((size_t)total);
         std::vector<std::vector<std::vector<double>>> exb((size_t)total);   // [step][cta][local index]
         for (int g = 0; g < total; ++g) {
-            if (g >= 3) for (auto &pr : pending[g - 3]) vis[pr.first] = pr.second;
+            if (g >= NB) for (auto &pr : pending[g - NB]) vis[pr.first] = pr.second;
             const int w = g % W;
             exb[g].assign(Cc, {});
             for (int c = Cc - 1; c >= 0; --c) {
@@ -78,7 +79,7 @@ void amgb200_debug_gs_walk(const amgb200_mat *A, const int *mark, int kind, int 
                 for (int i = 0; i < hd[4]; ++i) {
                     StreamLateC e;
                     memcpy(&e, lt + (size_t)i * 24, 24);
-                    const int d = (e.src & 1) + 1, ii = e.src >> 1;
+                    const int d = (e.src & 3) + 1, ii = e.src >> 2;
                     const double xv = g - d >= 0 ? exb[g - d][ii % Cc][ii / Cc] : vis[e.col];
                     *reinterpret_cast<double *>(blk.data() + e.pos) = e.val * xv;
                 }
@@ -96,7 +97,7 @@ void amgb200_debug_gs_walk(const amgb200_mat *A, const int *mark, int kind, int 
                     pending[g].emplace_back(rh[0], xn);
                 }
             }
-            if (g >= 3) exb[g - 3].clear();
+            if (g >= NB) exb[g - NB].clear();
         }
         for (int k = 0; k < n; ++k) x[S.order[k]] = xs[k];
         return;

@@ -11,6 +11,8 @@
 #include <cstring>
 #include <vector>
 
+#include <omp.h>
+
 #include "../../include/amg_b200.h"
 #include "analysis.h"
 #include "kernels.cuh"
@@ -206,6 +208,7 @@ struct Level {
     int *d_blk_ptr = nullptr;
     int stream_G = 1, stream_S = 1, stream_D = 2, stream_ring = 0;   // consumer warps per group, row slots per warp, groups (wavefronts in flight)
     long long chain_terms = 0;                                    // ordered levels: sum over wavefronts of the longest post-barrier chain (terms per sweep)
+    int xc_NB = 3;                                                // strategy 5: exchange buffers per CTA (late distance + 1)
     int xc_D = 2;                                                 // strategy 5: consumer groups (wavefronts in flight)
     int xc_F = 1, xc_S = 1, xc_P = 32, xc_ring = 0, xc_cap = 0;   // strategy 5 (streaming cluster): folding warps per group, row slots, ring bytes, exchange-buffer doubles
     int dsmem_sh = 0;                  // strategy 3: x distributed over the cluster's shared memory, 2^sh rows per CTA (0 = x in global memory)
@@ -317,21 +320,27 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
     if (lv.strategy == 5) {
         static bool attr_set = false;
         if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(gs_stream_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            CUDA_CHECK(cudaFuncSetAttribute(gs_stream_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+            auto k3 = &gs_stream_cluster_kernel<3>;
+            auto k4 = &gs_stream_cluster_kernel<4>;
+            CUDA_CHECK(cudaFuncSetAttribute(k3, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            CUDA_CHECK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+            CUDA_CHECK(cudaFuncSetAttribute(k4, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            CUDA_CHECK(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
             attr_set = true;
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(XC_CTAS);
         cfg.blockDim = dim3(32 * (lv.xc_D * XC_G + 2));
-        cfg.dynamicSmemBytes = XC_HDR + (size_t)3 * lv.xc_cap * 8 + (size_t)lv.xc_ring + 128;
+        cfg.dynamicSmemBytes = XC_HDR + (size_t)lv.xc_NB * lv.xc_cap * 8 + (size_t)lv.xc_ring + 128;
         cfg.stream = h->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = XC_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        CUDA_CHECK(cudaLaunchKernelEx(&cfg, gs_stream_cluster_kernel, (const unsigned char *)lv.d_stream, (const int *)lv.d_blk_ptr, (const int *)lv.d_wf_row_ptr,
+        auto kern = &gs_stream_cluster_kernel<3>;
+        if (lv.xc_NB == 4) kern = &gs_stream_cluster_kernel<4>;
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, (const unsigned char *)lv.d_stream, (const int *)lv.d_blk_ptr, (const int *)lv.d_wf_row_ptr,
                                       (const double *)lv.b, lv.x, lv.W, nsweeps, lv.xc_F, lv.xc_S, lv.xc_P, lv.xc_D, lv.xc_ring, lv.xc_cap, lv.A.v.recip, h->d_dbg));
         ++g_launches;
 #ifdef AMGB200_TIMELINE
@@ -905,6 +914,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     std::vector<Schedule> sched_b(nl);
     std::vector<char> natural(nl, 0);
     for (int l = 0; l + 1 < nl; ++l) natural[l] = !(mg->pars.cf_order && mg->cg[l].cfmark.d);
+    omp_set_max_active_levels(2);                                                                   // (build_schedule runs its two passes on two threads)
 #pragma omp parallel for schedule(dynamic, 1)
     for (int l = 0; l < nl - 1; ++l) {                                                              // levels are independent
         const amgb200_mat &A = mg->cg[l].A;
@@ -1051,13 +1061,14 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     if (lv.ordered && h->exact && lv.strategy != 4 && lv.W >= 4 && !getenv("AMGB200_GS_STRATEGY") && !(getenv("AMGB200_NO_XC") && atoi(getenv("AMGB200_NO_XC")))) {
         ClusterStreamLayout SL;
         const double tl = now_s();
-        build_stream_cluster(Amat, S, XC_CTAS, SL, (long long)h->max_dyn_smem - XC_HDR - 128);
+        build_stream_cluster(Amat, S, XC_CTAS, SL, (long long)h->max_dyn_smem - XC_HDR - 128, getenv("AMGB200_XC_LD") ? atoi(getenv("AMGB200_XC_LD")) : 3);
         tl_note("xcluster", lv.n, now_s() - tl);
         const int cap = (SL.max_width + 1) & ~1;        // every CTA holds the whole wavefront (x3)
-        const long long avail = (long long)h->max_dyn_smem - XC_HDR - 3LL * cap * 8 - 128;
+        const long long avail = (long long)h->max_dyn_smem - XC_HDR - (SL.late_dist + 1LL) * cap * 8 - 128;
         if (SL.filled && (long long)SL.max_block * 2 <= avail) {
             lv.strategy = 5;
             lv.xc_cap = cap;
+            lv.xc_NB = SL.late_dist + 1;
             lv.xc_ring = (int)(std::min<long long>(avail, std::max<long long>(8LL * SL.max_block, 65536)) & ~15LL);
             const double mean_local = (double)S.n / lv.W / XC_CTAS;
             lv.xc_S = 1;

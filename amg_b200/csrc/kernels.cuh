@@ -818,6 +818,11 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
 // Dynamic shared memory: [mbarriers full[NS], empty[NS] | ring offsets | 64 B of zeros : 256 B][x : n doubles][ring]
 // ------------------------------------------------------------------------------------------
 constexpr int STREAM_NS = 8;                  // wavefront blocks in flight (ring descriptors)
+#ifndef AMGB200_PROD_U
+#define AMGB200_PROD_U 4
+#endif
+constexpr int PROD_U = AMGB200_PROD_U;         // entries per lane per round of the product pass (3x as many shared-memory requests in flight per warp;
+                                              // measured 2/4/8: 4 disturbs the folding warps of the other wavefronts least: level 4 2.58 -> 2.49 ms per sweep)
 constexpr int STREAM_HDR = 384;               // bytes of barriers / descriptors in front of x
 constexpr int STREAM_MAX_WARPS = 13;          // D groups of G warps + the loader (D*G <= 12: up to 157 registers per thread)
 constexpr int STREAM_MAX_G = 4;               // product warps per group (1, 2 or 4)
@@ -960,19 +965,19 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
                 // explicit shared-space accesses in program order (volatile asm): 8 column loads, then the 16 value /
                 // x loads they feed, then the products -- ptxas otherwise sinks every value load next to its multiply
                 const unsigned val_a = smem_u32(rec + 32), col_a = val_a + 8u * (unsigned)len_pad;
-                for (int p0 = 0; p0 < len_pad; p0 += 256) {
-                    int j[8];
-                    double v[8], xv[8];
+                for (int p0 = 0; p0 < len_pad; p0 += 32 * PROD_U) {
+                    int j[PROD_U];
+                    double v[PROD_U], xv[PROD_U];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) { const int p = p0 + u * 32 + lane; j[u] = lds_s32(col_a + 4u * (unsigned)(p < len_pad ? p : 0)); if (p >= len_pad) j[u] = -1; }
+                    for (int u = 0; u < PROD_U; ++u) { const int p = p0 + u * 32 + lane; j[u] = lds_s32(col_a + 4u * (unsigned)(p < len_pad ? p : 0)); if (p >= len_pad) j[u] = -1; }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < PROD_U; ++u) {
                         const int p = p0 + u * 32 + lane;
                         v[u] = lds_f64(val_a + 8u * (unsigned)(p < len_pad ? p : 0));
                         xv[u] = lds_f64(x_a + 8u * (unsigned)max(j[u], 0));
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) { const int p = p0 + u * 32 + lane; if (j[u] >= 0) sts_f64(val_a + 8u * (unsigned)p, __dmul_rn(v[u], xv[u])); }
+                    for (int u = 0; u < PROD_U; ++u) { const int p = p0 + u * 32 + lane; if (j[u] >= 0) sts_f64(val_a + 8u * (unsigned)p, __dmul_rn(v[u], xv[u])); }
                 }
             }
             SL_MARK(1)
@@ -1003,9 +1008,8 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
                 // ---- the prefix chains.  Everything the post-barrier half of the FIRST round needs is kept in
                 // registers (c_*): its dependent path is x of the late entries -> product -> store -> suffix chain ->
                 // divide -> store.
-                bool c_mine = false;
                 unsigned c_suf = 0, c_late = 0, c_val = 0;       // shared-space addresses: suffix products, late list, products
-                int c_cnt = 0, c_maxc = 0, c_row = 0, c_nlate = 0;
+                int c_cnt = 0, c_maxc = 0, c_nlate = 0;
                 double c_t = 0.0, c_d = 0.0, c_y = 0.0;
                 bool c_dsafe = false, c_store = false;
                 unsigned c_xaddr = 0;
@@ -1023,7 +1027,7 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
                     const int maxc = __reduce_max_sync(FULL, cnt);
                     const double t = chain_fold_slots(mine ? bseg[rh.x - hd.y] : 0.0, smem_u32(rec + 32), cnt, maxc, zeros_a);
                     if (base == 0) {
-                        c_mine = mine; c_row = rh.x; c_t = t; c_d = reinterpret_cast<const double *>(rec)[2];
+                        c_t = t; c_d = reinterpret_cast<const double *>(rec)[2];
                         c_y = __ddiv_rn(1.0, c_d); c_dsafe = gs_quotient_dsafe(c_d);
                         c_store = mine && leader && fabs(c_d) > GS_TINY;
                         c_xaddr = x_a + 8u * (unsigned)rh.x;
@@ -1076,7 +1080,7 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
                     tl[5] += c_maxc;
 #endif
 #if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 11
-                    if (c_mine && leader && fabs(c_d) > GS_TINY) sts_f64(x_a + 8u * (unsigned)c_row, __dmul_rn(t, c_d));
+                    if (c_store) sts_f64(c_xaddr, __dmul_rn(t, c_d));
 #else
                     {
                         const double xn = gs_quotient_pre(t, c_d, c_y, c_dsafe, recip, c_store);
@@ -1198,24 +1202,28 @@ __device__ __forceinline__ void st_async_f64(unsigned raddr, double v, unsigned 
 }
 // x of one late entry: from the exchange buffer of the wavefront that produced it (distance d = 1 or 2 before wavefront g),
 // or -- for the first wavefronts of a launch, whose predecessors belong to the previous launch -- from global memory
+template <int NB>
 __device__ __forceinline__ double xc_late_x(int g, int src, int col, unsigned xb_a, int xb_cap, const double *x) {
-    const int d = (src & 1) + 1;
+    const int d = (src & 3) + 1;
     double v;
     if (g - d < 0) asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(x + col) : "memory");
-    else v = lds_f64(xb_a + 8u * ((unsigned)((g - d) % 3) * (unsigned)xb_cap + ((unsigned)src >> 1)));
+    else v = lds_f64(xb_a + 8u * ((unsigned)((g - d) % NB) * (unsigned)xb_cap + ((unsigned)src >> 2)));
     return v;
 }
 
+// NB = exchange buffers per CTA = late distance + 1 (3 or 4; compile-time: it is the modulus of every buffer / barrier index)
+// NB = exchange buffers per CTA = late distance + 1 (3 or 4; compile-time: it is the modulus of every buffer / barrier index)
+template <int NB>
 __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
     const unsigned char *__restrict__ stream, const int *__restrict__ blk_ptr, const int *__restrict__ wf_row_ptr,
     const double *__restrict__ b, double *x, int W, int nsweeps, int F, int S, int P, int D, int ring_bytes, int xb_cap, int recip, long long *dbg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);      // full[0..8) empty[8..16) WF[16..19) GV[19..23)
-    volatile int *stage_off = reinterpret_cast<volatile int *>(smem_raw + 192);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);      // full[0..8) empty[8..16) WF[16..20) GV[20..28)
+    volatile int *stage_off = reinterpret_cast<volatile int *>(smem_raw + 224);
     const unsigned zeros_a = smem_u32(smem_raw + 256);
     double *xb = reinterpret_cast<double *>(smem_raw + XC_HDR);
     const unsigned xb_a = smem_u32(xb);
-    unsigned char *ring = smem_raw + XC_HDR + (size_t)3 * xb_cap * 8;
+    unsigned char *ring = smem_raw + XC_HDR + (size_t)NB * xb_cap * 8;       // NB = late distance + 1 exchange buffers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int totalw = W * nsweeps;
     const int C = XC_CTAS, G = XC_G;
@@ -1227,11 +1235,11 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
 #else
 #define XC_MARK(i)
 #endif
-    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + XC_NS), wf0 = smem_u32(bars + 2 * XC_NS), gv0 = smem_u32(bars + 2 * XC_NS + 3);
+    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + XC_NS), wf0 = smem_u32(bars + 2 * XC_NS), gv0 = smem_u32(bars + 2 * XC_NS + 4);
     if (threadIdx.x == 0) {
         for (int s = 0; s < XC_NS; ++s) { mbar_init(full0 + 8u * s, 1); mbar_init(empty0 + 8u * s, 1); }
-        for (int s = 0; s < 4; ++s) mbar_init(gv0 + 8u * s, C);
-        for (int s = 0; s < 3; ++s) mbar_init(wf0 + 8u * s, 1);
+        for (int s = 0; s < 8; ++s) mbar_init(gv0 + 8u * s, C);
+        for (int s = 0; s < 4; ++s) mbar_init(wf0 + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 8) reinterpret_cast<double *>(smem_raw + 256)[threadIdx.x] = 0.0;
@@ -1259,10 +1267,10 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
             // right-hand side of my first-round row: requested now, used after the product pass
             double b0 = 0.0;
             if (folder && slot * F + f < hd.x) b0 = __ldg(b + hd.y + (int)cta + (slot * F + f) * C);
-            // global x visible through wavefront g-3 (this also means: the previous use of WF[g % 3], by wavefront g-3, is over)
-            if (g >= 3) mbar_wait_cluster(gv0 + 8u * ((g - 3) & 3), ((g - 3) >> 2) & 1);
+            // global x visible through wavefront g-NB (this also means: the previous use of WF[g % NB], by wavefront g-NB, is over)
+            if (g >= NB) mbar_wait_cluster(gv0 + 8u * ((g - NB) & 7), ((g - NB) >> 3) & 1);
             // this CTA expects the whole wavefront g (width x 8 bytes) in its exchange buffer g % 3: one arrival per phase
-            if (f == 0 && lane == 0) mbar_arrive_expect_tx(wf0 + 8u * (unsigned)(g % 3), (unsigned)hd.z * 8u);
+            if (f == 0 && lane == 0) mbar_arrive_expect_tx(wf0 + 8u * (unsigned)(g % NB), (unsigned)hd.z * 8u);
             XC_MARK(1)
             // ---- before the wavefront barrier: products of every entry (late ones are redone below).  P lanes per row, all
             // row groups of the warp walk in lockstep (a diverged warp would serialise the L2 round trips of its row groups)
@@ -1324,8 +1332,10 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
                 __syncwarp();
             }
             XC_MARK(4)
-            if (g > 1) mbar_wait_cluster(wf0 + 8u * ((g - 2) % 3), ((g - 2) / 3) & 1);
-            if (g > 0) mbar_wait_cluster(wf0 + 8u * ((g - 1) % 3), ((g - 1) / 3) & 1);
+#pragma unroll
+#pragma unroll
+            for (int d = NB - 1; d >= 1; --d)
+                if (g >= d) mbar_wait_cluster(wf0 + 8u * (unsigned)((g - d) % NB), ((g - d) / NB) & 1);
             XC_MARK(5)
             // ---- after the barrier: ALL late products of the block (x from the exchange buffers), shared evenly by the lanes of the
             // group; then the suffix chains, and x_k pushed to every CTA
@@ -1336,8 +1346,8 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
                     const unsigned a0 = flat_a + 24u * (unsigned)i0, a1 = flat_a + 24u * (unsigned)(i1 < hf.x ? i1 : i0);
                     const double v0 = lds_f64(a0), v1 = lds_f64(a1);
                     const int d0 = lds_s32(a0 + 8u), d1 = lds_s32(a1 + 8u);
-                    const double x0 = xc_late_x(g, lds_s32(a0 + 16u), lds_s32(a0 + 12u), xb_a, xb_cap, x);
-                    const double x1 = xc_late_x(g, lds_s32(a1 + 16u), lds_s32(a1 + 12u), xb_a, xb_cap, x);
+                    const double x0 = xc_late_x<NB>(g, lds_s32(a0 + 16u), lds_s32(a0 + 12u), xb_a, xb_cap, x);
+                    const double x1 = xc_late_x<NB>(g, lds_s32(a1 + 16u), lds_s32(a1 + 12u), xb_a, xb_cap, x);
                     sts_f64(blk_a + (unsigned)d0, __dmul_rn(v0, x0));
                     if (i1 < hf.x) sts_f64(blk_a + (unsigned)d1, __dmul_rn(v1, x1));
                 }
@@ -1345,7 +1355,7 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
             asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");      // all late products are in place
             XC_MARK(6)
             if (folder) {
-                const unsigned xb_g = xb_a + 8u * (unsigned)(g % 3) * (unsigned)xb_cap, wf_g = wf0 + 8u * (unsigned)(g % 3);
+                const unsigned xb_g = xb_a + 8u * (unsigned)(g % NB) * (unsigned)xb_cap, wf_g = wf0 + 8u * (unsigned)(g % NB);
                 for (int base = 0; base < hd.x; base += FS) {
                     bool mine; unsigned suf_a; int cnt, maxc, row, li; double t, dg;
                     if (base == 0) { mine = c_mine; suf_a = c_suf; cnt = c_cnt; maxc = c_maxc; row = c_row; li = c_li; t = c_t; dg = c_d; }
@@ -1421,12 +1431,12 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
         int wl = 0;
         for (int g = 0; g < totalw; ++g) {
             const int start = wf_row_ptr[wl], width = wf_row_ptr[wl + 1] - start;
-            mbar_wait_cluster(wf0 + 8u * (unsigned)(g % 3), (g / 3) & 1);
-            const double *xb_g = xb + (size_t)(g % 3) * xb_cap;
+            mbar_wait_cluster(wf0 + 8u * (unsigned)(g % NB), (g / NB) & 1);
+            const double *xb_g = xb + (size_t)(g % NB) * xb_cap;
             for (int i = (int)cta + C * lane; i < width; i += C * 32) x[start + i] = xb_g[i];
             __threadfence();
             __syncwarp();
-            if (lane < C) mbar_arrive_remote(mapa_u32(gv0 + 8u * (unsigned)(g & 3), (unsigned)lane));
+            if (lane < C) mbar_arrive_remote(mapa_u32(gv0 + 8u * (unsigned)(g & 7), (unsigned)lane));
             if (++wl == W) wl = 0;
         }
     }
