@@ -62,8 +62,9 @@ amgb200_rtn SSS_amg_solve(amgb200_amg *mg, amgb200_vec *x, amgb200_vec *b) {
     }
     mg->rtn = rtn;
     amgb200_free(h);
+    const double t2 = wall();
     printf("AMG solve time: %g s\n", t1 - t0);
-    if (opt.verbose >= 2) printf("libamgb200: hierarchy analysis + upload %g s\n", t0 - t_up);
+    if (opt.verbose >= 2) printf("libamgb200: hierarchy analysis + upload %g s, release %g s, whole call %g s\n", t0 - t_up, t2 - t1, t2 - t_up);
     return rtn;
 }
 

@@ -74,7 +74,8 @@ struct DevPool {
     }
     void trim() { for (auto &b : free_blocks) cudaFree(b.second); free_blocks.clear(); }
 };
-DevPool &pool() { static DevPool *p = new DevPool(); return *p; }   // intentionally leaked: the driver reclaims at process exit
+DevPool &pool() { static DevPool *p = new DevPool(); return *p; }
+std::vector<double *> &pinned_scalars() { static std::vector<double *> *v = new std::vector<double *>(); return *v; }   // 64-byte pinned slots, leaked like the pool   // intentionally leaked: the driver reclaims at process exit
 void dev_free(const void *p) { pool().put(const_cast<void *>(p)); }
 
 template <class T>
@@ -1182,7 +1183,12 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     h->partial_stride = std::max(1184, (max_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     h->d_partial = dev_alloc<double>((size_t)4 * h->partial_stride);
     h->d_scal = dev_alloc<double>(8);
-    CUDA_CHECK(cudaMallocHost((void **)&h->h_scal, 8 * sizeof(double)));
+    {
+        // pinned read-back slots are recycled across hierarchies (cudaMallocHost / cudaFreeHost cost up to tens of milliseconds each)
+        std::vector<double *> &fl = pinned_scalars();
+        if (!fl.empty()) { h->h_scal = fl.back(); fl.pop_back(); }
+        else CUDA_CHECK(cudaMallocHost((void **)&h->h_scal, 8 * sizeof(double)));
+    }
     if (getenv("AMGB200_DEBUG_TIMING")) h->d_dbg = dev_alloc<long long>(16 * 8 + 8);
     h->d_xnat = dev_alloc<double>(maxn);
     h->d_bnat = dev_alloc<double>(maxn);
@@ -1218,7 +1224,8 @@ void amgb200_free(amgb200_hier *h) {
             delete lv.bk;
         }
     }
-    dev_free(h->d_partial); dev_free(h->d_scal); cudaFreeHost(h->h_scal);
+    dev_free(h->d_partial); dev_free(h->d_scal);
+    if (h->h_scal) pinned_scalars().push_back(h->h_scal);
     dev_free(h->d_xnat); dev_free(h->d_bnat); dev_free(h->kry); dev_free(h->d_dbg);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->stream);

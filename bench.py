@@ -39,6 +39,10 @@ WORKLOADS = {           # name: (generator kind, N, eps_z, description)
     "v27_64": ("v27", 64, 0.0, "3D 27-point variable-coefficient diffusion 64^3"),
 }
 METRIC = "vcycle_solve_time_to_1e-8"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture
+# (profiles/r1_ncu_full_summary.md: 25.86 MB per ONE-sweep launch of gs_stream_cta_kernel on level 6 of 128^3; the solve's smoother
+# launches are two sweeps each).  Algorithmic bytes of that launch: 49.5 MB -> no wasted re-reads.
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {("p3d128", "gs_stream_cta_kernel", 6): 2 * 25.86e6}
 SM_CLOCK_MHZ = 1965.0   # B200 SM clock under these single-/16-SM kernels (the clocks sampler reports the measured one)
 TOL = 1e-8
 
@@ -275,7 +279,8 @@ def main():
     kernels.sort(key=lambda k: -k["ms_per_solve"])
     top = kernels[0]
     roofline = {"bound": "hbm", "kernel": f"{top['kernel']} (level {top['level']})", "achieved": top["gbs"], "peak": hbm, "unit": "GB/s",
-                "frac": top["gbs"] / hbm, "traffic": None, "peak_source": hbm_src, "share_of_step": top["share"],
+                "frac": top["gbs"] / hbm, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get((args.workload, top["kernel"], top["level"])),
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_full_summary.md)", "peak_source": hbm_src, "share_of_step": top["share"],
                 "avg_launch_ms": top["ms_per_solve"] / top["launches_per_solve"],
                 "note": "the dominant kernel is an ordered Gauss-Seidel sweep: bounded by the dependency chain of the reference's row order "
                         "(chain_floor_frac = chain floor / measured), not by HBM; the HBM-bound kernels are under level0",
@@ -295,12 +300,14 @@ def main():
     # ---- e2e through the reference-facing call with host buffers: every call analyses and uploads the host
     # hierarchy, solves and copies x back; one untimed warm-up call (device memory pool, pinned staging buffers --
     # the same once-per-process costs the warm-up steps of the device-timed leg absorb), then the mean of E2E_CALLS
-    os.environ["AMGB200_VERBOSE"] = "0"
+    os.environ["AMGB200_VERBOSE"] = "2"                    # (the library's own breakdown of every call is parsed below)
     dev.close()                                            # the resident copy is not part of the e2e path
     E2E_CALLS = 3
-    e2e_times = []
-    with open(os.devnull, "w") as devnull:
-        saved = os.dup(1); sys.stdout.flush(); os.dup2(devnull.fileno(), 1)
+    e2e_times, e2e_parts = [], []
+    import re
+    import tempfile
+    with tempfile.TemporaryFile(mode="w+") as cap:
+        saved = os.dup(1); sys.stdout.flush(); os.dup2(cap.fileno(), 1)
         try:
             for rep in range(1 + E2E_CALLS):
                 x_host, b_host = np.ones(n), np.ones(n)
@@ -309,7 +316,17 @@ def main():
                 if rep:
                     e2e_times.append(1e3 * (time.perf_counter() - t0))
         finally:
-            os.dup2(saved, 1); os.close(saved)
+            C.CDLL(None).fflush(None)                      # the library prints through C stdio: drain it into the capture file
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+        cap.seek(0)
+        text = cap.read()
+    ups = re.findall(r"schedule analysis ([0-9.]+) s, layout build ([0-9.]+) s, cudaMalloc\+H2D ([0-9.]+) s, total ([0-9.]+) s", text)
+    sol = re.findall(r"AMG solve time: ([0-9.eE+-]+) s", text)
+    whole = re.findall(r"upload ([0-9.eE+-]+) s, release ([0-9.eE+-]+) s, whole call ([0-9.eE+-]+) s", text)
+    for u, so, wh in list(zip(ups, sol, whole))[1:]:
+        e2e_parts.append({"analysis_ms": 1e3 * float(u[0]), "layout_ms": 1e3 * float(u[1]), "alloc_h2d_ms": 1e3 * float(u[2]),
+                          "upload_total_ms": 1e3 * float(wh[0]), "solve_ms": 1e3 * float(so), "release_ms": 1e3 * float(wh[1]),
+                          "inside_library_ms": 1e3 * float(wh[2])})
     e2e_ms = sum(e2e_times) / len(e2e_times)
     h2d = device_bytes + 2 * 8 * n
     d2h = 8 * n + 8 * (rtn_e2e.nits + 1)
@@ -335,6 +352,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "calls": E2E_CALLS, "warmup_calls": 1, "min_ms": min(e2e_times), "max_ms": max(e2e_times),
+                    "per_call_ms": e2e_times, "per_call_breakdown": e2e_parts,
                     "analysis_ms": 1e3 * analysis_s, "analysis_plus_upload_ms_first_upload": 1e3 * upload_s, "vcycles": rtn_e2e.nits},
             "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "kernels": kernels[:6],

@@ -10,6 +10,6 @@ from amg_b200 import HostHierarchy, generate, solve_dropin
 kind, N = sys.argv[1], int(sys.argv[2])
 A = generate(kind, N); hier = HostHierarchy(A, tol=1e-8); n = A.nrows
 os.environ["AMGB200_VERBOSE"] = os.environ.get("AMGB200_VERBOSE", "2")
-for rep in range(3):
+for rep in range(int(os.environ.get("E2E_REPS", "3"))):
     t = time.perf_counter(); rtn, x = solve_dropin(hier, np.ones(n), np.ones(n)); dt = time.perf_counter() - t
     print(f"=== e2e call {rep}: {dt*1e3:.1f} ms, {rtn.nits} cycles", flush=True)
