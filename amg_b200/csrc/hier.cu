@@ -483,6 +483,14 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
                 attr_set1 = true;
             }
             CUDA_CHECK(cudaLaunchKernelEx(&cfg, gs_ordered_cluster_kernel<KIND, EXACT, true>, lv.A.v, (const double *)lv.b, lv.x, (const int *)lv.d_wf_item_ptr, lv.W, nsweeps, h->d_dbg));
+        } else if (KIND == 0 && lv.A.v.max_row <= 28) {
+            auto k28 = &gs_ordered_cluster_kernel<KIND, EXACT, true, 28>;
+            static bool attr_set2 = false;
+            if (!attr_set2) {
+                CUDA_CHECK(cudaFuncSetAttribute(k28, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                attr_set2 = true;
+            }
+            CUDA_CHECK(cudaLaunchKernelEx(&cfg, k28, lv.A.v, (const double *)lv.b, lv.x, (const int *)lv.d_wf_item_ptr, lv.W, nsweeps, h->d_dbg));
         } else
         CUDA_CHECK(cudaLaunchKernelEx(&cfg, gs_ordered_cluster_kernel<KIND, EXACT>, lv.A.v, (const double *)lv.b, lv.x, (const int *)lv.d_wf_item_ptr, lv.W, nsweeps, h->d_dbg));
         ++g_launches;

@@ -955,7 +955,7 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
             const int *rec_off = reinterpret_cast<const int *>(blk + 16);
             const double *bseg = reinterpret_cast<const double *>(blk + hd.w);
             // ---- products of every entry (late / late2 ones are redone below) ...
-#if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 13
+#if defined(AMGB200_ABLATE) && (AMGB200_ABLATE == 13 || AMGB200_ABLATE == 16)
             for (int ri = r; ri < 0; ri += G) {
 #else
             for (int ri = r; ri < hd.x; ri += G) {                                   // all 32 lanes on one row at a time
@@ -1019,7 +1019,7 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
                     const bool mine = ri < hd.x;
                     unsigned char *rec = blk + (mine ? rec_off[ri] : rec_off[0]);
                     const int4 rh = *reinterpret_cast<const int4 *>(rec);               // row, prefix_pad, len_pad, nlate | nlate2 << 16
-#if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 14
+#if defined(AMGB200_ABLATE) && (AMGB200_ABLATE == 14 || AMGB200_ABLATE == 16)
                     const int cnt = 0;
 #else
                     const int cnt = mine ? rh.y : 0;
@@ -1055,7 +1055,9 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
                 }
                 SL_MARK(2)
                 __syncwarp();
-                if (g > 0) mbar_wait_spin(done0 + 8u * (unsigned)((g - 1) & 7), ((g - 1) >> 3) & 1);
+                // hand-off from the folding warp of wavefront g-1: a named barrier between exactly these two warps (bar.arrive /
+                // bar.sync, ~130 cycles faster than polling the mbarrier, which the wavefront g+1 still uses for its late2 wait)
+                if (g > 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + ((g - 1) & 7)), "r"(64) : "memory");
                 SL_MARK(3)
                 // ---- after done(g-1): late products (the first two per lane from registers), suffix chains, x_k
                 {
@@ -1108,8 +1110,11 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
                 }
                 // the leaders' x stores are ordered before lane 0's arrive by the warp barrier (memory ordering among its
                 // participants); mbarrier.arrive has release, the waiters' try_wait acquire semantics at CTA scope
+                // bar.arrive orders this thread's prior shared-memory stores before the consumer's bar.sync (PTX ISA, bar:
+                // producer/consumer example)
+                if (g + 1 < totalw) asm volatile("bar.arrive %0, %1;" ::"r"(1 + (g & 7)), "r"(64) : "memory");
                 __syncwarp();
-                if (lane == 0 && g + 1 < totalw) mbar_arrive(done0 + 8u * (unsigned)(g & 7));
+                if (lane == 0 && g + 2 < totalw) mbar_arrive(done0 + 8u * (unsigned)(g & 7));
                 SL_MARK(8)
             }
             // every warp's generic writes to the block precede its reuse by the async proxy: fence, group barrier, release
@@ -1454,11 +1459,12 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
 constexpr int CLUSTER_WARPS_SELL = 8, CLUSTER_WARPS_CSR = 16;
 // ONE (SELL only): every row fits in one register chunk (max row length <= 20): no next-chunk registers, which leaves room
 // for a second register-resident item -- my item of the NEXT wavefront, requested before this wavefront's rows are finished
-template <int KIND, bool EXACT, bool ONE = false>
+// SCH: entries per thread kept in registers (20, or 28 with ONE: whole rows of 27-point operators in one L2 round trip)
+template <int KIND, bool EXACT, bool ONE = false, int SCH = 20>
 __global__ void __launch_bounds__(KIND == 0 ? 32 * CLUSTER_WARPS_SELL : 32 * CLUSTER_WARPS_CSR) gs_ordered_cluster_kernel(
     DMat A, const double *__restrict__ b, double *x, const int *__restrict__ wf_item_ptr, int W, int nsweeps, long long *dbg) {
     __shared__ double sprod[KIND == 1 ? CLUSTER_WARPS_CSR * STAGE : 1];
-    using Item = typename std::conditional<KIND == 0, SellItem<20>, CsrItem>::type;
+    using Item = typename std::conditional<KIND == 0, SellItem<SCH>, CsrItem>::type;
     using Desc = typename Item::Desc;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nw = blockDim.x >> 5;
@@ -1474,7 +1480,7 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CLUSTER_WARPS_SELL : 32 * CLU
         else if constexpr (KIND == 0) gs_finish_sell<true>(w, x);
         else gs_finish_csr<true, EXACT>(A, w, x, lane, sp);
     };
-    constexpr bool DB = KIND == 0 && ONE;
+    constexpr bool DB = KIND == 0 && ONE && SCH <= 20;
     // Look-ahead pipeline over the (static) schedule, one stage per wavefront step, so that no dependent
     // load chain (wavefront table -> item descriptor -> matrix entries) is exposed between two barriers:
     //   (a0,a1) item range of wavefront g     cur : entries of my item in g     (loaded during step g-1)
