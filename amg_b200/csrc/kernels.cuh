@@ -1381,7 +1381,11 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
 #endif
                     double xn = 0.0;
                     if (mine && lis == 0) {
+#if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 21
+                        if (fabs(dg) > GS_TINY) xn = __dmul_rn(t, c_y);
+#else
                         if (fabs(dg) > GS_TINY) xn = base == 0 ? gs_quotient_pre(t, dg, c_y, c_dsafe, recip) : gs_quotient(t, dg, recip);
+#endif
                         else asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(xn) : "l"(x + row) : "memory");     // row without a diagonal: x_k unchanged (never speculated)
                     }
                     XC_MARK(8)
