@@ -367,3 +367,38 @@ def test_host_and_device_sell_fill_agree(name, oracle, monkeypatch):
     r2, x2, h2 = dev_h.solve(np.ones(n0), np.ones(n0))
     assert r1.nits == r2.nits and x1.tobytes() == x2.tobytes()
     dev_h.close()
+
+
+GOLDEN_CASES = {"p3d64": ("p3d", 64, 0.0), "aniso3d64": ("aniso3d", 64, 1e-3), "v2732": ("v27", 32, 0.0), "p2d256": ("p2d", 256, 0.0),
+                "p3d128": ("p3d", 128, 0.0)}     # p3d128 = BASELINE.json configs[1], the bench workload, at full size
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_solve_matches_reference_fixture(name):
+    """full solves on the device against the committed fixtures generated from the REFERENCE ITSELF (tests/golden/golden.json,
+    make_golden.py): same V-cycle count, ||r|| history within 1e-10 relative per iteration (the north-star's bar; observed ~1e-15,
+    the norm is tree-reduced), solution bit-identical (sha256); plus size-independent properties at these sizes: solving twice
+    gives the same bytes, and the returned residual is the true residual of the returned solution"""
+    import hashlib
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json")))[name]
+    kind, N, eps = GOLDEN_CASES[name]
+    A = generate(kind, N, eps)
+    assert (A.nrows, A.nnz) == (gold["n"], gold["nnz"])
+    hier = HostHierarchy(A, tol=gold["tol"])
+    dev = DeviceHierarchy(hier)
+    n = A.nrows
+    rtn, x, hist = dev.solve(np.ones(n), np.ones(n))
+    want = np.array([float.fromhex(h) for h in gold["history_fix"]])
+    assert rtn.nits == len(want)
+    assert np.max(np.abs(hist - want) / want) <= RTOL_HISTORY
+    assert hashlib.sha256(x.tobytes()).hexdigest() == gold["x_sha_fix"], "solution not bit-identical to the reference's"
+    rtn2, x2, hist2 = dev.solve(np.ones(n), np.ones(n))
+    assert x2.tobytes() == x.tobytes() and hist2.tobytes() == hist.tobytes()
+    r, nrm = dev.residual(0, x, np.ones(n))
+    assert abs(nrm - want[-1]) <= 1e-10 * want[-1]
+    assert abs(np.linalg.norm(np.ones(n) - A.matvec(x)) - want[-1]) <= 1e-6 * want[-1]
+    dev.close()
+    hier.close()

@@ -16,7 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))
 GEN = {"p2d64": ("p2d", 64, 0.0), "p2d256": ("p2d", 256, 0.0), "p3d16": ("p3d", 16, 0.0), "p3d32": ("p3d", 32, 0.0),
        "p3d64": ("p3d", 64, 0.0), "aniso3d32": ("aniso3d", 32, 1e-3), "aniso3d64": ("aniso3d", 64, 1e-3),
-       "v2712": ("v27", 12, 0.0), "v2716": ("v27", 16, 0.0), "v2732": ("v27", 32, 0.0)}
+       "v2712": ("v27", 12, 0.0), "v2716": ("v27", 16, 0.0), "v2732": ("v27", 32, 0.0),
+       "p3d128": ("p3d", 128, 0.0)}            # the bench size (BASELINE.json configs[1])
 
 
 def sha(a):
