@@ -135,7 +135,29 @@ def reference_cpu_solve(A, tol):
     return run, "port", lambda: None
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """everything other than the result line (NCCL's version banner, the library's iteration tables, ...) goes to stderr:
+    stdout carries exactly ONE JSON line"""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    try:
+        C.CDLL(None).fflush(None)
+    except Exception:
+        pass
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -175,7 +197,7 @@ def main():
                 "cpu_baseline": {"value": ms, "unit": "ms", "cores": 1, "kind": how,
                                  "sample": f"full solve ({rtn.nits} V-cycles), mean of {args.steps}", "host_cores_available": os.cpu_count()},
                 "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -251,7 +273,7 @@ def main():
                             "note": "x0/b copied from host and x gathered to rank 0 and copied back inside every step"},
                     "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
                     "roofline": None, "cpu_baseline": None}
-            print(json.dumps(line))
+            emit(line)
         dist.destroy_process_group()
         return 0
 
@@ -359,7 +381,7 @@ def main():
             "phase_ms_per_solve": {"gs": phase[0], "residual": phase[1], "restrict": phase[2], "prolong": phase[3],
                                    "coarse_solve": phase[4], "outer_residual": phase[5], "total_profiled": phase[6]},
             "cpu_baseline": cpu}
-    print(json.dumps(line))
+    emit(line)
     if dist:
         dist.destroy_process_group()
     return 0
