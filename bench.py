@@ -247,6 +247,26 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
         rtn = capi.Rtn(float(hist[-1]), float(hist[-1]) / float(np.sqrt(n)), int(nits))
+        # "SpMV GB/s vs HBM peak at N GPUs": every rank times its own row-block of the level-0 residual and of one Gauss-Seidel
+        # sweep (halo exchange excluded from numerator and time), aggregate = whole-level algorithmic bytes / max over ranks
+        def shard_time(fn, reps=20):
+            fn(); torch.cuda.synchronize(); dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            tt = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        fa, fb = sharded.part.f_items[rank]
+        ca, cb = sharded.part.c_items[rank]
+        nF_items = sharded.sh["itemsF"]
+        def own_residual():
+            be.residual(fa, fb); be.residual(nF_items + ca, nF_items + cb)
+        def own_sweep():
+            be.gs_pass(0, fa, fb); be.gs_pass(1, ca, cb)
+        shard_ms = {"residual": shard_time(own_residual), "gs_sweep": shard_time(own_sweep)}
     else:
         torch.cuda.synchronize()
         sampler.start()
@@ -269,6 +289,11 @@ def main():
                     "vcycles": rtn.nits, "relres": rtn.rres, "ares": rtn.ares, "ms_per_vcycle": ms_step / max(1, rtn.nits),
                     "vcycle_algorithmic_gb": vb / 1e9, "vcycle_gbs": vb * rtn.nits / ms_step / 1e6,
                     "halo_bytes_per_exchange_per_rank": sharded.halo_bytes, "clocks": clocks,
+                    "level0_sharded": {"residual_gbs_aggregate": dev.bytes(0, 1) / shard_ms["residual"] / 1e6,
+                                       "gs_sweep_gbs_aggregate": dev.bytes(0, 0) / shard_ms["gs_sweep"] / 1e6,
+                                       "residual_frac_of_aggregate_hbm": dev.bytes(0, 1) / shard_ms["residual"] / 1e6 / (hbm * world),
+                                       "gs_sweep_frac_of_aggregate_hbm": dev.bytes(0, 0) / shard_ms["gs_sweep"] / 1e6 / (hbm * world),
+                                       "note": "each rank's own row block of level 0 (halo exchange excluded), whole-level algorithmic bytes / max over ranks"},
                     "e2e": {"value": ms_step, "unit": "ms", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n,
                             "note": "x0/b copied from host and x gathered to rank 0 and copied back inside every step"},
                     "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
