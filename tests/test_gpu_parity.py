@@ -402,3 +402,31 @@ def test_solve_matches_reference_fixture(name):
     assert abs(np.linalg.norm(np.ones(n) - A.matvec(x)) - want[-1]) <= 1e-6 * want[-1]
     dev.close()
     hier.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+def test_1138_bus_matches_reference_fixture(mode):
+    """the reference's only fixture matrix (Matrix/1138_bus.mtx: symmetric MatrixMarket file, irregular rows, reference default
+    tol 1e-6) in both CG-beta modes against the committed results of the reference itself"""
+    import hashlib
+    import json
+    import os
+    from amg_b200 import read_mtx
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "oracle", "_ref", "1138_bus.mtx")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/1138_bus.mtx not staged")
+    gold = json.load(open(os.path.join(root, "tests", "golden", "golden.json")))["1138_bus_tol1e-6"]
+    key = "fix" if mode == 0 else "asc"
+    A = read_mtx(path)
+    hier = HostHierarchy(A, tol=gold["tol"])
+    dev = DeviceHierarchy(hier, coarse_mode=mode)
+    n = A.nrows
+    rtn, x, hist = dev.solve(np.ones(n), np.ones(n))
+    want = np.array([float.fromhex(h) for h in gold[f"history_{key}"]])
+    assert rtn.nits == len(want)
+    assert np.max(np.abs(hist - want) / want) <= RTOL_HISTORY
+    assert hashlib.sha256(x.tobytes()).hexdigest() == gold[f"x_sha_{key}"]
+    dev.close()
+    hier.close()
