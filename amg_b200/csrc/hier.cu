@@ -1138,7 +1138,16 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         // use the warp-per-row layout there; SpMV/residual (throughput-bound) keep the coalesced SELL layout
         int gs_kind = kind_of(c.A);
         const double mean_len = (double)c.A.num_nnzs / std::max(1, c.A.num_rows);
-        if (is_ordered && h->exact && mean_len > ordered_csr_min) gs_kind = KIND_CSR;
+        if (is_ordered && h->exact && mean_len > ordered_csr_min) {
+            // ... unless every row fits the single-chunk thread-per-row kernel (<= 28 entries in registers: 27-point operators) and
+            // the level is too large for the single-CTA streaming smoother anyway (measured on the 27-point 64^3 level 0: 2.78 ->
+            // 2.34 ms per sweep against the warp-per-row cluster kernel)
+            int max_len = 0;
+#pragma omp parallel for reduction(max : max_len) schedule(static)
+            for (int i = 0; i < c.A.num_rows; ++i) max_len = std::max(max_len, c.A.row_ptr[i + 1] - c.A.row_ptr[i]);
+            const bool one_chunk = max_len <= 28 && (size_t)c.A.num_rows * 8 > (size_t)h->max_dyn_smem && kind_of(c.A) == KIND_SELL;
+            if (!one_chunk) gs_kind = KIND_CSR;
+        }
         put_matrix(lv.A, lay, c.A, S, lv.d_order, &S, d_pos[l], gs_kind, lv.smoothed ? &S.wf_row_ptr : nullptr, "A", l);
         max_items = std::max(max_items, lay.nitems());
         if (gs_kind != kind_of(c.A)) {
