@@ -1337,7 +1337,13 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
                 __syncwarp();
             }
             XC_MARK(4)
-#pragma unroll
+            // the (static) descriptors of my first two late entries are fetched before the wait: after it only x -> product -> store remain
+            const unsigned flat_a = smem_u32(blk + hf.y), blk_a = smem_u32(blk);
+            const int i0 = r * 32 + lane, i1 = i0 + G * 32;
+            double pv0 = 0.0, pv1 = 0.0;
+            int pd0 = 0, pd1 = 0, ps0 = 0, ps1 = 0, pc0 = 0, pc1 = 0;
+            if (i0 < hf.x) { const unsigned a = flat_a + 24u * (unsigned)i0; pv0 = lds_f64(a); pd0 = lds_s32(a + 8u); pc0 = lds_s32(a + 12u); ps0 = lds_s32(a + 16u); }
+            if (i1 < hf.x) { const unsigned a = flat_a + 24u * (unsigned)i1; pv1 = lds_f64(a); pd1 = lds_s32(a + 8u); pc1 = lds_s32(a + 12u); ps1 = lds_s32(a + 16u); }
 #pragma unroll
             for (int d = NB - 1; d >= 1; --d)
                 if (g >= d) mbar_wait_cluster(wf0 + 8u * (unsigned)((g - d) % NB), ((g - d) / NB) & 1);
@@ -1345,16 +1351,13 @@ __global__ void __launch_bounds__(32 * XC_WARPS) gs_stream_cluster_kernel(
             // ---- after the barrier: ALL late products of the block (x from the exchange buffers), shared evenly by the lanes of the
             // group; then the suffix chains, and x_k pushed to every CTA
             {
-                const unsigned flat_a = smem_u32(blk + hf.y), blk_a = smem_u32(blk);
-                for (int i0 = r * 32 + lane; i0 < hf.x; i0 += 2 * G * 32) {               // two entries per lane at a time
-                    const int i1 = i0 + G * 32;
-                    const unsigned a0 = flat_a + 24u * (unsigned)i0, a1 = flat_a + 24u * (unsigned)(i1 < hf.x ? i1 : i0);
-                    const double v0 = lds_f64(a0), v1 = lds_f64(a1);
-                    const int d0 = lds_s32(a0 + 8u), d1 = lds_s32(a1 + 8u);
-                    const double x0 = xc_late_x<NB>(g, lds_s32(a0 + 16u), lds_s32(a0 + 12u), xb_a, xb_cap, x);
-                    const double x1 = xc_late_x<NB>(g, lds_s32(a1 + 16u), lds_s32(a1 + 12u), xb_a, xb_cap, x);
-                    sts_f64(blk_a + (unsigned)d0, __dmul_rn(v0, x0));
-                    if (i1 < hf.x) sts_f64(blk_a + (unsigned)d1, __dmul_rn(v1, x1));
+                if (i0 < hf.x) sts_f64(blk_a + (unsigned)pd0, __dmul_rn(pv0, xc_late_x<NB>(g, ps0, pc0, xb_a, xb_cap, x)));
+                if (i1 < hf.x) sts_f64(blk_a + (unsigned)pd1, __dmul_rn(pv1, xc_late_x<NB>(g, ps1, pc1, xb_a, xb_cap, x)));
+                for (int j0 = i0 + 2 * G * 32; j0 < hf.x; j0 += G * 32) {
+                    const unsigned a = flat_a + 24u * (unsigned)j0;
+                    const double v = lds_f64(a);
+                    const int dd = lds_s32(a + 8u);
+                    sts_f64(blk_a + (unsigned)dd, __dmul_rn(v, xc_late_x<NB>(g, lds_s32(a + 16u), lds_s32(a + 12u), xb_a, xb_cap, x)));
                 }
             }
             asm volatile("bar.sync %0, %1;" ::"r"(9 + grp), "r"(G * 32) : "memory");      // all late products are in place
