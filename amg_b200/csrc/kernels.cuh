@@ -885,12 +885,9 @@ __device__ __forceinline__ double chain_fold_slots(double t, unsigned sp, int cn
         AMGB200_LOAD(v0, q + 24) AMGB200_FOLD(v1)
         AMGB200_LOAD(v1, q + 32) AMGB200_FOLD(v2)
     }
-#pragma unroll 1
-    for (; q < maxc; q += 8) {
-        AMGB200_LOAD(v2, q + 16) AMGB200_FOLD(v0)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { v0[u] = v1[u]; v1[u] = v2[u]; }
-    }
+    // at most two 8-term blocks are left, and both are already in registers (v0 = block q, v1 = block q + 8): no loads, no moves
+    if (q < maxc) { AMGB200_FOLD(v0) }
+    if (q + 8 < maxc) { AMGB200_FOLD(v1) }
 #undef AMGB200_FOLD
 #undef AMGB200_LOAD
     return t;
