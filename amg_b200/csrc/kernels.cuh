@@ -971,7 +971,11 @@ __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
                     for (int u = 0; u < PROD_U; ++u) {
                         const int p = p0 + u * 32 + lane;
                         v[u] = lds_f64(val_a + 8u * (unsigned)(p < len_pad ? p : 0));
+#if defined(AMGB200_ABLATE) && AMGB200_ABLATE == 17
+                        xv[u] = lds_f64(x_a + 8u * (unsigned)(j[u] >= 0 ? lane : 0));       // (timing only: conflict-free stand-in for the x gather)
+#else
                         xv[u] = lds_f64(x_a + 8u * (unsigned)max(j[u], 0));
+#endif
                     }
 #pragma unroll
                     for (int u = 0; u < PROD_U; ++u) { const int p = p0 + u * 32 + lane; if (j[u] >= 0) sts_f64(val_a + 8u * (unsigned)p, __dmul_rn(v[u], xv[u])); }
