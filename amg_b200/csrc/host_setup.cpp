@@ -19,6 +19,8 @@
 #include <cstring>
 #include <vector>
 
+#include <omp.h>
+
 #include "../../include/amg_b200.h"
 
 namespace {
@@ -363,56 +365,75 @@ amgb200_mat transpose(const amgb200_mat &A) {       // SSS_matvec.c:330-387
 // Galerkin product R*A*P (SSS_matvec.c:398-534): diagonal slot first, then columns in
 // discovery order; products accumulated as (r*a)*p in traversal order.
 amgb200_mat galerkin(const amgb200_mat &R, const amgb200_mat &A, const amgb200_mat &P) {
+    // Rows of the product are independent; the reference's markers only have to tell "already discovered in this row"
+    // (slot[i3] >= row0) and "fine column already expanded for this row" (seen[i2] == ic).  Each thread therefore walks a
+    // contiguous block of coarse rows with its own marker arrays: pass 1 counts, a prefix sum places the rows, pass 2 fills.
+    // The arithmetic and the order of every row are exactly those of the sequential loop.
     const int nc = R.num_rows, nf = A.num_rows;
-    std::vector<int> slot(nc), seen(nf);
     int *ptr = zalloc<int>((size_t)nc + 1);
-    std::fill(slot.begin(), slot.end(), -1);
-    std::fill(seen.begin(), seen.end(), -1);
-    int cnt = 0;
-    for (int ic = 0; ic < nc; ++ic) {                 // pass 1: count
-        const int row0 = cnt;
-        slot[ic] = cnt++;
-        for (int a = R.row_ptr[ic]; a < R.row_ptr[ic + 1]; ++a) {
-            const int i1 = R.col_idx[a];
-            for (int bq = A.row_ptr[i1]; bq < A.row_ptr[i1 + 1]; ++bq) {
-                const int i2 = A.col_idx[bq];
-                if (seen[i2] == ic) continue;
-                seen[i2] = ic;
-                for (int c = P.row_ptr[i2]; c < P.row_ptr[i2 + 1]; ++c) {
-                    const int i3 = P.col_idx[c];
-                    if (slot[i3] < row0) slot[i3] = cnt++;
-                }
-            }
-        }
-        ptr[ic] = row0;
-    }
-    ptr[nc] = cnt;
+    const int nt = std::max(1, std::min(omp_get_max_threads(), nc / 4096 + 1));
+    std::vector<std::vector<int>> slot_t(nt), seen_t(nt);
     amgb200_mat C;
-    C.num_rows = C.num_cols = nc; C.num_nnzs = cnt; C.row_ptr = ptr;
-    C.col_idx = zalloc<int>((size_t)cnt);
-    C.val = zalloc<double>((size_t)cnt);
-    std::fill(slot.begin(), slot.end(), -1);
-    std::fill(seen.begin(), seen.end(), -1);
-    cnt = 0;
-    for (int ic = 0; ic < nc; ++ic) {                 // pass 2: fill
-        const int row0 = cnt;
-        slot[ic] = cnt; C.col_idx[cnt] = ic; C.val[cnt] = 0.0; ++cnt;
-        for (int a = R.row_ptr[ic]; a < R.row_ptr[ic + 1]; ++a) {
-            const double r = R.val[a];
-            const int i1 = R.col_idx[a];
-            for (int bq = A.row_ptr[i1]; bq < A.row_ptr[i1 + 1]; ++bq) {
-                const double ra = r * A.val[bq];
-                const int i2 = A.col_idx[bq];
-                if (seen[i2] != ic) {
+    C.num_rows = C.num_cols = nc; C.row_ptr = ptr; C.col_idx = nullptr; C.val = nullptr; C.num_nnzs = 0;
+#pragma omp parallel num_threads(nt)
+    {
+        const int t = omp_get_thread_num();
+        const int r0 = (int)((long long)nc * t / nt), r1 = (int)((long long)nc * (t + 1) / nt);
+        std::vector<int> &slot = slot_t[t], &seen = seen_t[t];
+        slot.assign(nc, -1);
+        seen.assign(nf, -1);
+        int cnt = 0;
+        for (int ic = r0; ic < r1; ++ic) {            // pass 1: row lengths
+            const int row0 = cnt;
+            slot[ic] = cnt++;
+            for (int a = R.row_ptr[ic]; a < R.row_ptr[ic + 1]; ++a) {
+                const int i1 = R.col_idx[a];
+                for (int bq = A.row_ptr[i1]; bq < A.row_ptr[i1 + 1]; ++bq) {
+                    const int i2 = A.col_idx[bq];
+                    if (seen[i2] == ic) continue;
                     seen[i2] = ic;
                     for (int c = P.row_ptr[i2]; c < P.row_ptr[i2 + 1]; ++c) {
-                        const double rap = ra * P.val[c];
                         const int i3 = P.col_idx[c];
-                        if (slot[i3] < row0) { slot[i3] = cnt; C.val[cnt] = rap; C.col_idx[cnt] = i3; ++cnt; }
-                        else C.val[slot[i3]] += rap;
+                        if (slot[i3] < row0) slot[i3] = cnt++;
                     }
-                } else {
-                    for (int c = P.row_ptr[i2]; c < P.row_ptr[i2 + 1]; ++c) C.val[slot[P.col_idx[c]]] += ra * P.val[c];
+                }
+            }
+            ptr[ic + 1] = cnt - row0;
+        }
+#pragma omp barrier
+#pragma omp single
+        {
+            long long tot = 0;
+            for (int ic = 0; ic < nc; ++ic) { const int len = ptr[ic + 1]; ptr[ic] = (int)tot; tot += len; }
+            if (tot > 2147483647LL) { fprintf(stderr, "amgb200_setup: coarse matrix exceeds 2^31 entries\n"); exit(-20); }
+            ptr[nc] = (int)tot;
+            C.num_nnzs = (int)tot;
+            C.col_idx = zalloc<int>((size_t)tot);
+            C.val = zalloc<double>((size_t)tot);
+        }
+        std::fill(slot.begin(), slot.end(), -1);
+        std::fill(seen.begin(), seen.end(), -1);
+        for (int ic = r0; ic < r1; ++ic) {            // pass 2: fill
+            const int row0 = ptr[ic];
+            cnt = row0;
+            slot[ic] = cnt; C.col_idx[cnt] = ic; C.val[cnt] = 0.0; ++cnt;
+            for (int a = R.row_ptr[ic]; a < R.row_ptr[ic + 1]; ++a) {
+                const double r = R.val[a];
+                const int i1 = R.col_idx[a];
+                for (int bq = A.row_ptr[i1]; bq < A.row_ptr[i1 + 1]; ++bq) {
+                    const double ra = r * A.val[bq];
+                    const int i2 = A.col_idx[bq];
+                    if (seen[i2] != ic) {
+                        seen[i2] = ic;
+                        for (int c = P.row_ptr[i2]; c < P.row_ptr[i2 + 1]; ++c) {
+                            const double rap = ra * P.val[c];
+                            const int i3 = P.col_idx[c];
+                            if (slot[i3] < row0) { slot[i3] = cnt; C.val[cnt] = rap; C.col_idx[cnt] = i3; ++cnt; }
+                            else C.val[slot[i3]] += rap;
+                        }
+                    } else {
+                        for (int c = P.row_ptr[i2]; c < P.row_ptr[i2 + 1]; ++c) C.val[slot[P.col_idx[c]]] += ra * P.val[c];
+                    }
                 }
             }
         }
@@ -461,8 +482,11 @@ extern "C" void amgb200_setup(amgb200_amg *mg, const amgb200_mat *A, const amgb2
     while (mg->cg[lvl].A.num_rows > min_cdof && lvl < pars->max_levels - 1) {
         amgb200_comp &L = mg->cg[lvl];
         Pattern S;
+        const double tt0 = omp_get_wtime();
         strength(L.A, *pars, S);
+        const double tt1 = omp_get_wtime();
         int nc = rs_split(S, mark.data());
+        const double tt2 = omp_get_wtime();
         if (nc <= 0) {
             if (verbose) { printf("### WARNING: Could not find any C-variables!\n"); printf("### WARNING: RS coarsening on level-%d failed!\n", lvl); }
             break;
@@ -477,9 +501,13 @@ extern "C" void amgb200_setup(amgb200_amg *mg, const amgb200_mat *A, const amgb2
         L.cfmark.n = L.A.num_rows;
         L.cfmark.d = zalloc<int>((size_t)L.A.num_rows);
         memcpy(L.cfmark.d, mark.data(), (size_t)L.A.num_rows * sizeof(int));
+        const double tt3 = omp_get_wtime();
         interp_direct(L.A, mark.data(), L.P, *pars);
+        const double tt4 = omp_get_wtime();
         L.R = transpose(L.P);
+        const double tt5 = omp_get_wtime();
         mg->cg[lvl + 1].A = galerkin(L.R, L.A, L.P);
+        if (verbose >= 2) printf("[setup] level %d: strength %.3f split %.3f clean+pattern %.3f interp %.3f transpose %.3f galerkin %.3f s\n", lvl, tt1 - tt0, tt2 - tt1, tt3 - tt2, tt4 - tt3, tt5 - tt4, omp_get_wtime() - tt5);
         if (L.A.num_nnzs / L.A.num_rows > L.A.num_cols * 0.2) {       // (sic) tests the *fine* level, integer division
             if (verbose) { printf("### WARNING: Coarse matrix is too dense!\n"); printf("### WARNING: m = n = %d, nnz = %d!\n", L.A.num_cols, L.A.num_nnzs); }
             free_mat(mg->cg[lvl + 1].A);

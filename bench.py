@@ -37,6 +37,10 @@ WORKLOADS = {           # name: (generator kind, N, eps_z, description)
     "aniso64": ("aniso3d", 64, 1e-3, "anisotropic 3D diffusion (1,1,1e-3) 64^3"),
     "v27_32": ("v27", 32, 0.0, "3D 27-point variable-coefficient diffusion 32^3"),
     "v27_64": ("v27", 64, 0.0, "3D 27-point variable-coefficient diffusion 64^3"),
+    "v27_96": ("v27", 96, 0.0, "3D 27-point variable-coefficient diffusion 96^3"),
+    "v27_192": ("v27", 192, 0.0, "3D 27-point variable-coefficient diffusion 192^3"),
+    "aniso128": ("aniso3d", 128, 1e-3, "anisotropic 3D diffusion (1,1,1e-3) 128^3"),
+    "aniso256": ("aniso3d", 256, 1e-3, "anisotropic 3D diffusion (1,1,1e-3) 256^3"),
 }
 METRIC = "vcycle_solve_time_to_1e-8"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture

@@ -404,6 +404,40 @@ def test_solve_matches_reference_fixture(name):
     hier.close()
 
 
+# BASELINE.json configs[2], [3], [4] at their stated sizes: 3D 7-point 256^3, 27-point variable-coefficient
+# 192^3, anisotropic (1,1,1e-3) 256^3.  Fixtures: tests/golden/make_golden.py add p3d 256 | add v27 192 | add aniso3d 256 1e-3, i.e. the
+# reference's own SSS_amg_setup + SSS_amg_solve (/root/reference/amg/SSS_main.c:121-160 with tol 1e-8).
+FULL_SIZE_CASES = {"p3d256": ("p3d", 256, 0.0, 20), "v27192": ("v27", 192, 0.0, 23), "aniso3d256": ("aniso3d", 256, 1e-3, 8)}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(FULL_SIZE_CASES))
+def test_baseline_config_full_size(name):
+    """the three large BASELINE configs on the device against fixtures generated by the reference itself: same level table (rows/nnz
+    per level of the hierarchy the host setup produces), same V-cycle count (20 / 23 / 8), ||r|| history within
+    1e-10 relative per iteration, solution bit-identical (sha256), and the returned residual is the true residual of the solution"""
+    import hashlib
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json")))[name]
+    kind, N, eps, cycles = FULL_SIZE_CASES[name]
+    A = generate(kind, N, eps)
+    assert (A.nrows, A.nnz) == (gold["n"], gold["nnz"])
+    hier = HostHierarchy(A, tol=gold["tol"])
+    assert hier.table() == [(lv["A"]["rows"], lv["A"]["nnz"]) for lv in gold["levels"]]
+    dev = DeviceHierarchy(hier)
+    n = A.nrows
+    rtn, x, hist = dev.solve(np.ones(n), np.ones(n))
+    want = np.array([float.fromhex(h) for h in gold["history_fix"]])
+    assert rtn.nits == len(want) == cycles
+    assert np.max(np.abs(hist - want) / want) <= RTOL_HISTORY
+    assert hashlib.sha256(x.tobytes()).hexdigest() == gold["x_sha_fix"], "solution not bit-identical to the reference's"
+    r, nrm = dev.residual(0, x, np.ones(n))
+    assert abs(nrm - want[-1]) <= 1e-10 * want[-1]
+    dev.close()
+    hier.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", [0, 1])
 def test_1138_bus_matches_reference_fixture(mode):
