@@ -213,6 +213,11 @@ struct Level {
     int xc_D = 2;                                                 // strategy 5: consumer groups (wavefronts in flight)
     int xc_F = 1, xc_S = 1, xc_P = 32, xc_ring = 0, xc_cap = 0;   // strategy 5 (streaming cluster): folding warps per group, row slots, ring bytes, exchange-buffer doubles
     int dsmem_sh = 0;                  // strategy 3: x distributed over the cluster's shared memory, 2^sh rows per CTA (0 = x in global memory)
+    XRec *d_rec = nullptr;             // strategy 6 (data-flow): one {x_k, version} record per row,
+    unsigned *d_hint = nullptr;        //   per-wavefront "closed" hint words of a launch,
+    int hint_cap = 0;
+    unsigned df_vbase = 0;             //   version base of the next launch (versions grow monotonically: records are never reset)
+    int df_grid = 0, df_sch = 20;
     bool natural = false;              // natural-order Gauss-Seidel (cf_order = 0 or no cfmark): forward sweeps use this level's
     Level *bk = nullptr;               // schedule, backward sweeps (post-smoothing) the schedule/layout/vectors of *bk
     int *d_fb = nullptr;               // position in this level's numbering of row k of bk's numbering
@@ -230,6 +235,7 @@ struct amgb200_hier {
     bool exact = true;
     int max_dyn_smem = 0;
     int cluster_block = 256;
+    int df_ahead = 2;                  // data-flow smoother: wavefronts ahead of the completed frontier that poll their records
     double *d_partial = nullptr;       // 4 x partial_stride block partials
     int partial_stride = 0;
     double *d_scal = nullptr;          // 8 reduced scalars
@@ -300,6 +306,11 @@ void spmv(amgb200_hier *h, const DMat &A, int mode, int red, const double *x, do
     else spmv_k<1, false>(h, A, mode, red, x, y, b, alpha);
 }
 
+const void *df_kernel(int sch) {
+    return sch == 8 ? (const void *)gs_dataflow_kernel<8> : sch == 20 ? (const void *)gs_dataflow_kernel<20>
+         : sch == 28 ? (const void *)gs_dataflow_kernel<28> : (const void *)gs_dataflow_kernel<16>;
+}
+
 // ---- Gauss-Seidel -------------------------------------------------------------------------
 template <int KIND, bool EXACT>
 void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
@@ -316,6 +327,38 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
                 first += cnt;
             }
         }
+        return;
+    }
+    if (lv.strategy == 6) {
+        const int need = nsweeps * lv.W;
+        if (need > lv.hint_cap) {
+            if (lv.d_hint) dev_free(lv.d_hint);
+            lv.d_hint = dev_alloc<unsigned>((size_t)need * DF_HINT_STRIDE);
+            lv.hint_cap = need;
+            CUDA_CHECK(cudaMemsetAsync(lv.d_hint, 0, (size_t)need * DF_HINT_STRIDE * sizeof(unsigned), h->stream));
+        }
+        DMat A = lv.A.v;
+        const double *b = lv.b; double *x = lv.x; XRec *rec = lv.d_rec;
+        const int *iw = lv.d_item_wf, *wp = lv.d_wf_item_ptr;
+        unsigned *hint = lv.d_hint;
+        int W = lv.W, ns = nsweeps, ahead = h->df_ahead;
+        unsigned vbase = lv.df_vbase;
+        long long *dbg = h->d_dbg;
+        void *args[] = {&A, &b, &x, &rec, &iw, &wp, &hint, &W, &ns, &ahead, &vbase, &dbg};
+        const void *kern = df_kernel(lv.df_sch);
+        CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(lv.df_grid), dim3(DF_BLOCK), args, 0, h->stream));
+        ++g_launches;
+        lv.df_vbase += (unsigned)nsweeps;
+#ifdef AMGB200_DF_TIMING
+        if (h->d_dbg) {
+            long long hd[64];
+            CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            CUDA_CHECK(cudaMemcpy(hd, h->d_dbg, sizeof(hd), cudaMemcpyDeviceToHost));
+            for (int w = 0; w < 4; ++w) { const long long *o = hd + w * 8; const double ni = (double)std::max(1LL, o[6]);
+                printf("   [df] warp %d: %lld items; cycles per item: static-load wait %.0f  gate %.0f  first round %.0f  poll rounds %.0f (%.1f rounds)  chain+push %.0f\n",
+                       w, o[6], o[0] / ni, o[1] / ni, o[2] / ni, o[3] / ni, o[5] / ni, o[4] / ni); }
+        }
+#endif
         return;
     }
     if (lv.strategy == 5) {
@@ -912,6 +955,9 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     if (getenv("AMGB200_CLUSTER_BLOCK")) h->cluster_block = std::max(32, std::min(BLOCK, atoi(getenv("AMGB200_CLUSTER_BLOCK")) / 32 * 32));
     auto kind_of = [&](const amgb200_mat &M) { return choose_kind(M, sell_max_mean); };
     const double ordered_csr_min = getenv("AMGB200_ORDERED_CSR_MIN") ? atof(getenv("AMGB200_ORDERED_CSR_MIN")) : 24.0;
+    const bool no_df = getenv("AMGB200_NO_DF") && atoi(getenv("AMGB200_NO_DF"));
+    const bool df_all = getenv("AMGB200_DF_ALL") && atoi(getenv("AMGB200_DF_ALL"));       // also SELL levels the streaming kernels took
+    if (getenv("AMGB200_DF_AHEAD")) h->df_ahead = std::max(1, atoi(getenv("AMGB200_DF_AHEAD")));
 
     const double t0 = now_s();
     const int nl = h->nl;
@@ -1097,6 +1143,35 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                                             XC_CTAS, lv.xc_F, lv.xc_S, lv.xc_ring, SL.mean_block, SL.max_block, SL.max_local, SL.data.size() / 1e6);
         }
     }
+    // data-flow smoother (whole GPU, no wavefront barriers): thread-per-row levels that the streaming kernels did not take.
+    // The matrix of the level is already on the device here (lv.A); its pattern must be structurally symmetric.
+    if (lv.ordered && h->exact && lay.kind == KIND_SELL && lv.A.valid && (lv.strategy == 3 || df_all) && !getenv("AMGB200_GS_STRATEGY") && !no_df) {
+        const double tl = now_s();
+        int *d_row_slice = dev_alloc<int>((size_t)lv.n);
+        int *d_missing = dev_alloc<int>(1);
+        CUDA_CHECK(cudaMemsetAsync(d_missing, 0, sizeof(int), (cudaStream_t)0));
+        const int ns = lay.nitems(), g = std::max(1, (ns + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+        LAUNCH(df_row_slice_kernel, g, BLOCK, (cudaStream_t)0, ns, lv.A.v.slice_row, d_row_slice);
+        LAUNCH(df_symmetry_kernel, g, BLOCK, (cudaStream_t)0, lv.A.v, (const int *)d_row_slice, d_missing);
+        int missing = 0;
+        CUDA_CHECK(cudaMemcpy(&missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost));
+        dev_free(d_row_slice); dev_free(d_missing);
+        if (missing == 0) {
+            lv.strategy = 6;
+            lv.d_rec = dev_alloc<XRec>((size_t)lv.n);
+            CUDA_CHECK(cudaMemsetAsync(lv.d_rec, 0, (size_t)lv.n * sizeof(XRec), (cudaStream_t)0));
+            lv.df_vbase = 0;
+            lv.df_sch = lay.max_row <= 8 ? 8 : lay.max_row <= 20 ? 20 : lay.max_row <= 28 ? 28 : 16;
+            const void *kern = df_kernel(lv.df_sch);
+            int per_sm = 0;
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DF_BLOCK, 0));
+            if (getenv("AMGB200_DF_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("AMGB200_DF_PER_SM"))));
+            lv.df_grid = std::max(1, std::min(per_sm * h->num_sms, (ns + DF_BLOCK / 32 - 1) / (DF_BLOCK / 32)));
+            if (lv.d_stream) { dev_free(lv.d_stream); dev_free(lv.d_blk_ptr); lv.d_stream = nullptr; lv.d_blk_ptr = nullptr; }
+            if (h->opt.verbose >= 2) printf("      data-flow smoother: %d CTAs x %d threads (%d per SM), %d entries per thread in registers\n", lv.df_grid, DF_BLOCK, per_sm, lv.df_sch);
+        } else if (h->opt.verbose >= 2) printf("      data-flow smoother not used: %d entries without a mirror entry (non-symmetric pattern)\n", missing);
+        tl_note("symmetry", lv.n, now_s() - tl);
+    }
     };
 
     // SELL layouts are permuted and padded on the device from the raw CSR arrays (sell_fill_kernel); the host only builds their
@@ -1234,7 +1309,9 @@ void amgb200_free(amgb200_hier *h) {
         lv.A.release(); lv.Asp.release(); lv.P.release(); lv.R.release();
         dev_free(lv.d_order); dev_free(lv.x); dev_free(lv.b); dev_free(lv.wp);
         dev_free(lv.d_item_wf); dev_free(lv.d_wf_item_ptr); dev_free(lv.d_cnt); dev_free(lv.d_fb); dev_free(lv.d_stream); dev_free(lv.d_blk_ptr); dev_free(lv.d_wf_row_ptr);
+        dev_free(lv.d_rec); dev_free(lv.d_hint);
         if (lv.bk) {
+            dev_free(lv.bk->d_rec); dev_free(lv.bk->d_hint);
             lv.bk->A.release();
             dev_free(lv.bk->x); dev_free(lv.bk->b);
             dev_free(lv.bk->d_item_wf); dev_free(lv.bk->d_wf_item_ptr); dev_free(lv.bk->d_cnt); dev_free(lv.bk->d_stream); dev_free(lv.bk->d_blk_ptr); dev_free(lv.bk->d_wf_row_ptr);
@@ -1311,7 +1388,7 @@ const char *amgb200_level_kernel(const amgb200_hier *h, int level) {
     check_level(h, level);
     const Level &lv = h->L[level];
     if (!lv.smoothed) return "none";
-    static const char *names[6] = {"gs_pass_kernel", "gs_ordered_grid_kernel", "gs_ordered_cta_kernel", "gs_ordered_cluster_kernel", "gs_stream_cta_kernel", "gs_stream_cluster_kernel"};
+    static const char *names[7] = {"gs_pass_kernel", "gs_ordered_grid_kernel", "gs_ordered_cta_kernel", "gs_ordered_cluster_kernel", "gs_stream_cta_kernel", "gs_stream_cluster_kernel", "gs_dataflow_kernel"};
     return names[lv.strategy];
 }
 
@@ -1479,9 +1556,10 @@ double amgb200_time_op(amgb200_hier *h, int level, int op, int reps) {
     if ((op == 0 && !lv.smoothed) || ((op == 2 || op == 3) && !lv.P.valid)) return 0.0;
     cudaEvent_t a, b;
     CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+    const int nsw = getenv("AMGB200_TIMEOP_SWEEPS") ? std::max(1, atoi(getenv("AMGB200_TIMEOP_SWEEPS"))) : 1;   // (developer probe: sweeps per launch)
     auto run = [&]() {
         switch (op) {
-            case 0: smooth(h, level, 1); break;
+            case 0: smooth(h, level, nsw); break;
             case 1: spmv(h, lv.spmvA(), MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0); break;
             case 2: spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[level + 1].b, nullptr, 0.0); break;
             case 3: spmv(h, lv.P.v, MODE_AMXPY, RED_NONE, h->L[level + 1].x, lv.x, nullptr, 1.0); break;
@@ -1496,7 +1574,7 @@ double amgb200_time_op(amgb200_hier *h, int level, int op, int reps) {
     float ms = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
-    return ms / reps;
+    return ms / reps / (op == 0 ? nsw : 1);
 }
 
 

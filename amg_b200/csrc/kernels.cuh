@@ -1618,6 +1618,248 @@ __global__ void __launch_bounds__(32 * CLUSTER_WARPS_CSR) gs_ordered_cluster_dsm
     for (int i = threadIdx.x; i < chunk; i += blockDim.x) { const int k = rank * chunk + i; if (k < n) xg[k] = xs[i]; }
 }
 
+// ==========================================================================================
+// Data-flow ("sync-free") ordered Gauss-Seidel for WIDE levels: the whole GPU, no wavefront barriers.
+//
+// The reference's sweep (amg/Solve/SSS_smooth.c:16-48) orders the updates of one call totally: (sweep, pass, row).  In
+// schedule numbering, position k of sweep s needs x_j of sweep s for j < k and x_j of sweep s-1 for j > k (rows of one
+// wavefront are never adjacent, wavefronts are numbered in execution order).
+//
+// Every x_k travels as a 16-byte record {lo32(x), version, hi32(x), version}, version = launch base + number of updates of
+// row k.  A consumer gathers the records of its columns and polls the ones that are not there yet until both version words
+// are equal and >= the version it needs: value and readiness arrive in ONE L2 round trip -- no flag, no fence, no barrier,
+// no atomic on the dependency path (tools/ubench3.cu: 250-400 ns per hop against ~1 000 ns for "store x, fence, store flag /
+// poll flag, load x").  Each 8-byte half carries its own version word, so only 8-byte single-copy atomicity is assumed (what
+// the NCCL LL protocol assumes).  With a structurally symmetric matrix the version found is exactly the one needed: the
+// producer's next update depends on the consumer's own result (checked at upload; other levels keep the barrier kernels).
+// In the first sweep of a launch the not-yet-updated neighbours (j > k) are read from the plain x vector (they cannot change
+// before row k is done); versions grow monotonically across launches, so the records never need to be reset.
+// The records (16 bytes per row) stay L2-resident on all but the largest levels.  (A push variant -- one private operand slot per
+// matrix entry, written by the producer through a mirror table, read coalesced and polled by its owner only -- was built and
+// measured: no line is polled by several SMs, but 16 bytes written and read per ENTRY make it DRAM-bound on large levels and
+// it lost everywhere: 2.33 vs 1.45 ms per sweep on level 1 of 128^3, 3.28 vs 2.63 on level 0 of the 27-point 96^3.)
+//
+// Persistent cooperative grid, thread per row (a slice never straddles a wavefront), slices dealt round-robin over all
+// warps in schedule order.  A warp only waits for rows at earlier positions of the total order and takes its items in
+// increasing order, so the earliest unfinished item is always runnable: no deadlock as long as the grid is co-resident.
+// Measured facts that shaped the loop (tools/ubench4.cu, -DAMGB200_DF_TIMING): volatile loads whose results are examined one
+// by one serialise into one L2 round trip each (19 operands: 19 000 cycles), so operands are requested in batches; a warp
+// keeps only ~64 sectors in flight, so the first round over all operands costs several memory latencies and runs BEFORE the
+// warp goes to sleep on its hint; warps that are far ahead sleep on a per-wavefront hint word (written, without any ordering
+// guarantee, by the row that closes a wavefront) instead of flooding L2 with polls; correctness never depends on the hint.
+// ==========================================================================================
+struct __align__(16) XRec { unsigned lo, v0, hi, v1; };
+constexpr int DF_BLOCK = 128;
+constexpr int DF_BATCH = 10;          // operand loads in flight per thread
+constexpr int DF_HINT_STRIDE = 32;    // one hint word per 128-byte line: the words of consecutive wavefronts live in different L2 slices
+#ifndef DF_GATE_NS
+#define DF_GATE_NS 400
+#endif
+
+__device__ __forceinline__ void st_xrec(XRec *p, double x, unsigned ver) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"(ver), "r"((unsigned)(b >> 32)), "r"(ver) : "memory");
+}
+__device__ __forceinline__ bool ld_xrec(const XRec *p, unsigned need, double &x) {
+    unsigned lo, v0, hi, v1;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(v0), "=r"(hi), "=r"(v1) : "l"(p) : "memory");
+    x = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+    return v0 == v1 && (int)(v0 - need) >= 0;
+}
+
+// the same load split in two, so that a batch of loads can be ISSUED back to back before the first result is examined
+// (volatile asm statements stay in program order: a load whose result is checked right away serialises the batch into one
+// L2 round trip per entry -- measured 19 000 cycles for the 19 operands of a row)
+__device__ __forceinline__ void ld_xrec_raw(const XRec *p, uint4 &r) {
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+}
+__device__ __forceinline__ bool xrec_ok(const uint4 &r, unsigned need, double &x) {
+    x = __longlong_as_double((long long)(((unsigned long long)r.z << 32) | r.x));
+    return r.y == r.w && (int)(r.y - need) >= 0;
+}
+
+// upload: slice of every row, then the number of entries (k, j) without a stored mirror entry (j, k)
+__global__ void __launch_bounds__(BLOCK) df_row_slice_kernel(int nslices, const int *__restrict__ slice_row, int *row_slice) {
+    const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= nslices) return;
+    const int k = slice_row[s] + lane;
+    if (k < slice_row[s + 1]) row_slice[k] = s;
+}
+__global__ void __launch_bounds__(BLOCK) df_symmetry_kernel(DMat A, const int *__restrict__ row_slice, int *missing) {
+    const int s = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= A.nitems) return;
+    const int r0 = A.slice_row[s], r1 = A.slice_row[s + 1];
+    const long long p0 = A.slice_ptr[s];
+    const int width = (int)((A.slice_ptr[s + 1] - p0) >> 5);
+    const int k = r0 + lane;
+    int bad = 0;
+    for (int u = 0; u < width; ++u) {
+        const int j = A.col[p0 + (long long)u * 32 + lane];
+        if (k < r1 && j >= 0 && j != k) {
+            const int s2 = row_slice[j];
+            const long long q0 = A.slice_ptr[s2] + (j - A.slice_row[s2]);
+            const int w2 = (int)((A.slice_ptr[s2 + 1] - A.slice_ptr[s2]) >> 5);
+            bool found = false;
+            for (int e = 0; e < w2 && !found; ++e) found = A.col[q0 + (long long)e * 32] == k;
+            bad += !found;
+        }
+    }
+    if (bad) atomicAdd(missing, bad);
+}
+
+__device__ __noinline__ void tacc_sink(long long *p) { if (p) p[127] = 1; }
+template <int SCH>
+__global__ void __launch_bounds__(DF_BLOCK) gs_dataflow_kernel(DMat A, const double *__restrict__ b, double *x, XRec *rec,
+                                                               const int *__restrict__ item_wf, const int *__restrict__ wf_item_ptr, unsigned *hint,
+                                                               int W, int nsweeps, int ahead, unsigned vbase, long long *dbg) {
+#ifdef AMGB200_DF_TIMING
+    long long tg = 0, tf = 0, tp_ = 0, tt = 0, nr = 0, ni = 0, ts = 0;
+#define DF_CLK(v) const long long v = clock64();
+#else
+#define DF_CLK(v)
+#endif
+    const int lane = threadIdx.x & 31;
+    const int TW = gridDim.x * (DF_BLOCK / 32);
+    const int gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;            // consecutive items on different SMs
+    const int nitems = A.nitems;
+    const long long total = (long long)nitems * nsweeps;
+    int s = gw / nitems, q = gw - s * nitems;
+    for (long long t = gw; t < total; t += TW) {
+        // ---- static data of the item: slice descriptor, first chunk of matrix entries, right-hand side
+        const int r0 = A.slice_row[q], r1 = A.slice_row[q + 1];
+        const long long p0 = A.slice_ptr[q];
+        const int width = (int)((A.slice_ptr[q + 1] - p0) >> 5);
+        const int k = r0 + lane;
+        const bool active = k < r1;
+        const int *cp = A.col + p0 + lane;
+        const double *vp = A.val + p0 + lane;
+        int j[SCH];
+        double a[SCH];
+#pragma unroll
+        for (int u = 0; u < SCH; ++u) {
+            if (u < width) { j[u] = cp[(size_t)u * 32]; a[u] = vp[(size_t)u * 32]; }
+            else { j[u] = -1; a[u] = 0.0; }
+        }
+        const double bk = active ? b[k] : 0.0;
+        const int wf = item_wf[q];
+        const int gwf = s * W + wf;
+        const bool closes = q + 1 == wf_item_ptr[wf + 1];                  // last item of its wavefront: writes the hint
+        const unsigned vold = vbase + (unsigned)s, vnew = vold + 1u;
+        double tacc = bk, d = 0.0, yrec = 0.0;
+        bool dfound = false, dsafe = false;
+        for (int e0 = 0; e0 < width; e0 += SCH) {
+            DF_CLK(c0)
+            if (e0 > 0) {
+#pragma unroll
+                for (int u = 0; u < SCH; ++u) {
+                    if (e0 + u < width) { j[u] = cp[(size_t)(e0 + u) * 32]; a[u] = vp[(size_t)(e0 + u) * 32]; }
+                    else { j[u] = -1; a[u] = 0.0; }
+                }
+            }
+            // ---- first round: the operands of the chunk are requested in batches of DF_BATCH loads in flight (volatile loads
+            // whose results are examined one by one serialise into one L2 round trip per entry); the products of the ready
+            // ones replace a[u]
+            unsigned pend = 0;
+#pragma unroll
+            for (int u0 = 0; u0 < SCH; u0 += DF_BATCH) {
+                uint4 r[DF_BATCH];
+                double xo[DF_BATCH];
+#pragma unroll
+                for (int v = 0; v < DF_BATCH; ++v) {
+                    const int u = u0 + v;
+                    if (u < SCH && j[u] >= 0 && j[u] != k) {
+                        if (s == 0 && j[u] > k) xo[v] = __ldcg(x + j[u]);                      // not updated yet in this launch
+                        else ld_xrec_raw(rec + j[u], r[v]);
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < DF_BATCH; ++v) {
+                    const int u = u0 + v;
+                    if (u < SCH) {
+                        if (j[u] == k) d = a[u];
+                        else if (j[u] >= 0) {
+                            double xv;
+                            if (s == 0 && j[u] > k) a[u] = __dmul_rn(a[u], xo[v]);
+                            else if (xrec_ok(r[v], j[u] < k ? vnew : vold, xv)) a[u] = __dmul_rn(a[u], xv);
+                            else pend |= 1u << u;
+                        }
+                    }
+                }
+            }
+            // the reciprocal of the diagonal is an IEEE division done while the row still waits (gs_quotient_pre)
+            if (!dfound && d != 0.0) { dfound = true; yrec = __ddiv_rn(1.0, d); dsafe = gs_quotient_dsafe(d); }
+            // ---- hint: sleep until the wavefront `ahead` steps back has been closed.  The first round above ran BEFORE this wait:
+            // it costs several memory latencies (a warp keeps only ~64 sectors in flight, tools/ubench4.cu); what is left for the
+            // dependency path is one L2 round trip per polling round
+            DF_CLK(c1)
+            if (e0 == 0 && gwf >= ahead && __any_sync(FULL, pend != 0)) {
+                if (lane == 0) {
+                    unsigned f;
+                    for (;;) {
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(hint + (size_t)(gwf - ahead) * DF_HINT_STRIDE) : "memory");
+                        if ((int)(f - vbase) > 0) break;
+                        __nanosleep(DF_GATE_NS);
+                    }
+                }
+                __syncwarp();
+            }
+            DF_CLK(c2)
+            // ---- polling rounds: all operands still missing are requested together, batch by batch
+            while (pend) {
+#ifdef AMGB200_DF_TIMING
+                ++nr;
+#endif
+#pragma unroll
+                for (int u0 = 0; u0 < SCH; u0 += DF_BATCH) {
+                    if ((pend >> u0) & ((1u << DF_BATCH) - 1u)) {
+                        uint4 r[DF_BATCH];
+#pragma unroll
+                        for (int v = 0; v < DF_BATCH; ++v)
+                            if (u0 + v < SCH && (pend & (1u << (u0 + v)))) ld_xrec_raw(rec + j[u0 + v], r[v]);
+#pragma unroll
+                        for (int v = 0; v < DF_BATCH; ++v) {
+                            const int u = u0 + v;
+                            if (u < SCH && (pend & (1u << u))) {
+                                double xv;
+                                if (xrec_ok(r[v], j[u] < k ? vnew : vold, xv)) { a[u] = __dmul_rn(a[u], xv); pend &= ~(1u << u); }
+                            }
+                        }
+                    }
+                }
+            }
+            DF_CLK(c3)
+            // ---- in-order chain over the separately rounded products
+#pragma unroll
+            for (int u = 0; u < SCH; ++u)
+                if (j[u] >= 0 && j[u] != k) tacc = __dsub_rn(tacc, a[u]);
+#ifdef AMGB200_DF_TIMING
+            tf += c1 - c0; tg += c2 - c1; tp_ += c3 - c2;
+#endif
+        }
+        DF_CLK(c4)
+        if (active) {
+            double xn;
+            if (fabs(d) > GS_TINY) xn = gs_quotient_pre(tacc, d, yrec, dsafe, A.recip);
+            else xn = __ldcg(x + k);                                       // row left as it is (SSS_smooth.c:32): only its version moves on
+            st_xrec(rec + k, xn, vnew);
+            if (s == nsweeps - 1 || fabs(d) <= GS_TINY) __stcg(x + k, xn);
+        }
+        if (closes) {
+            __syncwarp();
+            if (lane == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(hint + (size_t)gwf * DF_HINT_STRIDE), "r"(vbase + 1u) : "memory");
+        }
+#ifdef AMGB200_DF_TIMING
+        { const long long c5 = clock64(); tt += c5 - c4; ++ni; }
+#endif
+        q += TW;
+        while (q >= nitems) { q -= nitems; ++s; }
+    }
+#ifdef AMGB200_DF_TIMING
+    if (dbg && lane == 0 && gw < 8) { long long *o = dbg + gw * 8; o[0] = ts; o[1] = tg; o[2] = tf; o[3] = tp_; o[4] = tt; o[5] = nr; o[6] = ni; }
+#endif
+#undef DF_CLK
+}
+
 // ------------------------------------------------------------------------------------------
 // SpMV family (amg/SSS_utils.c:161-201)
 // ------------------------------------------------------------------------------------------

@@ -124,6 +124,39 @@ def test_every_ordered_smoother_kernel_is_bit_identical(name, strategy, kernel, 
     assert kernel in used, f"{kernel} was not exercised (kernels used: {sorted(used)})"
 
 
+@pytest.mark.parametrize("per_sm", [None, "1"])
+@pytest.mark.parametrize("name", ["p2d64", "p3d32", "aniso32", "v27_16"])
+def test_dataflow_smoother_is_bit_identical(name, per_sm, oracle, monkeypatch):
+    """the data-flow (sync-free) smoother of the wide thread-per-row levels -- every x_k travels as a {value, version} record,
+    rows poll the records of their columns, no wavefront barrier -- reproduces the sequential sweep (SSS_smooth.c:16-48) bit for
+    bit for 1, 2 and 3 sweeps per launch, with the grid the occupancy allows and with one CTA per SM (different item-to-warp
+    mapping, wraps around the sweeps differently); AMGB200_DF_ALL=1 also sends the levels the streaming kernels would take to it"""
+    monkeypatch.setenv("AMGB200_DF_ALL", "1")
+    if per_sm:
+        monkeypatch.setenv("AMGB200_DF_PER_SM", per_sm)
+    kind, N, eps = CASES[name]
+    hier = HostHierarchy(generate(kind, N, eps), tol=1e-8)
+    dev = DeviceHierarchy(hier)
+    used = set()
+    for l in range(hier.num_levels - 1):
+        c = hier.level(l)
+        n = c.A.num_rows
+        used.add(dev.gs_kernel(l))
+        for sweeps in (1, 2, 3):
+            x0 = rng_vec(n, 270 + l)
+            b = rng_vec(n, 280 + l)
+            got = dev.smooth(l, sweeps, x0, b)
+            want = oracle.gs_cf(c.A, hier.cfmark(l), x0, b, sweeps, 1)
+            check_vec(dev, l, got, want, f"GS x{sweeps} ({dev.gs_kernel(l)})")
+    assert "gs_dataflow_kernel" in used, f"data-flow kernel not exercised (kernels used: {sorted(used)})"
+    n0 = hier.level(0).A.num_rows
+    rtn, x, hist = dev.solve(np.ones(n0), np.ones(n0))
+    rtn_o, x_o, hist_o = oracle.solve(hier, np.ones(n0), np.ones(n0), 0)
+    assert rtn.nits == rtn_o.nits and x.tobytes() == x_o.tobytes()
+    dev.close()
+    hier.close()
+
+
 @pytest.mark.parametrize("name", ["p2d64", "p3d16", "v27_12"])
 def test_residual_and_norm(name, oracle):
     A, hier, dev = case(name)
