@@ -1662,6 +1662,27 @@ __attribute__((visibility("default"))) long long amgb200_debug_quotient_check(lo
     CUDA_CHECK(cudaFree(d_bad));
     return (long long)bad;
 }
+// test hook: rows (of `trials` x 4 x blocks generated rows) for which scan_fold_slots differs from the sequential fp64 chain
+__attribute__((visibility("default"))) long long amgb200_debug_scanfold_check(int blocks, int trials, unsigned long long seed, int mode, int sub, double *cycles_per_term) {
+    unsigned long long *d_out = nullptr, out[4] = {0, 0, 0, 0};
+    CUDA_CHECK(cudaMalloc(&d_out, sizeof(out)));
+    CUDA_CHECK(cudaMemset(d_out, 0, sizeof(out)));
+    scanfold_check_kernel<<<blocks, 128>>>(trials, seed, mode, sub, d_out);
+    ++g_launches;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpy(out, d_out, sizeof(out), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaFree(d_out));
+#ifdef AMGB200_SF_TIMING
+    { unsigned long long c[8]; CUDA_CHECK(cudaMemcpyFromSymbol(c, sf_cyc, sizeof(c))); const double it = (double)std::max(1ULL, c[4]);
+      printf("[sf] per iteration: load %.0f (per round)  loop top %.0f  compose %.0f  scan %.0f  tail %.0f cycles; %llu iterations\n", c[0] / it, c[5] / it, c[1] / it, c[2] / it, c[3] / it, c[4]);
+      unsigned long long z[8] = {0}; CUDA_CHECK(cudaMemcpyToSymbol(sf_cyc, z, sizeof(z))); }
+#endif
+    if (cycles_per_term && out[3]) {                       // warp-level cycles per term of the longest slot: sequential chain, scan fold
+        cycles_per_term[0] = (double)out[1] / (double)out[3];
+        cycles_per_term[1] = (double)out[2] / (double)out[3];
+    }
+    return (long long)out[0];
+}
 void amgb200_sync(amgb200_hier *h) { CUDA_CHECK(cudaStreamSynchronize(h->stream)); }
 
 }  // extern "C"

@@ -893,6 +893,135 @@ __device__ __forceinline__ double chain_fold_slots(double t, unsigned sp, int cn
     return t;
 }
 
+// ------------------------------------------------------------------------------------------
+// scan_fold_slots: the same in-order fold  t <- RN(t - p_q), q = 0 .. cnt-1  as chain_fold_slots, bit for bit, but in
+// O(log) dependent steps per 8*sub terms instead of one dependent DSUB (8.1 cycles) per term.
+//
+// While the running sum stays inside one binade [2^E, 2^(E+1)) every partial sum is an integer multiple N*u of u = 2^(E-52)
+// with 2^52 <= |N| < 2^53, and RN(N*u - p) = u * RNE(N - p/u): with p/u = I + f, I = nearest integer, this is N - I unless
+// f is exactly a half -- then (I := floor(p/u), M := N - I) the exact value M - 1/2 goes to the EVEN neighbour, M - (M & 1).
+// So one term is the integer map  N -> N - D[N & 1]  with two constants D[0], D[1]; such maps compose into maps of the same
+// form (D[b] = A.D[b] + B.D[(b - A.D[b]) & 1]) -- an associative operation, i.e. a parallel prefix scan reproduces the
+// sequentially rounded sums EXACTLY as long as no partial sum leaves the binade.  Each lane of a slot folds one 8-term
+// block into such a map (tracking the range of its partial sums), a shuffle scan over the slot's lanes gives every block its
+// starting value, and every block checks that all its partial sums stay in [2^52 + 1, 2^53 - 2] (conservatively, in units of
+// 2^32).  The first block that fails (a binade crossing: 1-3 per row on the AMG levels, tools/chain_stats in DESIGN.md) is
+// folded by real DSUBs from its exact starting value and the scan resumes behind it with the new binade.  Terms that cannot
+// be scaled (non-finite, or 2^9 times larger than the sum) and sums that are zero / subnormal / non-finite take the same
+// DSUB path, so the function is total.  Validated against the sequential chain on the device (amgb200_debug_scanfold_check:
+// random magnitudes, exact ties, cancellation, zeros, growth) and by every parity test of the smoothers that use it.
+// All lanes of the warp must call it together; the result is valid in every lane of the slot.  cnt, maxc multiples of 8.
+struct FoldMap { long long d0, d1; };
+#ifdef AMGB200_SF_TIMING
+__device__ unsigned long long sf_cyc[8];
+#define SF_CLK(i) { const long long c_ = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&sf_cyc[i], (unsigned long long)(c_ - sfc)); sfc = c_; }
+#else
+#define SF_CLK(i)
+#endif
+__device__ __forceinline__ double scan_fold_slots(double t, unsigned sp, int cnt, int maxc, int sub, int lis, unsigned zeros) {
+    const long long LO = (1LL << 52) + 1, HI = (1LL << 53) - 2;
+    for (int q0 = 0; q0 < maxc; q0 += 8 * sub) {
+        // my block of the round: 8 consecutive terms (blocks past the slot's own cnt are exact no-ops)
+        const int qb = q0 + 8 * lis;
+        const unsigned src = qb < cnt ? sp + 8u * (unsigned)qb : zeros;
+        double p[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const double2 v = lds_v2f64(src + 16u * u); p[2 * u] = v.x; p[2 * u + 1] = v.y; }
+        int lo = 0;                                   // blocks [0, lo) of the round are folded into t
+#ifdef AMGB200_SF_TIMING
+        long long sfc = clock64();
+        { double sink = p[0] + p[7]; if (sink == 1.2345e300) t = 0; }
+        SF_CLK(0)
+#endif
+        while (__any_sync(FULL, lo < sub)) {
+            SF_CLK(5)
+            const unsigned long long tb = (unsigned long long)__double_as_longlong(t);
+            const int eb = (int)((tb >> 52) & 0x7ff);
+            const bool scal = eb >= 54 && eb <= 2046 && lo < sub;             // a binade the integer picture can represent
+            const double sc = __longlong_as_double((long long)(2098 - (scal ? eb : 1075)) << 52);      // 2^(52-E)
+            const double usc = __longlong_as_double((long long)((scal ? eb : 1075) - 52) << 52);       // 2^(E-52)
+            const long long n0 = __double2ll_rn(__dmul_rn(t, sc));
+            const bool neg = n0 < 0;
+            // ---- my block as a map under this binade
+            FoldMap m = {0, 0};
+            int mxh = -(1 << 30), mnh = 1 << 30;
+            bool bad = false;
+            if (lis >= lo) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double q = __dmul_rn(p[u], sc);
+                    bad |= !(fabs(q) < 0x1p57);                            // (8 such terms cannot overflow the offsets)
+                    const double qr = rint(q);
+                    long long I = __double2ll_rn(q);
+                    const double fr = __dsub_rn(q, qr);
+                    const bool tie = fabs(fr) == 0.5;
+                    if (fr == -0.5) I -= 1;                                   // ties: I = floor(p/u)
+                    long long a0 = m.d0 + I, a1 = m.d1 + I;                   // N - a = the sum before a tie is resolved
+                    const int h = (int)(a0 >> 32);
+                    mxh = max(mxh, h); mnh = min(mnh, h);
+                    if (tie) { a0 += a0 & 1; a1 += (a1 & 1) ^ 1; }            // parity of N - a for start parity 0 / 1: odd -> one further down
+                    m.d0 = a0; m.d1 = a1;
+                }
+            }
+#ifdef AMGB200_SF_TIMING
+            if (m.d0 == 0x7fffffffffffffffLL) t = 0;
+#endif
+            SF_CLK(1)
+            // ---- inclusive scan of the maps over the lanes of the slot
+            FoldMap inc = m;
+            for (int dlt = 1; dlt < sub; dlt <<= 1) {
+                FoldMap a;
+                a.d0 = __shfl_up_sync(FULL, inc.d0, dlt, sub);
+                a.d1 = __shfl_up_sync(FULL, inc.d1, dlt, sub);
+                if (lis >= dlt) {                                             // a (earlier blocks) then inc
+                    const long long c0 = a.d0 + ((a.d0 & 1) ? inc.d1 : inc.d0);
+                    const long long c1 = a.d1 + (((1 - a.d1) & 1) ? inc.d1 : inc.d0);
+                    inc.d0 = c0; inc.d1 = c1;
+                }
+            }
+#ifdef AMGB200_SF_TIMING
+            if (inc.d0 == 0x7fffffffffffffffLL) t = 0;
+#endif
+            SF_CLK(2)
+            // ---- my starting value, the validity of my block, the first block of the slot that fails
+            FoldMap exc;
+            exc.d0 = __shfl_up_sync(FULL, inc.d0, 1, sub);
+            exc.d1 = __shfl_up_sync(FULL, inc.d1, 1, sub);
+            if (lis == 0) { exc.d0 = 0; exc.d1 = 0; }
+            const long long nst = n0 - ((n0 & 1) ? exc.d1 : exc.d0);
+            // all partial sums of my block lie in [nst - ((mxh + 2) << 32), nst - ((mnh - 1) << 32)]
+            const long long vlo = nst - ((long long)(mxh + 2) << 32), vhi = nst - ((long long)(mnh - 1) << 32);
+            bool ok = scal && !bad && (neg ? (vlo >= -HI && vhi <= -LO) : (vlo >= LO && vhi <= HI));
+            if (lis < lo) ok = true;
+            const unsigned okm = __ballot_sync(FULL, ok);
+            const unsigned smask = sub == 32 ? FULL : ((1u << sub) - 1u) << ((threadIdx.x & 31) - lis);
+            const unsigned fail = ~okm & smask;
+            const int first = fail ? (__ffs(fail) - 1) - ((int)(threadIdx.x & 31) - lis) : sub;     // first failing block of my slot
+            // value in front of block `first` (or behind the last block of the round): exact
+            const bool act = lo < sub;
+            const long long nsrc = __shfl_sync(FULL, first < sub ? nst : n0 - ((n0 & 1) ? inc.d1 : inc.d0), first < sub ? first : sub - 1, sub);
+            const double tn = scal ? __dmul_rn(__ll2double_rn(nsrc), usc) : t;
+            // the failing block by real subtractions (its owner holds the terms); the scan then resumes behind it
+            double tf = tn;
+            if (act && lis == first) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) tf = __dsub_rn(tf, p[u]);
+            }
+            tf = __shfl_sync(FULL, tf, first < sub ? first : 0, sub);
+            if (act) {
+                if (first < sub) { t = tf; lo = first + 1; }
+                else { t = tn; lo = sub; }
+            }
+#ifdef AMGB200_SF_TIMING
+            if (t == 1.2345e300) lo = 0;
+            SF_CLK(3)
+            if ((threadIdx.x & 31) == 0) atomicAdd(&sf_cyc[4], 1ULL);
+#endif
+        }
+    }
+    return t;
+}
+
 __global__ void __launch_bounds__(32 * STREAM_MAX_WARPS) gs_stream_cta_kernel(
     const unsigned char *__restrict__ stream, const int *__restrict__ blk_ptr, const int *__restrict__ wf_row_ptr,
     const double *__restrict__ b, double *xg, int n, int W, int nsweeps, int G, int S, int D, int ring_bytes, int recip, long long *dbg) {
@@ -2048,6 +2177,75 @@ __global__ void __launch_bounds__(BLOCK) quotient_check_kernel(long long n, unsi
 // rows taken in `order` (schedule position -> natural row, or identity), columns renumbered through `col_pos`, padding
 // col = -1 / val = +0.0, row-internal storage order untouched.  Writes are fully coalesced; the host only computes the O(rows)
 // slice table (analysis.cpp: build_sell_structure).
+// test hook: scan_fold_slots against the sequential chain on generated rows (see its comment); counts rows whose results differ in any bit
+__device__ __forceinline__ unsigned long long sf_rng(unsigned long long &s) {
+    s += 0x9E3779B97F4A7C15ULL;
+    unsigned long long z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double sf_unit(unsigned long long &s) { return (double)(sf_rng(s) >> 11) * 0x1p-53; }
+__global__ void __launch_bounds__(128) scanfold_check_kernel(int trials, unsigned long long seed, int mode, int sub, unsigned long long *out) {
+    __shared__ __align__(16) double terms[4][1024];
+    __shared__ __align__(16) double zeros[8];
+    if (threadIdx.x < 8) zeros[threadIdx.x] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nactive = (mode >> 8) ? (mode >> 8) : 4;                         // (timing: warps per block that work)
+    mode &= 255;
+    if (warp >= nactive) return;
+    const int S = 32 / sub, slot = lane / sub, lis = lane - slot * sub;
+    const int region = 1024 / S;
+    double *mine = terms[warp] + slot * region;
+    unsigned long long bad = 0, iters = 0;
+    long long tch = 0, tsc = 0;
+    for (int tr = 0; tr < trials; ++tr) {
+        unsigned long long st = seed * 0x100000001B3ULL + ((unsigned long long)(blockIdx.x * 4 + warp) * (unsigned long long)trials + tr) * 64 + slot;
+        // slot-uniform draws first
+        const int cnt = 8 * (1 + (int)(sf_rng(st) % (unsigned)(region / 8)));
+        double t0 = (sf_unit(st) - 0.5) * exp2((double)((int)(sf_rng(st) % 41) - 20));
+        const int special = (int)(sf_rng(st) % 64);
+        if (mode == 4 && special == 0) t0 = 0.0;
+        if (mode == 4 && special == 1) t0 = 0x1p-1060;
+        if (mode == 4 && special == 2) t0 = __longlong_as_double(0x7ff0000000000000LL);
+        if (mode == 4 && special == 3) t0 = __longlong_as_double(0x7ff8000000000001LL);
+        if (mode == 4 && special == 4) t0 = -0.0;
+        const double ulp0 = exp2(floor(log2(fabs(t0) > 0 && isfinite(t0) ? fabs(t0) : 1.0)) - 52.0);
+        for (int q = lis; q < cnt; q += sub) {
+            unsigned long long sq = st + 0x1234567ULL * (unsigned long long)(q + 1);
+            double pv;
+            const double r1 = sf_unit(sq), r2 = sf_unit(sq);
+            const int k = (int)(sf_rng(sq) % 13);
+            switch (mode) {
+                case 0: pv = -t0 * r1 * exp2(-(double)(3 + k)); break;                                   // same-sign growth, realistic gaps
+                case 1: pv = (r1 - 0.5) * exp2((double)((int)(sf_rng(sq) % 61) - 30)); break;              // anything
+                case 2: pv = ((double)((int)(sf_rng(sq) % 17) - 8) + 0.5) * ulp0 * exp2((double)(k % 4)) * (r2 < 0.5 ? -1.0 : 1.0); break;   // exact ties
+                case 3: pv = t0 * (0.3 + 1.4 * r1) * (q & 1 ? -1.0 : 1.0); break;                        // cancellation, binade hopping
+                case 4: pv = k < 6 ? 0.0 : k < 8 ? 0x1p-1070 * r1 : k == 8 ? -0.0 : (r1 - 0.5) * fabs(t0) * 1e-3; break;
+                default: pv = -fabs(t0) * (t0 < 0 ? -1.0 : 1.0) * exp2(-(double)(5 + k)) * (0.5 + r1); break;  // growth by 2^-5..2^-17 steps
+            }
+            if (mode == 1 && (sf_rng(sq) % 97) == 0) pv = t0 * 1e6;
+            mine[q] = pv;
+        }
+        __syncwarp();
+        const int maxc = __reduce_max_sync(FULL, cnt);
+        const long long c0 = clock64();
+        double ref = chain_fold_slots(t0, smem_u32(mine), cnt, maxc, smem_u32(zeros));        // (the production chain: all slots at once)
+        const long long c1 = clock64();
+        const double got = scan_fold_slots(t0, smem_u32(mine), cnt, maxc, sub, lis, smem_u32(zeros));
+        const long long c2 = clock64();
+        double seq = t0;
+        if (lis == 0) for (int q = 0; q < cnt; ++q) seq = __dsub_rn(seq, mine[q]);
+        seq = __shfl_sync(FULL, seq, 0, sub);
+        if (lis == 0 && (__double_as_longlong(seq) != __double_as_longlong(got) || __double_as_longlong(seq) != __double_as_longlong(ref))) ++bad;
+        tch += c1 - c0; tsc += c2 - c1; iters += maxc;
+        __syncwarp();
+    }
+    if (bad) atomicAdd(out, bad);
+    if (lane == 0) { atomicAdd(out + 1, (unsigned long long)tch); atomicAdd(out + 2, (unsigned long long)tsc); atomicAdd(out + 3, iters); }
+}
+
 __global__ void __launch_bounds__(BLOCK) sell_fill_kernel(int nslices, const int *__restrict__ slice_row, const long long *__restrict__ slice_ptr,
                                                            const int *__restrict__ order, const int *__restrict__ col_pos,
                                                            const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,

@@ -378,6 +378,24 @@ def test_quotient_fast_path(mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("sub", [32, 16, 8, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
+def test_scan_fold_is_bit_identical_to_the_sequential_chain(mode, sub):
+    """scan_fold_slots (kernels.cuh: in-order fp64 accumulation as a parallel prefix scan of integer maps inside a binade, real
+    subtractions across binade crossings) against the sequential chain t = RN(t - p_q) (SSS_smooth.c:22-29) on generated rows of
+    8..1024 terms: same-sign growth with realistic magnitude gaps, arbitrary magnitudes and signs, exact ties on the last bit,
+    cancellation / binade hopping, zeros / subnormals / signed zeros / infinities / NaNs; 32, 16, 8 and 4 lanes per row"""
+    import ctypes as C
+    L = capi.lib()
+    L.amgb200_debug_scanfold_check.restype = C.c_longlong
+    L.amgb200_debug_scanfold_check.argtypes = [C.c_int, C.c_int, C.c_ulonglong, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    cyc = (C.c_double * 2)()
+    for seed in (1, 2026):
+        assert L.amgb200_debug_scanfold_check(296, 64, seed, mode, sub, cyc) == 0
+    print(f"mode {mode}, {sub} lanes per row: {cyc[0]:.2f} cycles per term (chain, all slots at once) vs {cyc[1]:.2f} (scan fold)")
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["p3d16", "v27_12"])
 def test_host_and_device_sell_fill_agree(name, oracle, monkeypatch):
     """SELL-32 layouts permuted/padded on the device (sell_fill_kernel, the default) and on the host
