@@ -1,4 +1,5 @@
-# Build libamgb200.so (the product: sm_100a CUDA kernels + C ABI + host helpers) and
+# Build libamgb200.so (the product: sm_100a CUDA kernels + C ABI + host helpers),
+# tests/libamgb200_testhooks.so (CPU emulations of the schedule / layouts for the CPU test-suite; not shipped in the product) and
 # oracle/liboracle.so (the CPU checker; test infrastructure only).
 NVCC      ?= nvcc
 CC        ?= gcc
@@ -8,11 +9,11 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -fmad=false -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off,-fopenmp -Iinclude
 CSRC      := amg_b200/csrc
 CU_SRCS   := $(wildcard $(CSRC)/*.cu)
-CPP_SRCS  := $(wildcard $(CSRC)/*.cpp)
+CPP_SRCS  := $(filter-out $(CSRC)/debug_host.cpp,$(wildcard $(CSRC)/*.cpp))
 OBJS      := $(CU_SRCS:.cu=.o) $(CPP_SRCS:.cpp=.o)
 HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/amg_b200.h
 
-all: amg_b200/libamgb200.so oracle/liboracle.so
+all: amg_b200/libamgb200.so tests/libamgb200_testhooks.so oracle/liboracle.so
 
 amg_b200/libamgb200.so: $(OBJS)
 	$(NVCC) -shared $(ARCH) -Xcompiler -fopenmp -o $@ $(OBJS) -lcudart
@@ -23,10 +24,13 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
 $(CSRC)/%.o: $(CSRC)/%.cpp $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
+tests/libamgb200_testhooks.so: $(CSRC)/debug_host.o $(CSRC)/analysis.o
+	$(NVCC) -shared -Xcompiler -fopenmp -o $@ $^
+
 oracle/liboracle.so: oracle/amg_oracle.c include/amg_b200.h
 	$(CC) -O2 -ffp-contract=off -fPIC -shared -o $@ oracle/amg_oracle.c -lm
 
 clean:
-	rm -f $(CSRC)/*.o $(CSRC)/*.ptxas.log amg_b200/libamgb200.so oracle/liboracle.so
+	rm -f $(CSRC)/*.o $(CSRC)/*.ptxas.log amg_b200/libamgb200.so tests/libamgb200_testhooks.so oracle/liboracle.so
 
 .PHONY: all clean

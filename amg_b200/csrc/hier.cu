@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include <omp.h>
@@ -74,12 +75,37 @@ struct DevPool {
     }
     void trim() { for (auto &b : free_blocks) cudaFree(b.second); free_blocks.clear(); }
 };
-DevPool &pool() { static DevPool *p = new DevPool(); return *p; }
-std::vector<double *> &pinned_scalars() { static std::vector<double *> *v = new std::vector<double *>(); return *v; }   // 64-byte pinned slots, leaked like the pool   // intentionally leaked: the driver reclaims at process exit
-void dev_free(const void *p) { pool().put(const_cast<void *>(p)); }
+// Everything process-global below is keyed by the CUDA device it belongs to (amgb200_options.device lets one process keep
+// hierarchies on several GPUs: a block freed on device A must never be handed to device B, and per-function attributes are
+// per device) and guarded by one mutex (uploads / frees from several host threads).
+constexpr int MAX_DEVICES = 64;
+std::mutex &global_mutex() { static std::mutex *m = new std::mutex(); return *m; }
+int current_device() { int d = 0; cudaGetDevice(&d); return d < 0 || d >= MAX_DEVICES ? 0 : d; }
+DevPool &pool(int dev) { static DevPool *p = new DevPool[MAX_DEVICES]; return p[dev]; }                 // intentionally leaked: the driver reclaims at process exit
+std::vector<double *> &pinned_scalars() { static std::vector<double *> *v = new std::vector<double *>(); return *v; }   // 64-byte pinned slots (host memory: device independent)
+// true exactly once per (call site id, device): cudaFuncSetAttribute has to be repeated on every device
+bool first_use(int id) {
+    static bool seen[16][MAX_DEVICES];
+    std::lock_guard<std::mutex> lk(global_mutex());
+    bool &b = seen[id][current_device()];
+    const bool first = !b;
+    b = true;
+    return first;
+}
+void dev_free(const void *p) {
+    if (!p) return;
+    cudaPointerAttributes at;
+    int dev = current_device();
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.device >= 0 && at.device < MAX_DEVICES) dev = at.device;
+    std::lock_guard<std::mutex> lk(global_mutex());
+    pool(dev).put(const_cast<void *>(p));
+}
 
 template <class T>
-T *dev_alloc(size_t n) { return (T *)pool().get(std::max<size_t>(n, 1) * sizeof(T)); }
+T *dev_alloc(size_t n) {
+    std::lock_guard<std::mutex> lk(global_mutex());
+    return (T *)pool(current_device()).get(std::max<size_t>(n, 1) * sizeof(T));
+}
 // Host -> device copy of pageable memory through a small ring of pinned staging buffers (allocated once per
 // process): OpenMP threads fill a staging buffer while the DMA engine drains the previous one.  ~4x faster than
 // cudaMemcpy from pageable memory for the ~1 GB of a hierarchy, without pinning the caller's arrays.
@@ -121,7 +147,7 @@ struct Stager {
         CUDA_CHECK(cudaStreamSynchronize(stream));
     }
 };
-Stager &stager() { static Stager s; return s; }
+Stager &stager() { static Stager *s = new Stager[MAX_DEVICES]; return s[current_device()]; }   // (its stream belongs to one device)
 
 template <class T>
 T *dev_upload_raw(const T *src, size_t n) {
@@ -197,10 +223,8 @@ struct Level {
     bool smoothed = false, ordered = false;
     int W = 0, wf_count[2] = {0, 0}, pass_items[2] = {0, 0}, pass_rows[2] = {0, 0}, max_width = 0;
     int *d_item_wf = nullptr, *d_wf_item_ptr = nullptr, *d_wf_row_ptr = nullptr;
-    unsigned *d_cnt = nullptr;
-    int cnt_cap = 0;
     bool pattern_symmetric = true;
-    int strategy = 0;                  // 0 = parallel passes, 1 = ordered across the grid, 2 = ordered inside one CTA, 3 = one cluster, 4 = streaming CTA, 5 = streaming cluster
+    int strategy = 0;                  // 0 = parallel passes, 2 = ordered inside one CTA, 3 = one cluster (barrier per wavefront), 4 = streaming CTA, 5 = streaming cluster, 6 = data-flow grid
     double prof_ms[4] = {0, 0, 0, 0};  // AMGB200_PROFILE: GS, residual, restrict, prolong of the last solve
     bool x_in_smem = false;            // strategy 2 only: x fits in the CTA's shared memory
     int cta_G = 1, cta_D = 1;          // strategy 2: D groups of G warps (pipeline depth D)
@@ -212,7 +236,6 @@ struct Level {
     int xc_NB = 3;                                                // strategy 5: exchange buffers per CTA (late distance + 1)
     int xc_D = 2;                                                 // strategy 5: consumer groups (wavefronts in flight)
     int xc_F = 1, xc_S = 1, xc_P = 32, xc_ring = 0, xc_cap = 0;   // strategy 5 (streaming cluster): folding warps per group, row slots, ring bytes, exchange-buffer doubles
-    int dsmem_sh = 0;                  // strategy 3: x distributed over the cluster's shared memory, 2^sh rows per CTA (0 = x in global memory)
     XRec *d_rec = nullptr;             // strategy 6 (data-flow): one {x_k, version} record per row,
     unsigned *d_hint = nullptr;        //   per-wavefront "closed" hint words of a launch,
     int hint_cap = 0;
@@ -231,7 +254,7 @@ struct amgb200_hier {
     amgb200_pars pars{};
     amgb200_options opt{};
     cudaStream_t stream = nullptr;
-    int num_sms = 0, gs_block = 64, gs_max_blocks[2] = {0, 0};
+    int num_sms = 0;
     bool exact = true;
     int max_dyn_smem = 0;
     int cluster_block = 256;
@@ -362,15 +385,13 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         return;
     }
     if (lv.strategy == 5) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (first_use(0)) {
             auto k3 = &gs_stream_cluster_kernel<3>;
             auto k4 = &gs_stream_cluster_kernel<4>;
             CUDA_CHECK(cudaFuncSetAttribute(k3, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             CUDA_CHECK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
             CUDA_CHECK(cudaFuncSetAttribute(k4, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             CUDA_CHECK(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
-            attr_set = true;
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(XC_CTAS);
@@ -405,10 +426,8 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         return;
     }
     if (lv.strategy == 4) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (first_use(1)) {
             CUDA_CHECK(cudaFuncSetAttribute(gs_stream_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
-            attr_set = true;
         }
         const size_t xb = ((size_t)lv.n * 8 + 127) & ~(size_t)127;
         const size_t smem = STREAM_HDR + xb + (size_t)lv.stream_ring + 128;
@@ -439,17 +458,13 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         const size_t stage = (size_t)nw * (STAGE + (cap ? cap + 24 + 2 * LATE_CAP : 0)) * sizeof(double);
         const size_t xbytes = (size_t)((lv.n + 1) & ~1) * sizeof(double);
         if (lv.x_in_smem) {
-            static bool attr_set = false;
-            if (!attr_set) {
+            if (first_use(2)) {
                 CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cta_kernel<KIND, EXACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
-                attr_set = true;
             }
             gs_ordered_cta_kernel<KIND, EXACT, true><<<1, 32 * nw, xbytes + stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D, cap, h->d_dbg);
         } else {
-            static bool attr_set2 = false;
-            if (!attr_set2) {
+            if (first_use(3)) {
                 CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cta_kernel<KIND, EXACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
-                attr_set2 = true;
             }
             gs_ordered_cta_kernel<KIND, EXACT, false><<<1, 32 * nw, stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D, cap, h->d_dbg);
         }
@@ -476,33 +491,9 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         CUDA_CHECK(cudaGetLastError());
         return;
     }
-    if (lv.strategy == 3 && KIND == 1 && EXACT && lv.dsmem_sh > 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cluster_dsmem_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cluster_dsmem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
-            attr_set = true;
-        }
-        const int nwc = std::max(1, std::min(CLUSTER_WARPS_CSR, (lv.max_width + CLUSTER_CTAS - 1) / CLUSTER_CTAS));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(CLUSTER_CTAS);
-        cfg.blockDim = dim3(32 * nwc);
-        cfg.dynamicSmemBytes = ((size_t)1 << lv.dsmem_sh) * sizeof(double) + (size_t)nwc * STAGE * sizeof(double);
-        cfg.stream = h->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = CLUSTER_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        CUDA_CHECK(cudaLaunchKernelEx(&cfg, gs_ordered_cluster_dsmem_kernel<true>, lv.A.v, (const double *)lv.b, lv.x, (const int *)lv.d_wf_item_ptr, lv.W, nsweeps, lv.dsmem_sh));
-        ++g_launches;
-        return;
-    }
     if (lv.strategy == 3) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (first_use(4)) {
             CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cluster_kernel<KIND, EXACT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            attr_set = true;
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(CLUSTER_CTAS);
@@ -520,18 +511,14 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         cfg.attrs = at;
         cfg.numAttrs = 1;
         if (KIND == 0 && lv.A.v.max_row <= 20) {
-            static bool attr_set1 = false;
-            if (!attr_set1) {
+            if (first_use(5)) {
                 CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cluster_kernel<KIND, EXACT, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-                attr_set1 = true;
             }
             CUDA_CHECK(cudaLaunchKernelEx(&cfg, gs_ordered_cluster_kernel<KIND, EXACT, true>, lv.A.v, (const double *)lv.b, lv.x, (const int *)lv.d_wf_item_ptr, lv.W, nsweeps, h->d_dbg));
         } else if (KIND == 0 && lv.A.v.max_row <= 28) {
             auto k28 = &gs_ordered_cluster_kernel<KIND, EXACT, true, 28>;
-            static bool attr_set2 = false;
-            if (!attr_set2) {
+            if (first_use(6)) {
                 CUDA_CHECK(cudaFuncSetAttribute(k28, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-                attr_set2 = true;
             }
             CUDA_CHECK(cudaLaunchKernelEx(&cfg, k28, lv.A.v, (const double *)lv.b, lv.x, (const int *)lv.d_wf_item_ptr, lv.W, nsweeps, h->d_dbg));
         } else
@@ -546,25 +533,8 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         }
         return;
     }
-    const int need = nsweeps * lv.W;
-    if (need > lv.cnt_cap) {
-        if (lv.d_cnt) dev_free(lv.d_cnt);
-        lv.d_cnt = dev_alloc<unsigned>(need);
-        lv.cnt_cap = need;
-    }
-    CUDA_CHECK(cudaMemsetAsync(lv.d_cnt, 0, (size_t)need * sizeof(unsigned), h->stream));
-    const int wpb = h->gs_block / 32;
-    int grid = (lv.max_width + wpb - 1) / wpb;
-    grid = std::max(1, std::min(grid, h->gs_max_blocks[KIND]));
-    const int items = lv.pass_items[0] + lv.pass_items[1];
-    DMat A = lv.A.v;
-    const double *b = lv.b; double *x = lv.x;
-    const int *iw = lv.d_item_wf, *wp = lv.d_wf_item_ptr;
-    unsigned *cnt = lv.d_cnt;
-    int W = lv.W, ips = items, ns = nsweeps;
-    void *args[] = {&A, &b, &x, &iw, &wp, &cnt, &W, &ips, &ns};
-    CUDA_CHECK(cudaLaunchCooperativeKernel((void *)gs_ordered_grid_kernel<KIND, EXACT>, dim3(grid), dim3(h->gs_block), args, 0, h->stream));
-    ++g_launches;
+    fprintf(stderr, "libamgb200: internal error: no smoother kernel for strategy %d\n", lv.strategy);
+    exit(71);
 }
 
 void smooth_level(amgb200_hier *h, Level &lv, int nsweeps) {
@@ -915,6 +885,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         printf("### ERROR: Wrong smoother type %d!\n", mg->pars.smoother);   // SSS_smooth.c:216-218
         exit(-12);
     }
+    if (mg->num_levels < 1 || mg->num_levels > 64) { fprintf(stderr, "libamgb200: %d levels (supported: 1..64)\n", mg->num_levels); exit(72); }
     amgb200_hier *h = new amgb200_hier();
     h->nl = mg->num_levels;
     h->pars = mg->pars;
@@ -935,20 +906,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         h->max_dyn_smem = smem_optin - 1024;
         if (!coop) { fprintf(stderr, "libamgb200: device lacks cooperative launch\n"); exit(70); }
     }
-    if (getenv("AMGB200_GS_BLOCK")) h->gs_block = std::max(32, std::min(BLOCK, atoi(getenv("AMGB200_GS_BLOCK")) / 32 * 32));
     h->exact = !opt.fast;
-    int per_sm = 0;
-    if (h->exact) {
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_ordered_grid_kernel<0, true>, h->gs_block, 0));
-        h->gs_max_blocks[0] = std::max(1, per_sm * h->num_sms);
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_ordered_grid_kernel<1, true>, h->gs_block, 0));
-        h->gs_max_blocks[1] = std::max(1, per_sm * h->num_sms);
-    } else {
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_ordered_grid_kernel<0, true>, h->gs_block, 0));
-        h->gs_max_blocks[0] = std::max(1, per_sm * h->num_sms);
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_ordered_grid_kernel<1, false>, h->gs_block, 0));
-        h->gs_max_blocks[1] = std::max(1, per_sm * h->num_sms);
-    }
     const double sell_max_mean = getenv("AMGB200_SELL_MAX_MEAN") ? atof(getenv("AMGB200_SELL_MAX_MEAN")) : (h->exact ? 48.0 : 24.0);
     const double cta_max_avg = getenv("AMGB200_CTA_MAX_AVG") ? atof(getenv("AMGB200_CTA_MAX_AVG")) : 6.0;
     const double stream_max_avg = getenv("AMGB200_STREAM_MAX_AVG") ? atof(getenv("AMGB200_STREAM_MAX_AVG")) : 12.0;
@@ -1042,7 +1000,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             lv.chain_terms += longest;
         }
     }
-    // 0 parallel passes | 2 one CTA (narrow wavefronts) | 3 one 16-CTA cluster | 1 cooperative grid (fallback)
+    // 0 parallel passes | 2 one CTA (narrow wavefronts) | 3 one 16-CTA cluster | 4 / 5 streaming CTA / cluster | 6 data-flow grid
     if (!lv.ordered) lv.strategy = 0;
     else lv.strategy = ((double)wip[lv.W] / lv.W <= cta_max_avg) ? 2 : 3;
     {
@@ -1069,15 +1027,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             lv.cta_cap = cap >= 128 ? cap : 0;
         }
     }
-    // measured on B200 (128^3, levels 2-4): scattered 8-byte remote shared-memory gathers are SLOWER than L2 gathers
-    // (5.0 / 2.8 / 4.8 ms per sweep vs 2.8 / 2.3 / 4.5 ms), so the distributed-x variant is opt-in only
-    if (lv.strategy == 3 && lay.kind == KIND_CSR && h->exact && getenv("AMGB200_DSMEM_X") && atoi(getenv("AMGB200_DSMEM_X"))) {
-        int sh = 6;
-        while (((long long)CLUSTER_CTAS << sh) < lv.n) ++sh;
-        const int nwc = std::max(1, std::min(CLUSTER_WARPS_CSR, (lv.max_width + CLUSTER_CTAS - 1) / CLUSTER_CTAS));
-        if (((size_t)1 << sh) * 8 + (size_t)nwc * STAGE * 8 <= (size_t)h->max_dyn_smem) lv.dsmem_sh = sh;
-    }
-    if (getenv("AMGB200_GS_STRATEGY") && lv.ordered) lv.strategy = std::max(1, std::min(3, atoi(getenv("AMGB200_GS_STRATEGY"))));
+    if (getenv("AMGB200_GS_STRATEGY") && lv.ordered) lv.strategy = atoi(getenv("AMGB200_GS_STRATEGY")) <= 2 ? 2 : 3;       // (tests: force the CTA / cluster barrier kernels)
     // streaming single-CTA smoother: warp-per-row EXACT levels whose x vector plus a ring of at least two of the
     // largest wavefront blocks fit in shared memory
     if (lv.ordered && lay.kind == KIND_CSR && h->exact && !getenv("AMGB200_GS_STRATEGY") && (double)wip[lv.W] / lv.W <= stream_max_avg) {
@@ -1277,6 +1227,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     h->d_scal = dev_alloc<double>(8);
     {
         // pinned read-back slots are recycled across hierarchies (cudaMallocHost / cudaFreeHost cost up to tens of milliseconds each)
+        std::lock_guard<std::mutex> lk(global_mutex());
         std::vector<double *> &fl = pinned_scalars();
         if (!fl.empty()) { h->h_scal = fl.back(); fl.pop_back(); }
         else CUDA_CHECK(cudaMallocHost((void **)&h->h_scal, 8 * sizeof(double)));
@@ -1296,7 +1247,6 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                    lv.pass_rows[0], lv.wf_count[0], lv.wf_count[1], lv.P.valid ? lv.P.nnz : 0LL, lv.R.valid ? lv.R.nnz : 0LL, (int)lv.pattern_symmetric);
             printf("      strategy %d%s  max wavefront width %d items\n", lv.strategy, lv.x_in_smem ? " (x in smem)" : "", lv.max_width);
             if (lv.strategy == 2) printf("      CTA pipeline: %d groups x %d warps, parked suffix capacity %d\n", lv.cta_D, lv.cta_G, lv.cta_cap);
-            if (lv.strategy == 3 && lv.dsmem_sh) printf("      x distributed over the cluster's shared memory: %d rows per CTA\n", 1 << lv.dsmem_sh);
         }
     }
     return h;
@@ -1308,18 +1258,18 @@ void amgb200_free(amgb200_hier *h) {
     for (Level &lv : h->L) {
         lv.A.release(); lv.Asp.release(); lv.P.release(); lv.R.release();
         dev_free(lv.d_order); dev_free(lv.x); dev_free(lv.b); dev_free(lv.wp);
-        dev_free(lv.d_item_wf); dev_free(lv.d_wf_item_ptr); dev_free(lv.d_cnt); dev_free(lv.d_fb); dev_free(lv.d_stream); dev_free(lv.d_blk_ptr); dev_free(lv.d_wf_row_ptr);
+        dev_free(lv.d_item_wf); dev_free(lv.d_wf_item_ptr); dev_free(lv.d_fb); dev_free(lv.d_stream); dev_free(lv.d_blk_ptr); dev_free(lv.d_wf_row_ptr);
         dev_free(lv.d_rec); dev_free(lv.d_hint);
         if (lv.bk) {
             dev_free(lv.bk->d_rec); dev_free(lv.bk->d_hint);
             lv.bk->A.release();
             dev_free(lv.bk->x); dev_free(lv.bk->b);
-            dev_free(lv.bk->d_item_wf); dev_free(lv.bk->d_wf_item_ptr); dev_free(lv.bk->d_cnt); dev_free(lv.bk->d_stream); dev_free(lv.bk->d_blk_ptr); dev_free(lv.bk->d_wf_row_ptr);
+            dev_free(lv.bk->d_item_wf); dev_free(lv.bk->d_wf_item_ptr); dev_free(lv.bk->d_stream); dev_free(lv.bk->d_blk_ptr); dev_free(lv.bk->d_wf_row_ptr);
             delete lv.bk;
         }
     }
     dev_free(h->d_partial); dev_free(h->d_scal);
-    if (h->h_scal) pinned_scalars().push_back(h->h_scal);
+    if (h->h_scal) { std::lock_guard<std::mutex> lk(global_mutex()); pinned_scalars().push_back(h->h_scal); }
     dev_free(h->d_xnat); dev_free(h->d_bnat); dev_free(h->kry); dev_free(h->d_dbg);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -1388,7 +1338,7 @@ const char *amgb200_level_kernel(const amgb200_hier *h, int level) {
     check_level(h, level);
     const Level &lv = h->L[level];
     if (!lv.smoothed) return "none";
-    static const char *names[7] = {"gs_pass_kernel", "gs_ordered_grid_kernel", "gs_ordered_cta_kernel", "gs_ordered_cluster_kernel", "gs_stream_cta_kernel", "gs_stream_cluster_kernel", "gs_dataflow_kernel"};
+    static const char *names[7] = {"gs_pass_kernel", "-", "gs_ordered_cta_kernel", "gs_ordered_cluster_kernel", "gs_stream_cta_kernel", "gs_stream_cluster_kernel", "gs_dataflow_kernel"};
     return names[lv.strategy];
 }
 
@@ -1434,6 +1384,7 @@ amgb200_rtn amgb200_solve_device(amgb200_hier *h, double *d_x, const double *d_b
     if (fabs(sumb) == 0.) {                                                   // SSS_SOLVE.c:41-46
         CUDA_CHECK(cudaMemsetAsync(d_x, 0, (size_t)l0.n * sizeof(double), h->stream));
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        if (t0) { cudaEventDestroy(t0); cudaEventDestroy(t1); }
         return rtn;
     }
     int iter = 0;
@@ -1601,11 +1552,14 @@ void amgb200_l0_shape(const amgb200_hier *h, long long info[8]) {
     info[0] = lv.n; info[1] = lv.pass_rows[0]; info[2] = lv.pass_items[0]; info[3] = lv.pass_items[1];
     info[4] = lv.A.v.kind; info[5] = (lv.smoothed && !lv.ordered) ? 1 : 0; info[6] = lv.A.v.kind == KIND_SELL ? 32 : 1;
     info[7] = lv.P.valid ? lv.P.v.nitems : 0;
+    // (the item ranges of amgb200_l0_prolong are derived from row ranges with info[6]: only meaningful when P uses A's layout kind)
+    if (lv.P.valid && lv.P.v.kind != lv.A.v.kind) info[5] = 0;
 }
 // one Gauss-Seidel pass (0 = F, 1 = C) over the pass-relative item range [item0, item1) of level 0
 void amgb200_l0_gs_pass(amgb200_hier *h, int pass, int item0, int item1) {
     Level &lv = h->L[0];
     if (!lv.smoothed || lv.ordered) { fprintf(stderr, "libamgb200: level 0 is not two-colour; it cannot be sharded\n"); exit(73); }
+    if (pass < 0 || pass > 1 || item0 < 0 || item1 > lv.pass_items[pass]) { fprintf(stderr, "libamgb200: item range [%d,%d) outside pass %d (%d items)\n", item0, item1, pass, pass >= 0 && pass <= 1 ? lv.pass_items[pass] : 0); exit(72); }
     const int base = pass ? lv.pass_items[0] : 0;
     const int cnt = item1 - item0;
     if (cnt <= 0) return;
@@ -1618,6 +1572,7 @@ void amgb200_l0_gs_pass(amgb200_hier *h, int pass, int item0, int item1) {
 // wp = b - A x on the absolute item range [item0, item1) of level 0's smoother layout
 void amgb200_l0_residual(amgb200_hier *h, int item0, int item1) {
     Level &lv = h->L[0];
+    if (item0 < 0 || item1 > lv.A.v.nitems) { fprintf(stderr, "libamgb200: item range [%d,%d) outside level 0 (%d items)\n", item0, item1, lv.A.v.nitems); exit(72); }
     if (item1 <= item0) return;
     h->item0 = item0; h->item1 = item1;
     spmv(h, lv.A.v, MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0);
@@ -1626,6 +1581,8 @@ void amgb200_l0_residual(amgb200_hier *h, int item0, int item1) {
 // x_0 += P_0 x_1 on the item range [item0, item1) of P_0 (32 schedule rows per item for SELL)
 void amgb200_l0_prolong(amgb200_hier *h, int item0, int item1) {
     Level &lv = h->L[0];
+    if (!lv.P.valid) { fprintf(stderr, "libamgb200: level 0 has no transfer operators\n"); exit(72); }
+    if (item0 < 0 || item1 > lv.P.v.nitems) { fprintf(stderr, "libamgb200: item range [%d,%d) outside P_0 (%d items)\n", item0, item1, lv.P.v.nitems); exit(72); }
     if (item1 <= item0) return;
     h->item0 = item0; h->item1 = item1;
     spmv(h, lv.P.v, MODE_AMXPY, RED_NONE, h->L[1].x, lv.x, nullptr, 1.0);
@@ -1634,7 +1591,9 @@ void amgb200_l0_prolong(amgb200_hier *h, int item0, int item1) {
 // b_{level+1} = R_level wp_level ; x_{level+1} = 0   (SSS_cycle.cu:921,929)
 void amgb200_restrict_from(amgb200_hier *h, int level) {
     check_level(h, level);
+    check_level(h, level + 1);
     Level &lv = h->L[level];
+    if (!lv.R.valid) { fprintf(stderr, "libamgb200: level %d has no transfer operators\n", level); exit(72); }
     spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[level + 1].b, nullptr, 0.0);
     dev_zero(h, h->L[level + 1].n, h->L[level + 1].x);
 }
@@ -1661,27 +1620,6 @@ __attribute__((visibility("default"))) long long amgb200_debug_quotient_check(lo
     CUDA_CHECK(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
     CUDA_CHECK(cudaFree(d_bad));
     return (long long)bad;
-}
-// test hook: rows (of `trials` x 4 x blocks generated rows) for which scan_fold_slots differs from the sequential fp64 chain
-__attribute__((visibility("default"))) long long amgb200_debug_scanfold_check(int blocks, int trials, unsigned long long seed, int mode, int sub, double *cycles_per_term) {
-    unsigned long long *d_out = nullptr, out[4] = {0, 0, 0, 0};
-    CUDA_CHECK(cudaMalloc(&d_out, sizeof(out)));
-    CUDA_CHECK(cudaMemset(d_out, 0, sizeof(out)));
-    scanfold_check_kernel<<<blocks, 128>>>(trials, seed, mode, sub, d_out);
-    ++g_launches;
-    CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaMemcpy(out, d_out, sizeof(out), cudaMemcpyDeviceToHost));
-    CUDA_CHECK(cudaFree(d_out));
-#ifdef AMGB200_SF_TIMING
-    { unsigned long long c[8]; CUDA_CHECK(cudaMemcpyFromSymbol(c, sf_cyc, sizeof(c))); const double it = (double)std::max(1ULL, c[4]);
-      printf("[sf] per iteration: load %.0f (per round)  loop top %.0f  compose %.0f  scan %.0f  tail %.0f cycles; %llu iterations\n", c[0] / it, c[5] / it, c[1] / it, c[2] / it, c[3] / it, c[4]);
-      unsigned long long z[8] = {0}; CUDA_CHECK(cudaMemcpyToSymbol(sf_cyc, z, sizeof(z))); }
-#endif
-    if (cycles_per_term && out[3]) {                       // warp-level cycles per term of the longest slot: sequential chain, scan fold
-        cycles_per_term[0] = (double)out[1] / (double)out[3];
-        cycles_per_term[1] = (double)out[2] / (double)out[3];
-    }
-    return (long long)out[0];
 }
 void amgb200_sync(amgb200_hier *h) { CUDA_CHECK(cudaStreamSynchronize(h->stream)); }
 

@@ -87,16 +87,6 @@ struct GlobalX {                       // global memory (or this CTA's shared me
     __device__ __forceinline__ double ld(int j) const { return ld_x<COH>(x + j); }
     __device__ __forceinline__ void st(int k, double v) const { x[k] = v; }
 };
-struct ClusterX {                      // distributed over the shared memory of the CTAs of a cluster: row k lives in CTA k >> sh
-    double *xs;                        // this CTA's slice
-    int sh, mask;
-    __device__ __forceinline__ double *at(int j) const {
-        return cooperative_groups::this_cluster().map_shared_rank(xs, j >> sh) + (j & mask);
-    }
-    __device__ __forceinline__ double ld(int j) const { return *at(j); }
-    __device__ __forceinline__ void st(int k, double v) const { *at(k) = v; }
-};
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(FULL, v, o));
@@ -594,50 +584,6 @@ __global__ void __launch_bounds__(BLOCK) gs_pass_kernel(DMat A, const double *__
     }
 }
 
-// Ordered sweeps across the grid: persistent warps walk the item list of nsweeps x (F pass, C pass)
-// in schedule order; an item of (global) wavefront g starts when the completion counter of
-// wavefront g-1 has reached that wavefront's item count.  All warps must be co-resident
-// (cooperative launch).  cnt[] holds nsweeps*W zero-initialised counters.  The matrix entries of an
-// item are fetched before the wait.
-template <int KIND, bool EXACT>
-__global__ void __launch_bounds__(BLOCK) gs_ordered_grid_kernel(DMat A, const double *__restrict__ b, double *x,
-                                                                const int *__restrict__ item_wf, const int *__restrict__ wf_item_ptr,
-                                                                unsigned *cnt, int W, int items_per_sweep, int nsweeps) {
-    __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * STAGE : 1];
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const long long total = (long long)items_per_sweep * nsweeps;
-    int known = -1;                               // highest global wavefront known to be complete
-    int sweep = 0, it = warp;                     // (sweep, item) of work unit t, tracked without divisions
-    while (it >= items_per_sweep) { it -= items_per_sweep; ++sweep; }
-    for (long long t = warp; t < total; t += nwarps) {
-        const int wl = item_wf[it];
-        const int g = sweep * W + wl;
-        SellItem<20> ws;
-        CsrItem wc;
-        if constexpr (KIND == 0) ws.prologue(A, it, lane, b); else wc.prologue(A, it, lane, b);
-        if (g - 1 > known) {
-            if (lane == 0) {
-                const int pw = wl == 0 ? W - 1 : wl - 1;
-                const unsigned need = (unsigned)(wf_item_ptr[pw + 1] - wf_item_ptr[pw]);
-                const volatile unsigned *c = cnt + (g - 1);
-                while (*c < need) { }
-            }
-            __syncwarp();
-            __threadfence();
-            known = g - 1;
-        }
-        if constexpr (KIND == 0) gs_finish_sell<true>(ws, x);
-        else gs_finish_csr<true, EXACT>(A, wc, x, lane, sprod + (threadIdx.x >> 5) * STAGE);
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(cnt + g, 1u);
-        it += nwarps;
-        while (it >= items_per_sweep) { it -= items_per_sweep; ++sweep; }
-    }
-}
-
 // Ordered sweeps inside ONE thread block (levels whose wavefronts are narrow).  The block's G*D
 // warps form D groups of G warps; group (g mod D) owns wavefront g: its warps take the wavefront's
 // items round-robin.  A group fetches the matrix entries (row pointers, col, val, b) of its next
@@ -890,135 +836,6 @@ __device__ __forceinline__ double chain_fold_slots(double t, unsigned sp, int cn
     if (q + 8 < maxc) { AMGB200_FOLD(v1) }
 #undef AMGB200_FOLD
 #undef AMGB200_LOAD
-    return t;
-}
-
-// ------------------------------------------------------------------------------------------
-// scan_fold_slots: the same in-order fold  t <- RN(t - p_q), q = 0 .. cnt-1  as chain_fold_slots, bit for bit, but in
-// O(log) dependent steps per 8*sub terms instead of one dependent DSUB (8.1 cycles) per term.
-//
-// While the running sum stays inside one binade [2^E, 2^(E+1)) every partial sum is an integer multiple N*u of u = 2^(E-52)
-// with 2^52 <= |N| < 2^53, and RN(N*u - p) = u * RNE(N - p/u): with p/u = I + f, I = nearest integer, this is N - I unless
-// f is exactly a half -- then (I := floor(p/u), M := N - I) the exact value M - 1/2 goes to the EVEN neighbour, M - (M & 1).
-// So one term is the integer map  N -> N - D[N & 1]  with two constants D[0], D[1]; such maps compose into maps of the same
-// form (D[b] = A.D[b] + B.D[(b - A.D[b]) & 1]) -- an associative operation, i.e. a parallel prefix scan reproduces the
-// sequentially rounded sums EXACTLY as long as no partial sum leaves the binade.  Each lane of a slot folds one 8-term
-// block into such a map (tracking the range of its partial sums), a shuffle scan over the slot's lanes gives every block its
-// starting value, and every block checks that all its partial sums stay in [2^52 + 1, 2^53 - 2] (conservatively, in units of
-// 2^32).  The first block that fails (a binade crossing: 1-3 per row on the AMG levels, tools/chain_stats in DESIGN.md) is
-// folded by real DSUBs from its exact starting value and the scan resumes behind it with the new binade.  Terms that cannot
-// be scaled (non-finite, or 2^9 times larger than the sum) and sums that are zero / subnormal / non-finite take the same
-// DSUB path, so the function is total.  Validated against the sequential chain on the device (amgb200_debug_scanfold_check:
-// random magnitudes, exact ties, cancellation, zeros, growth) and by every parity test of the smoothers that use it.
-// All lanes of the warp must call it together; the result is valid in every lane of the slot.  cnt, maxc multiples of 8.
-struct FoldMap { long long d0, d1; };
-#ifdef AMGB200_SF_TIMING
-__device__ unsigned long long sf_cyc[8];
-#define SF_CLK(i) { const long long c_ = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&sf_cyc[i], (unsigned long long)(c_ - sfc)); sfc = c_; }
-#else
-#define SF_CLK(i)
-#endif
-__device__ __forceinline__ double scan_fold_slots(double t, unsigned sp, int cnt, int maxc, int sub, int lis, unsigned zeros) {
-    const long long LO = (1LL << 52) + 1, HI = (1LL << 53) - 2;
-    for (int q0 = 0; q0 < maxc; q0 += 8 * sub) {
-        // my block of the round: 8 consecutive terms (blocks past the slot's own cnt are exact no-ops)
-        const int qb = q0 + 8 * lis;
-        const unsigned src = qb < cnt ? sp + 8u * (unsigned)qb : zeros;
-        double p[8];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const double2 v = lds_v2f64(src + 16u * u); p[2 * u] = v.x; p[2 * u + 1] = v.y; }
-        int lo = 0;                                   // blocks [0, lo) of the round are folded into t
-#ifdef AMGB200_SF_TIMING
-        long long sfc = clock64();
-        { double sink = p[0] + p[7]; if (sink == 1.2345e300) t = 0; }
-        SF_CLK(0)
-#endif
-        while (__any_sync(FULL, lo < sub)) {
-            SF_CLK(5)
-            const unsigned long long tb = (unsigned long long)__double_as_longlong(t);
-            const int eb = (int)((tb >> 52) & 0x7ff);
-            const bool scal = eb >= 54 && eb <= 2046 && lo < sub;             // a binade the integer picture can represent
-            const double sc = __longlong_as_double((long long)(2098 - (scal ? eb : 1075)) << 52);      // 2^(52-E)
-            const double usc = __longlong_as_double((long long)((scal ? eb : 1075) - 52) << 52);       // 2^(E-52)
-            const long long n0 = __double2ll_rn(__dmul_rn(t, sc));
-            const bool neg = n0 < 0;
-            // ---- my block as a map under this binade
-            FoldMap m = {0, 0};
-            int mxh = -(1 << 30), mnh = 1 << 30;
-            bool bad = false;
-            if (lis >= lo) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const double q = __dmul_rn(p[u], sc);
-                    bad |= !(fabs(q) < 0x1p57);                            // (8 such terms cannot overflow the offsets)
-                    const double qr = rint(q);
-                    long long I = __double2ll_rn(q);
-                    const double fr = __dsub_rn(q, qr);
-                    const bool tie = fabs(fr) == 0.5;
-                    if (fr == -0.5) I -= 1;                                   // ties: I = floor(p/u)
-                    long long a0 = m.d0 + I, a1 = m.d1 + I;                   // N - a = the sum before a tie is resolved
-                    const int h = (int)(a0 >> 32);
-                    mxh = max(mxh, h); mnh = min(mnh, h);
-                    if (tie) { a0 += a0 & 1; a1 += (a1 & 1) ^ 1; }            // parity of N - a for start parity 0 / 1: odd -> one further down
-                    m.d0 = a0; m.d1 = a1;
-                }
-            }
-#ifdef AMGB200_SF_TIMING
-            if (m.d0 == 0x7fffffffffffffffLL) t = 0;
-#endif
-            SF_CLK(1)
-            // ---- inclusive scan of the maps over the lanes of the slot
-            FoldMap inc = m;
-            for (int dlt = 1; dlt < sub; dlt <<= 1) {
-                FoldMap a;
-                a.d0 = __shfl_up_sync(FULL, inc.d0, dlt, sub);
-                a.d1 = __shfl_up_sync(FULL, inc.d1, dlt, sub);
-                if (lis >= dlt) {                                             // a (earlier blocks) then inc
-                    const long long c0 = a.d0 + ((a.d0 & 1) ? inc.d1 : inc.d0);
-                    const long long c1 = a.d1 + (((1 - a.d1) & 1) ? inc.d1 : inc.d0);
-                    inc.d0 = c0; inc.d1 = c1;
-                }
-            }
-#ifdef AMGB200_SF_TIMING
-            if (inc.d0 == 0x7fffffffffffffffLL) t = 0;
-#endif
-            SF_CLK(2)
-            // ---- my starting value, the validity of my block, the first block of the slot that fails
-            FoldMap exc;
-            exc.d0 = __shfl_up_sync(FULL, inc.d0, 1, sub);
-            exc.d1 = __shfl_up_sync(FULL, inc.d1, 1, sub);
-            if (lis == 0) { exc.d0 = 0; exc.d1 = 0; }
-            const long long nst = n0 - ((n0 & 1) ? exc.d1 : exc.d0);
-            // all partial sums of my block lie in [nst - ((mxh + 2) << 32), nst - ((mnh - 1) << 32)]
-            const long long vlo = nst - ((long long)(mxh + 2) << 32), vhi = nst - ((long long)(mnh - 1) << 32);
-            bool ok = scal && !bad && (neg ? (vlo >= -HI && vhi <= -LO) : (vlo >= LO && vhi <= HI));
-            if (lis < lo) ok = true;
-            const unsigned okm = __ballot_sync(FULL, ok);
-            const unsigned smask = sub == 32 ? FULL : ((1u << sub) - 1u) << ((threadIdx.x & 31) - lis);
-            const unsigned fail = ~okm & smask;
-            const int first = fail ? (__ffs(fail) - 1) - ((int)(threadIdx.x & 31) - lis) : sub;     // first failing block of my slot
-            // value in front of block `first` (or behind the last block of the round): exact
-            const bool act = lo < sub;
-            const long long nsrc = __shfl_sync(FULL, first < sub ? nst : n0 - ((n0 & 1) ? inc.d1 : inc.d0), first < sub ? first : sub - 1, sub);
-            const double tn = scal ? __dmul_rn(__ll2double_rn(nsrc), usc) : t;
-            // the failing block by real subtractions (its owner holds the terms); the scan then resumes behind it
-            double tf = tn;
-            if (act && lis == first) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) tf = __dsub_rn(tf, p[u]);
-            }
-            tf = __shfl_sync(FULL, tf, first < sub ? first : 0, sub);
-            if (act) {
-                if (first < sub) { t = tf; lo = first + 1; }
-                else { t = tn; lo = sub; }
-            }
-#ifdef AMGB200_SF_TIMING
-            if (t == 1.2345e300) lo = 0;
-            SF_CLK(3)
-            if ((threadIdx.x & 31) == 0) atomicAdd(&sf_cyc[4], 1ULL);
-#endif
-        }
-    }
     return t;
 }
 
@@ -1692,61 +1509,6 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CLUSTER_WARPS_SELL : 32 * CLU
 #endif
 }
 
-// Same walk, warp-per-row EXACT rows, with the x vector of the level DISTRIBUTED over the shared memory of the
-// 16 CTAs (row k in CTA k >> sh): gathers are remote shared-memory loads (~215 cycles instead of an L2 round trip)
-// and a finished row is a remote shared-memory store, so the release half of the cluster barrier does not wait for
-// a global store to reach L2.  Levels with n <= 16 * 2^sh rows, 2^sh * 8 bytes + staging <= 227 KB.
-// Dynamic shared memory: [x slice: 2^sh doubles] [nwarps * STAGE doubles]
-template <bool EXACT>
-__global__ void __launch_bounds__(32 * CLUSTER_WARPS_CSR) gs_ordered_cluster_dsmem_kernel(
-    DMat A, const double *__restrict__ b, double *xg, const int *__restrict__ wf_item_ptr, int W, int nsweeps, int sh) {
-    extern __shared__ double dyn_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nw = blockDim.x >> 5;
-    const int rank = (int)cluster_ctarank();
-    const int gw = warp * CLUSTER_CTAS + rank;
-    const int TW = CLUSTER_CTAS * nw;
-    const int totalw = W * nsweeps;
-    const int chunk = 1 << sh, n = A.nrows;
-    double *xs = dyn_smem;
-    double *sp = dyn_smem + chunk + warp * STAGE;
-    for (int i = threadIdx.x; i < chunk; i += blockDim.x) { const int k = rank * chunk + i; xs[i] = k < n ? xg[k] : 0.0; }
-    cluster_arrive(); cluster_wait();
-    const ClusterX xa{xs, sh, chunk - 1};
-    auto finish = [&](CsrItem &w) {
-        const double t = EXACT ? csr_chain_run_x<ClusterX, true>(A, w, xa, w.bk, lane, sp) : 0.0;
-        const double d = csr_diag(w);
-        if (lane == 0 && fabs(d) > GS_TINY) xa.st(w.k, gs_quotient(t, d, A.recip));
-    };
-    int wl2 = 2 % W;
-    int a0 = wf_item_ptr[0], a1 = wf_item_ptr[1];
-    int b0 = wf_item_ptr[1 % W], b1 = wf_item_ptr[1 % W + 1];
-    int c0 = wf_item_ptr[wl2], c1 = wf_item_ptr[wl2 + 1];
-    CsrItem cur;
-    CsrItem::Desc dn = {};
-    bool have = a0 + gw < a1, have_n = b0 + gw < b1;
-    if (have) cur.prologue(A, a0 + gw, lane, b);
-    if (have_n) dn = CsrItem::load_desc(A, b0 + gw);
-    for (int g = 0; g < totalw; ++g) {
-        if (have) {
-            finish(cur);
-            for (int it = a0 + gw + TW; it < a1; it += TW) { cur.prologue(A, it, lane, b); finish(cur); }
-        }
-        if (g + 1 < totalw) {
-            cluster_arrive();
-            a0 = b0; a1 = b1; have = have_n;
-            if (have) cur.load_entries(A, dn, lane, b);
-            b0 = c0; b1 = c1; have_n = b0 + gw < b1;
-            if (have_n) dn = CsrItem::load_desc(A, b0 + gw);
-            if (++wl2 == W) wl2 = 0;
-            c0 = wf_item_ptr[wl2]; c1 = wf_item_ptr[wl2 + 1];
-            cluster_wait();
-        }
-    }
-    cluster_arrive(); cluster_wait();            // every remote access to my slice is done
-    for (int i = threadIdx.x; i < chunk; i += blockDim.x) { const int k = rank * chunk + i; if (k < n) xg[k] = xs[i]; }
-}
-
 // ==========================================================================================
 // Data-flow ("sync-free") ordered Gauss-Seidel for WIDE levels: the whole GPU, no wavefront barriers.
 //
@@ -2177,75 +1939,6 @@ __global__ void __launch_bounds__(BLOCK) quotient_check_kernel(long long n, unsi
 // rows taken in `order` (schedule position -> natural row, or identity), columns renumbered through `col_pos`, padding
 // col = -1 / val = +0.0, row-internal storage order untouched.  Writes are fully coalesced; the host only computes the O(rows)
 // slice table (analysis.cpp: build_sell_structure).
-// test hook: scan_fold_slots against the sequential chain on generated rows (see its comment); counts rows whose results differ in any bit
-__device__ __forceinline__ unsigned long long sf_rng(unsigned long long &s) {
-    s += 0x9E3779B97F4A7C15ULL;
-    unsigned long long z = s;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    return z ^ (z >> 31);
-}
-__device__ __forceinline__ double sf_unit(unsigned long long &s) { return (double)(sf_rng(s) >> 11) * 0x1p-53; }
-__global__ void __launch_bounds__(128) scanfold_check_kernel(int trials, unsigned long long seed, int mode, int sub, unsigned long long *out) {
-    __shared__ __align__(16) double terms[4][1024];
-    __shared__ __align__(16) double zeros[8];
-    if (threadIdx.x < 8) zeros[threadIdx.x] = 0.0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nactive = (mode >> 8) ? (mode >> 8) : 4;                         // (timing: warps per block that work)
-    mode &= 255;
-    if (warp >= nactive) return;
-    const int S = 32 / sub, slot = lane / sub, lis = lane - slot * sub;
-    const int region = 1024 / S;
-    double *mine = terms[warp] + slot * region;
-    unsigned long long bad = 0, iters = 0;
-    long long tch = 0, tsc = 0;
-    for (int tr = 0; tr < trials; ++tr) {
-        unsigned long long st = seed * 0x100000001B3ULL + ((unsigned long long)(blockIdx.x * 4 + warp) * (unsigned long long)trials + tr) * 64 + slot;
-        // slot-uniform draws first
-        const int cnt = 8 * (1 + (int)(sf_rng(st) % (unsigned)(region / 8)));
-        double t0 = (sf_unit(st) - 0.5) * exp2((double)((int)(sf_rng(st) % 41) - 20));
-        const int special = (int)(sf_rng(st) % 64);
-        if (mode == 4 && special == 0) t0 = 0.0;
-        if (mode == 4 && special == 1) t0 = 0x1p-1060;
-        if (mode == 4 && special == 2) t0 = __longlong_as_double(0x7ff0000000000000LL);
-        if (mode == 4 && special == 3) t0 = __longlong_as_double(0x7ff8000000000001LL);
-        if (mode == 4 && special == 4) t0 = -0.0;
-        const double ulp0 = exp2(floor(log2(fabs(t0) > 0 && isfinite(t0) ? fabs(t0) : 1.0)) - 52.0);
-        for (int q = lis; q < cnt; q += sub) {
-            unsigned long long sq = st + 0x1234567ULL * (unsigned long long)(q + 1);
-            double pv;
-            const double r1 = sf_unit(sq), r2 = sf_unit(sq);
-            const int k = (int)(sf_rng(sq) % 13);
-            switch (mode) {
-                case 0: pv = -t0 * r1 * exp2(-(double)(3 + k)); break;                                   // same-sign growth, realistic gaps
-                case 1: pv = (r1 - 0.5) * exp2((double)((int)(sf_rng(sq) % 61) - 30)); break;              // anything
-                case 2: pv = ((double)((int)(sf_rng(sq) % 17) - 8) + 0.5) * ulp0 * exp2((double)(k % 4)) * (r2 < 0.5 ? -1.0 : 1.0); break;   // exact ties
-                case 3: pv = t0 * (0.3 + 1.4 * r1) * (q & 1 ? -1.0 : 1.0); break;                        // cancellation, binade hopping
-                case 4: pv = k < 6 ? 0.0 : k < 8 ? 0x1p-1070 * r1 : k == 8 ? -0.0 : (r1 - 0.5) * fabs(t0) * 1e-3; break;
-                default: pv = -fabs(t0) * (t0 < 0 ? -1.0 : 1.0) * exp2(-(double)(5 + k)) * (0.5 + r1); break;  // growth by 2^-5..2^-17 steps
-            }
-            if (mode == 1 && (sf_rng(sq) % 97) == 0) pv = t0 * 1e6;
-            mine[q] = pv;
-        }
-        __syncwarp();
-        const int maxc = __reduce_max_sync(FULL, cnt);
-        const long long c0 = clock64();
-        double ref = chain_fold_slots(t0, smem_u32(mine), cnt, maxc, smem_u32(zeros));        // (the production chain: all slots at once)
-        const long long c1 = clock64();
-        const double got = scan_fold_slots(t0, smem_u32(mine), cnt, maxc, sub, lis, smem_u32(zeros));
-        const long long c2 = clock64();
-        double seq = t0;
-        if (lis == 0) for (int q = 0; q < cnt; ++q) seq = __dsub_rn(seq, mine[q]);
-        seq = __shfl_sync(FULL, seq, 0, sub);
-        if (lis == 0 && (__double_as_longlong(seq) != __double_as_longlong(got) || __double_as_longlong(seq) != __double_as_longlong(ref))) ++bad;
-        tch += c1 - c0; tsc += c2 - c1; iters += maxc;
-        __syncwarp();
-    }
-    if (bad) atomicAdd(out, bad);
-    if (lane == 0) { atomicAdd(out + 1, (unsigned long long)tch); atomicAdd(out + 2, (unsigned long long)tsc); atomicAdd(out + 3, iters); }
-}
-
 __global__ void __launch_bounds__(BLOCK) sell_fill_kernel(int nslices, const int *__restrict__ slice_row, const long long *__restrict__ slice_ptr,
                                                            const int *__restrict__ order, const int *__restrict__ col_pos,
                                                            const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,

@@ -17,6 +17,15 @@ sys.path.insert(0, ROOT)
 from amg_b200 import capi  # noqa: E402
 
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+HOOKS_SO = os.path.join(ROOT, "tests", "libamgb200_testhooks.so")
+
+
+def test_hooks():
+    """tests/libamgb200_testhooks.so: CPU emulations of the wavefront schedule and the device layouts (amg_b200/csrc/debug_host.cpp),
+    built next to the product but not part of it"""
+    if not os.path.exists(HOOKS_SO):
+        raise RuntimeError("tests/libamgb200_testhooks.so missing: run `make`")
+    return C.CDLL(HOOKS_SO)
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 

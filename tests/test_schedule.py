@@ -7,9 +7,10 @@ import ctypes as C
 import numpy as np
 import pytest
 
+import oracle_ffi
 from amg_b200 import HostHierarchy, capi, generate
 
-L = capi.lib()
+L = oracle_ffi.test_hooks()
 L.amgb200_debug_gs_walk.argtypes = [C.POINTER(capi.Mat), capi.c_int_p, C.c_int, C.c_int, capi.c_double_p, capi.c_double_p]
 L.amgb200_debug_schedule.restype = C.c_int
 L.amgb200_debug_schedule.argtypes = [C.POINTER(capi.Mat), capi.c_int_p, capi.c_int_p, capi.c_int_p, C.c_int, capi.c_int_p]

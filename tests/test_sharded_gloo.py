@@ -27,7 +27,7 @@ class CpuBackend:
         self.O.orc_gs_rowlist.argtypes = [C.POINTER(capi.Mat), dp, dp, ip, C.c_int]
         self.O.orc_resid_rowlist.argtypes = [C.POINTER(capi.Mat), dp, dp, dp, ip, C.c_int]
         self.O.orc_amxpy_rowlist.argtypes = [C.c_double, C.POINTER(capi.Mat), dp, dp, ip, C.c_int]
-        L = capi.lib()
+        L = oracle_ffi.test_hooks()
         L.amgb200_debug_schedule.restype = C.c_int
         L.amgb200_debug_schedule.argtypes = [C.POINTER(capi.Mat), ip, ip, ip, C.c_int, ip]
         c0 = hier.level(0)
