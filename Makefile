@@ -13,7 +13,7 @@ CPP_SRCS  := $(filter-out $(CSRC)/debug_host.cpp,$(wildcard $(CSRC)/*.cpp))
 OBJS      := $(CU_SRCS:.cu=.o) $(CPP_SRCS:.cpp=.o)
 HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/amg_b200.h
 
-all: amg_b200/libamgb200.so tests/libamgb200_testhooks.so oracle/liboracle.so
+all: amg_b200/libamgb200.so tests/libamgb200_testhooks.so oracle/liboracle.so oracle/libmatgen.so
 
 amg_b200/libamgb200.so: $(OBJS)
 	$(NVCC) -shared $(ARCH) -Xcompiler -fopenmp -o $@ $(OBJS) -lcudart
@@ -30,7 +30,10 @@ tests/libamgb200_testhooks.so: $(CSRC)/debug_host.o $(CSRC)/analysis.o
 oracle/liboracle.so: oracle/amg_oracle.c include/amg_b200.h
 	$(CC) -O2 -ffp-contract=off -fPIC -shared -o $@ oracle/amg_oracle.c -lm
 
+oracle/libmatgen.so: oracle/matgen.c
+	$(CC) -O2 -ffp-contract=off -fPIC -shared -o $@ oracle/matgen.c -lm
+
 clean:
-	rm -f $(CSRC)/*.o $(CSRC)/*.ptxas.log amg_b200/libamgb200.so tests/libamgb200_testhooks.so oracle/liboracle.so
+	rm -f $(CSRC)/*.o $(CSRC)/*.ptxas.log amg_b200/libamgb200.so tests/libamgb200_testhooks.so oracle/liboracle.so oracle/libmatgen.so
 
 .PHONY: all clean

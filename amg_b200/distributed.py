@@ -50,6 +50,19 @@ class Partition:
         return np.arange(a, b)
 
 
+def expand_ranges(starts, ends):
+    """concatenation of arange(s, e) for all (s, e), vectorised (level 0 of 256^3 has 2 million rows per rank)"""
+    lens = ends - starts
+    total = int(lens.sum())
+    if total == 0:
+        return np.zeros(0, np.int64)
+    out = np.ones(total, np.int64)
+    first = np.cumsum(lens) - lens                      # offset of every non-empty range in the output
+    nz = lens > 0
+    out[first[nz]] = starts[nz] - np.concatenate(([0], (ends[nz] - 1)[:-1]))
+    return np.cumsum(out)
+
+
 def ghost_lists(A_nat, order, part, rank):
     """For `rank`: ghosts[p][src] = schedule indices of pass-p x entries owned by `src` that this rank's
     rows of the OTHER pass (and, for the residual, of both passes) read.  Symmetric send lists follow by
@@ -61,9 +74,8 @@ def ghost_lists(A_nat, order, part, rank):
     for which in (0, 1):                      # ghost entries belonging to pass `which`
         reader_rows = np.concatenate([part.rows(rank, 0), part.rows(rank, 1)])
         nat = order[reader_rows]
-        starts, ends = A_nat.row_ptr[nat], A_nat.row_ptr[nat + 1]
-        idx = np.concatenate([np.arange(s, e) for s, e in zip(starts, ends)]) if len(nat) else np.zeros(0, np.int64)
-        cols = np.unique(pos[A_nat.col_idx[idx]])
+        starts, ends = A_nat.row_ptr[nat].astype(np.int64), A_nat.row_ptr[nat + 1].astype(np.int64)
+        cols = np.unique(pos[A_nat.col_idx[expand_ranges(starts, ends)]])
         cols = cols[(cols < part.nF) if which == 0 else (cols >= part.nF)]
         own = part.owner(cols)
         out[which] = {src: cols[own == src] for src in range(part.world) if src != rank and (own == src).any()}

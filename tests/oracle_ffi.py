@@ -44,6 +44,34 @@ def quiet():
         os.close(devnull)
 
 
+MATGEN_SO = os.path.join(ROOT, "oracle", "libmatgen.so")
+
+
+class MatGen:
+    """oracle/libmatgen.so: the synthetic operators of SURVEY.md Appendix B restated in plain C (oracle/matgen.c), so that the
+    reference arm of bench.py builds its input without loading libamgb200.so.  Returns (row_ptr, col_idx, val) numpy arrays."""
+    KINDS = {"p2d": 0, "p3d": 1, "aniso3d": 2, "v27": 3}
+
+    def __init__(self):
+        if not os.path.exists(MATGEN_SO):
+            raise RuntimeError("oracle/libmatgen.so missing: run `make`")
+        self.L = C.CDLL(MATGEN_SO)
+
+    def generate(self, kind, N, eps_z=1e-3):
+        class M(C.Structure):
+            _fields_ = [("num_rows", C.c_int), ("num_cols", C.c_int), ("num_nnzs", C.c_int), ("row_ptr", C.POINTER(C.c_int)),
+                        ("col_idx", C.POINTER(C.c_int)), ("val", C.POINTER(C.c_double))]
+        m = M()
+        rc = self.L.orc_generate(self.KINDS[kind], int(N), C.c_double(float(eps_z)), C.byref(m))
+        if rc != 0:
+            raise ValueError(f"orc_generate({kind},{N}) failed: {rc}")
+        rp = np.ctypeslib.as_array(m.row_ptr, shape=(m.num_rows + 1,)).copy()
+        ci = np.ctypeslib.as_array(m.col_idx, shape=(m.num_nnzs,)).copy()
+        va = np.ctypeslib.as_array(m.val, shape=(m.num_nnzs,)).copy()
+        self.L.orc_mat_free(C.byref(m))
+        return rp, ci, va
+
+
 def have_ref():
     return os.path.exists(os.path.join(REF_DIR, "libsss_ref_fix.so"))
 

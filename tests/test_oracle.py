@@ -135,6 +135,14 @@ def test_oracle_function_level_vs_reference(oracle, reference):
     assert xo.tobytes() == xr.tobytes()
 
 
+@pytest.mark.parametrize("case", [("p2d", 37, 0.0), ("p3d", 13, 0.0), ("aniso3d", 11, 1e-3), ("v27", 9, 0.0), ("v27", 16, 0.0)])
+def test_matgen_equals_product_generator(case):
+    """oracle/matgen.c (the generator the reference arm of bench.py uses) produces byte-identical CSR arrays to amgb200_generate"""
+    rp, ci, va = oracle_ffi.MatGen().generate(*case)
+    A = generate(*case)
+    assert rp.tobytes() == A.row_ptr.tobytes() and ci.tobytes() == A.col_idx.tobytes() and va.tobytes() == A.val.tobytes()
+
+
 def test_oracle_zero_rhs(oracle):
     A = generate("p2d", 16)
     hier = HostHierarchy(A, tol=1e-8)
