@@ -76,7 +76,7 @@ EXPORTS = [
     "amgb200_device_bytes", "amgb200_level_kernel", "amgb200_level_chain_terms", "amgb200_bench_solve",
     "amgb200_set_stream", "amgb200_level_vec", "amgb200_level_order", "amgb200_l0_shape", "amgb200_l0_gs_pass",
     "amgb200_l0_residual", "amgb200_l0_prolong", "amgb200_restrict_from", "amgb200_cycle_from",
-    "amgb200_vec_to_schedule", "amgb200_vec_to_natural", "amgb200_sync",
+    "amgb200_vec_to_schedule", "amgb200_vec_to_natural", "amgb200_sync", "amgb200_setup_ex", "amgb200_interp_device",
 ]
 
 _lib = None
@@ -126,6 +126,9 @@ def lib():
         L.amgb200_generate.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(Mat)]
         L.amgb200_mat_free.argtypes = [C.POINTER(Mat)]
         L.amgb200_setup.argtypes = [C.POINTER(Amg), C.POINTER(Mat), C.POINTER(Pars), C.c_int]
+        L.amgb200_setup_ex.argtypes = [C.POINTER(Amg), C.POINTER(Mat), C.POINTER(Pars), C.c_int, C.c_int]
+        L.amgb200_interp_device.restype = C.c_int
+        L.amgb200_interp_device.argtypes = [C.POINTER(Mat), c_int_p, C.POINTER(Mat), C.c_double]
         L.amgb200_amg_destroy.argtypes = [C.POINTER(Amg)]
         L.amgb200_default_pars.argtypes = [C.POINTER(Pars)]
         L.amgb200_last_level_ms.argtypes = [C.c_void_p, C.c_int, c_double_p]

@@ -458,6 +458,11 @@ extern "C" void amgb200_default_pars(amgb200_pars *p) {      // SSS_main.c:25-64
 }
 
 extern "C" void amgb200_setup(amgb200_amg *mg, const amgb200_mat *A, const amgb200_pars *pars, int verbose) {
+    const char *e = getenv("AMGB200_DEVICE_INTERP");
+    amgb200_setup_ex(mg, A, pars, verbose, e && atoi(e) ? AMGB200_SETUP_DEVICE_INTERP : 0);
+}
+
+extern "C" void amgb200_setup_ex(amgb200_amg *mg, const amgb200_mat *A, const amgb200_pars *pars, int verbose, int flags) {
     if (pars->cs_type != 1 || pars->interp_type != 1) {
         fprintf(stderr, "amgb200_setup: only RS coarsening (cs_type=1) with direct interpolation (interp_type=1) is implemented\n");
         exit(-12);
@@ -502,7 +507,8 @@ extern "C" void amgb200_setup(amgb200_amg *mg, const amgb200_mat *A, const amgb2
         L.cfmark.d = zalloc<int>((size_t)L.A.num_rows);
         memcpy(L.cfmark.d, mark.data(), (size_t)L.A.num_rows * sizeof(int));
         const double tt3 = omp_get_wtime();
-        interp_direct(L.A, mark.data(), L.P, *pars);
+        if (!((flags & AMGB200_SETUP_DEVICE_INTERP) && amgb200_interp_device(&L.A, mark.data(), &L.P, pars->trunc_threshold) == 0))
+            interp_direct(L.A, mark.data(), L.P, *pars);
         const double tt4 = omp_get_wtime();
         L.R = transpose(L.P);
         const double tt5 = omp_get_wtime();

@@ -89,14 +89,18 @@ def read_mtx(path):
 class HostHierarchy:
     """Host AMG hierarchy (an SSS_AMG) built by amgb200_setup."""
 
-    def __init__(self, A, tol=1e-8, verbose=0, **par_overrides):
+    def __init__(self, A, tol=1e-8, verbose=0, device_interp=False, **par_overrides):
+        """device_interp: interpolation weights + truncation on the GPU (amgb200_interp_device; same hierarchy bit for bit)"""
         self.A = A
         self.pars = capi.default_pars(tol)
         for k, v in par_overrides.items():
             setattr(self.pars, k, v)
         self.mg = capi.Amg()
         self._lib = capi.lib()
-        self._lib.amgb200_setup(C.byref(self.mg), C.byref(A.c), C.byref(self.pars), int(verbose))
+        if device_interp:
+            self._lib.amgb200_setup_ex(C.byref(self.mg), C.byref(A.c), C.byref(self.pars), int(verbose), 1)
+        else:
+            self._lib.amgb200_setup(C.byref(self.mg), C.byref(A.c), C.byref(self.pars), int(verbose))
         self._alive = True
 
     @property

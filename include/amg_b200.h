@@ -238,6 +238,16 @@ void amgb200_mat_free(amgb200_mat *A);
  * hierarchy that is bit-identical to the reference's.  Needed so the product runs without any
  * reference object; the reference's own setup can be used instead (it is the kept host). */
 void amgb200_setup(amgb200_amg *mg, const amgb200_mat *A, const amgb200_pars *pars, int verbose);
+/* flags & AMGB200_SETUP_DEVICE_INTERP: the interpolation weights, the coarse renumbering and the truncation of P are computed on
+ * the device (amgb200_interp_device) instead of the host loop -- the same hierarchy, bit for bit. */
+#define AMGB200_SETUP_DEVICE_INTERP 1
+void amgb200_setup_ex(amgb200_amg *mg, const amgb200_mat *A, const amgb200_pars *pars, int verbose, int flags);
+/* ---- 3b. setup step next to the hot path, on the device ---------
+ * Direct-interpolation weights + coarse numbering + truncation: replaces interp_DIR / interp_DIR_cuda + SSS_amg_interp_trunc
+ * (amg/Setup/SSS_inter.cu:400-547, :239-396, :16-102; the reference's kernel DIR_Step_1, :104-210, covers 131 072 rows only).
+ * P enters with the pattern the coarsening produced (col_idx = FINE indices of the interpolatory C points, val allocated) and
+ * leaves exactly as interp_DIR leaves it.  mark: 0 F, 1 C, 2 isolated.  Returns 0; 1 = a row has no stored diagonal, nothing done. */
+int amgb200_interp_device(const amgb200_mat *A, const int *mark, amgb200_mat *P, double trunc_threshold);
 void amgb200_amg_destroy(amgb200_amg *mg);
 void amgb200_default_pars(amgb200_pars *p);   /* SSS_main.c:25-64 */
 

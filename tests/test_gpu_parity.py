@@ -377,6 +377,38 @@ def test_quotient_fast_path(mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", [("p2d", 96, 0.0), ("p3d", 40, 0.0), ("aniso3d", 32, 1e-3), ("v27", 20, 0.0), ("p3d", 128, 0.0)])
+def test_device_interpolation_builds_the_same_hierarchy(case):
+    """direct-interpolation weights, coarse renumbering and truncation of P on the device (amgb200_interp_device, setup_dev.cu) against
+    the host loop that is byte-pinned to the reference's interp_DIR + SSS_amg_interp_trunc (Setup/SSS_inter.cu:400-547, :16-102;
+    tests/test_setup_parity.py): every array of every level of the resulting hierarchy (A, P, R, cfmark) is byte-identical -- P feeds
+    R = P^T and the Galerkin product, so one differing bit would show up on every coarser level.  For the sizes with a fixture the
+    sha256 of P is also compared with the one of the reference's own setup (tests/golden/golden.json)."""
+    import hashlib
+    import json
+    import os
+    kind, N, eps = case
+    A = generate(kind, N, eps)
+    host = HostHierarchy(A, tol=1e-8)
+    devh = HostHierarchy(A, tol=1e-8, device_interp=True)
+    assert host.table() == devh.table()
+    for l in range(host.num_levels):
+        for which in ("A", "P", "R"):
+            if which != "A" and l == host.num_levels - 1:
+                continue
+            a, b = host.level_matrix(l, which), devh.level_matrix(l, which)
+            assert a.row_ptr.tobytes() == b.row_ptr.tobytes() and a.col_idx.tobytes() == b.col_idx.tobytes() and a.val.tobytes() == b.val.tobytes(), (l, which)
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json")))
+    name = f"{kind}{N}"
+    if name in gold:
+        for l in range(devh.num_levels - 1):
+            P = devh.level_matrix(l, "P")
+            assert hashlib.sha256(P.val.tobytes()).hexdigest() == gold[name]["levels"][l]["P"]["val"]
+            assert hashlib.sha256(P.col_idx.tobytes()).hexdigest() == gold[name]["levels"][l]["P"]["col_idx"]
+    host.close(); devh.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["p3d16", "v27_12"])
 def test_host_and_device_sell_fill_agree(name, oracle, monkeypatch):
     """SELL-32 layouts permuted/padded on the device (sell_fill_kernel, the default) and on the host
