@@ -77,6 +77,7 @@ EXPORTS = [
     "amgb200_set_stream", "amgb200_level_vec", "amgb200_level_order", "amgb200_l0_shape", "amgb200_l0_gs_pass",
     "amgb200_l0_residual", "amgb200_l0_prolong", "amgb200_restrict_from", "amgb200_cycle_from",
     "amgb200_vec_to_schedule", "amgb200_vec_to_natural", "amgb200_sync", "amgb200_setup_ex", "amgb200_interp_device",
+    "amgb200_ipc_export", "amgb200_ipc_open", "amgb200_peer_plan", "amgb200_peer_run",
 ]
 
 _lib = None
@@ -155,6 +156,12 @@ def lib():
         L.amgb200_vec_to_schedule.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.amgb200_vec_to_natural.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.amgb200_sync.argtypes = [C.c_void_p]
+        L.amgb200_ipc_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        L.amgb200_ipc_open.restype = C.c_void_p
+        L.amgb200_ipc_open.argtypes = [C.c_void_p, C.c_char_p]
+        L.amgb200_peer_plan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(c_int_p), c_int_p,
+                                        c_int_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, c_int_p]
+        L.amgb200_peer_run.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
 

@@ -274,6 +274,16 @@ struct amgb200_hier {
     long long *d_dbg = nullptr;        // AMGB200_DEBUG_TIMING: per-warp cycle counters of the CTA kernel
     int item0 = -1, item1 = -1;        // >= 0: restrict the next spmv launch to this item range
     bool own_stream = true;
+    // peer-memory exchange plans (multi-GPU): flag words [plan][source rank] of THIS rank, written by the peers
+    static constexpr int PEER_MAX_PLANS = 8, PEER_MAX_RANKS = 64;
+    unsigned *d_peer_flags = nullptr;
+    struct PeerPlan {
+        PeerPush *d_push = nullptr; int npush = 0, max_count = 0;
+        unsigned **d_flag_ptr = nullptr; int nflag = 0;
+        int *d_src = nullptr; int nsrc = 0;
+        unsigned epoch = 0;
+    } peer_plan[PEER_MAX_PLANS];
+    std::vector<void *> ipc_opened;
 };
 
 namespace {
@@ -1268,6 +1278,9 @@ void amgb200_free(amgb200_hier *h) {
             delete lv.bk;
         }
     }
+    for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    for (auto &pl : h->peer_plan) { dev_free(pl.d_push); dev_free(pl.d_flag_ptr); dev_free(pl.d_src); }    // (index lists: a few KB, released with the pool)
+    dev_free(h->d_peer_flags);
     dev_free(h->d_partial); dev_free(h->d_scal);
     if (h->h_scal) { std::lock_guard<std::mutex> lk(global_mutex()); pinned_scalars().push_back(h->h_scal); }
     dev_free(h->d_xnat); dev_free(h->d_bnat); dev_free(h->kry); dev_free(h->d_dbg);
@@ -1620,6 +1633,76 @@ __attribute__((visibility("default"))) long long amgb200_debug_quotient_check(lo
     CUDA_CHECK(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
     CUDA_CHECK(cudaFree(d_bad));
     return (long long)bad;
+}
+// ---- peer-memory exchange (NVLink / NVSwitch P2P through CUDA IPC; one process per GPU) ----
+// which: 0 x, 1 b, 2 wp of `level`; 3: this rank's flag words (level ignored).  handle: 64 bytes (cudaIpcMemHandle_t)
+void amgb200_ipc_export(amgb200_hier *h, int level, int which, unsigned char *handle) {
+    void *p = nullptr;
+    if (which == 3) {
+        if (!h->d_peer_flags) {
+            h->d_peer_flags = dev_alloc<unsigned>((size_t)amgb200_hier::PEER_MAX_PLANS * amgb200_hier::PEER_MAX_RANKS);
+            CUDA_CHECK(cudaMemset(h->d_peer_flags, 0, sizeof(unsigned) * amgb200_hier::PEER_MAX_PLANS * amgb200_hier::PEER_MAX_RANKS));
+        }
+        p = h->d_peer_flags;
+    } else p = amgb200_level_vec(h, level, which);
+    cudaIpcMemHandle_t hd;
+    CUDA_CHECK(cudaIpcGetMemHandle(&hd, p));
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t");
+    memcpy(handle, &hd, 64);
+}
+void *amgb200_ipc_open(amgb200_hier *h, const unsigned char *handle) {
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, 64);
+    void *p = nullptr;
+    CUDA_CHECK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(p);
+    return p;
+}
+// Plan `plan` (0..7) of this rank: npush transfers  my_vec[idx] -> peer_vec[idx]  (idx[i] == nullptr: the contiguous range
+// [range0[i], range1[i]); idx arrays are host arrays, copied), after which the epoch of the run is stored into flag_slot[j] (device
+// addresses inside the PEERS' flag arrays: peer_flags + plan * 64 + my rank), j < nflag; then this rank waits until the flag words
+// [plan][src[i]], i < nsrc, of its own array have reached the epoch.  Every rank must run its plans in the same global order.
+void amgb200_peer_plan(amgb200_hier *h, int plan, int npush, const double *my_vec, void *const *peer_vec, const int *const *idx, const int *count,
+                       const int *range0, int nflag, void *const *flag_slot, int nsrc, const int *src) {
+    if (plan < 0 || plan >= amgb200_hier::PEER_MAX_PLANS) { fprintf(stderr, "libamgb200: peer plan %d out of range\n", plan); exit(72); }
+    amgb200_hier::PeerPlan &pl = h->peer_plan[plan];
+    std::vector<PeerPush> pp((size_t)npush);
+    pl.max_count = 1;
+    for (int i = 0; i < npush; ++i) {
+        pp[i].count = count[i];
+        pl.max_count = std::max(pl.max_count, count[i]);
+        if (idx[i]) {
+            std::vector<int> v(idx[i], idx[i] + count[i]);
+            pp[i].idx = dev_upload(v);
+            pp[i].src = my_vec; pp[i].dst = (double *)peer_vec[i];
+        } else {
+            pp[i].idx = nullptr;
+            pp[i].src = my_vec + range0[i]; pp[i].dst = (double *)peer_vec[i] + range0[i];
+        }
+    }
+    pl.npush = npush;
+    pl.d_push = npush ? dev_upload(pp) : nullptr;
+    std::vector<unsigned *> fl((size_t)nflag);
+    for (int i = 0; i < nflag; ++i) fl[i] = (unsigned *)flag_slot[i];
+    pl.nflag = nflag;
+    pl.d_flag_ptr = nflag ? dev_upload(fl) : nullptr;
+    std::vector<int> sr((size_t)nsrc);
+    for (int i = 0; i < nsrc; ++i) sr[i] = plan * amgb200_hier::PEER_MAX_RANKS + src[i];
+    pl.nsrc = nsrc;
+    pl.d_src = nsrc ? dev_upload(sr) : nullptr;
+    pl.epoch = 0;
+}
+void amgb200_peer_run(amgb200_hier *h, int plan) {
+    amgb200_hier::PeerPlan &pl = h->peer_plan[plan];
+    ++pl.epoch;
+    if (pl.npush) {
+        const int gx = std::max(1, std::min(64, (pl.max_count + BLOCK - 1) / BLOCK));
+        peer_push_kernel<<<dim3(gx, pl.npush), BLOCK, 0, h->stream>>>(pl.d_push);
+        ++g_launches;
+    }
+    if (pl.nflag) { peer_flag_kernel<<<1, 64, 0, h->stream>>>(pl.d_flag_ptr, pl.nflag, pl.epoch); ++g_launches; }
+    if (pl.nsrc) { peer_wait_kernel<<<1, 64, 0, h->stream>>>(h->d_peer_flags, pl.d_src, pl.nsrc, pl.epoch); ++g_launches; }
+    CUDA_CHECK(cudaGetLastError());
 }
 void amgb200_sync(amgb200_hier *h) { CUDA_CHECK(cudaStreamSynchronize(h->stream)); }
 

@@ -1963,6 +1963,40 @@ __global__ void __launch_bounds__(BLOCK) sell_fill_kernel(int nslices, const int
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Peer-memory exchange (multi-GPU, one process per GPU): ghost entries are STORED straight into the owning vector of the peer
+// (mapped through CUDA IPC, NVLink / NVSwitch P2P), then an epoch is written to the peer's flag word for this rank; the peer's
+// stream waits on its flag words.  No host round trip, no collective.
+// ------------------------------------------------------------------------------------------
+struct PeerPush {              // copy src[idx[i]] -> dst[idx[i]] (idx != nullptr) or src[i] -> dst[i], i in [0, count)
+    const double *src;
+    double *dst;
+    const int *idx;
+    int count;
+};
+__global__ void __launch_bounds__(BLOCK) peer_push_kernel(const PeerPush *__restrict__ d) {
+    const PeerPush p = d[blockIdx.y];
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < p.count; i += gridDim.x * BLOCK) {
+        const int k = p.idx ? p.idx[i] : i;
+        p.dst[k] = p.src[k];
+    }
+}
+// (runs after peer_push_kernel in stream order: its stores have been performed; the fence orders them before the flag at system scope)
+__global__ void peer_flag_kernel(unsigned *const *__restrict__ flag, int n, unsigned epoch) {
+    if ((int)threadIdx.x < n) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag[threadIdx.x]), "r"(epoch) : "memory");
+    }
+}
+__global__ void peer_wait_kernel(const unsigned *__restrict__ flags, const int *__restrict__ src, int n, unsigned epoch) {
+    if ((int)threadIdx.x < n) {
+        unsigned f;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(flags + src[threadIdx.x]) : "memory");
+        } while ((int)(f - epoch) < 0);
+    }
+}
+
 __global__ void __launch_bounds__(BLOCK) gather_kernel(int n, const int *__restrict__ order, const double *__restrict__ in, double *out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) out[k] = in[order[k]];

@@ -118,6 +118,20 @@ class ShardedSolver:
         self.halo_bytes = sum(8 * len(v) for w in (0, 1) for v in self.recv_idx[w].values())
         # prolongation item ranges (P's items are 32-row groups counted from schedule row 0) covering my rows;
         # at the seams an item may also touch rows of a neighbour: those are ghosts here, refreshed before use
+        self.peer = hasattr(backend, "peer_setup") and world > 1 and not getattr(backend, "no_peer", False)
+        if self.peer:
+            # peer-memory plans (NVLink P2P stores + flag words, no collective, no host round trip): 0/1 ghost entries of the F/C pass,
+            # 2 fine residual -> rank 0, 3 coarse correction rank 0 -> all, 4 solution -> rank 0
+            own = [(a, b) for a, b in (self.part.f_rows[rank], self.part.c_rows[rank]) if b > a]
+            plans = {}
+            for w in (0, 1):
+                plans[w] = {"vec": "x0", "sends": [(peer, idx.cpu().numpy().astype(np.int32), None) for peer, idx in self.send_idx[w].items()],
+                            "srcs": sorted(self.recv_idx[w].keys())}
+            for pid, vec in ((2, "wp0"), (4, "x0")):
+                plans[pid] = {"vec": vec, "sends": [(0, None, r) for r in own] if rank else [], "srcs": list(range(1, world)) if rank == 0 else []}
+            plans[3] = {"vec": "x1", "sends": [(peer, None, (0, sh.get("n1", 0))) for peer in range(1, world)] if rank == 0 else [],
+                        "srcs": [0] if rank else []}
+            backend.peer_setup(dist, rank, world, plans)
         rpi = sh["rows_per_item"]
         self.p_ranges = []
         for a, b in (self.part.f_rows[rank], self.part.c_rows[rank]):
@@ -132,6 +146,9 @@ class ShardedSolver:
     def exchange(self, which):
         """refresh my ghost copies of pass-`which` x entries from their owners (point-to-point)"""
         if self.world == 1:
+            return
+        if self.peer:
+            self.be.peer_run(which)
             return
         torch, dist = self.torch, self.dist
         x = self.be.x0()
@@ -151,6 +168,9 @@ class ShardedSolver:
     def gather_residual(self):
         """own rows of wp0 -> rank 0 (the restriction needs the whole fine residual)"""
         if self.world == 1:
+            return
+        if self.peer:
+            self.be.peer_run(2)
             return
         torch, dist = self.torch, self.dist
         wp = self.be.wp0()
@@ -192,7 +212,9 @@ class ShardedSolver:
         self.gather_residual()
         if self.rank == 0:
             self.be.restrict_and_lower_levels()
-        if self.world > 1:
+        if self.peer:
+            self.be.peer_run(3)                           # coarse correction stored into every rank's x1
+        elif self.world > 1:
             self.dist.broadcast(self.be.x1(), src=0)      # coarse correction to every rank
         for a, b in self.p_ranges:                        # own rows (+ partial items at the seams)
             self.be.prolong(a, b)
@@ -212,6 +234,9 @@ class ShardedSolver:
     def collect_solution(self):
         """owners -> rank 0 (level-0 x in schedule numbering)"""
         if self.world == 1:
+            return
+        if self.peer:
+            self.be.peer_run(4)
             return
         dist = self.dist
         x = self.be.x0()
@@ -267,6 +292,9 @@ class GpuBackend:
         self._shape = {"n": info[0], "nF": info[1], "itemsF": info[2], "itemsC": info[3], "rows_per_item": info[6],
                        "p_items": info[7], "shardable": bool(info[5]) and dev.num_levels >= 2}
         n0, n1 = info[0], dev.info(1)["rows"] if dev.num_levels > 1 else 0
+        self._shape["n1"] = n1
+        import os
+        self.no_peer = bool(int(os.environ.get("AMGB200_NO_PEER", "0")))      # (developer switch: NCCL point-to-point instead of peer stores)
         self._x0 = torch.as_tensor(_CudaArray(self.L.amgb200_level_vec(self.h, 0, 0), n0), device=self.device)
         self._b0 = torch.as_tensor(_CudaArray(self.L.amgb200_level_vec(self.h, 0, 1), n0), device=self.device)
         self._wp0 = torch.as_tensor(_CudaArray(self.L.amgb200_level_vec(self.h, 0, 2), n0), device=self.device)
@@ -275,6 +303,51 @@ class GpuBackend:
 
     def shape(self):
         return self._shape
+
+    # ---- peer-memory exchange plans (include/amg_b200.h: amgb200_ipc_*, amgb200_peer_*) ----
+    def peer_setup(self, dist, rank, world, plans):
+        C, L = self.C, self.L
+        vecs = {"x0": (0, 0), "wp0": (0, 2), "x1": (1, 0), "flags": (0, 3)}
+        mine = {}
+        for name, (lvl, which) in vecs.items():
+            buf = C.create_string_buffer(64)
+            L.amgb200_ipc_export(self.h, lvl, which, buf)
+            mine[name] = buf.raw
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        opened = {}
+        def peer_ptr(peer, name):
+            if (peer, name) not in opened:
+                opened[(peer, name)] = L.amgb200_ipc_open(self.h, everyone[peer][name])
+            return opened[(peer, name)]
+        local = {"x0": self._x0.data_ptr(), "wp0": self._wp0.data_ptr(), "x1": self._x1.data_ptr() if self._x1 is not None else 0}
+        self._keep = []
+        for pid, pl in sorted(plans.items()):
+            sends = pl["sends"]
+            n = len(sends)
+            peer_vec = (C.c_void_p * max(n, 1))()
+            idx = (self.capi.c_int_p * max(n, 1))()
+            count = (C.c_int * max(n, 1))()
+            range0 = (C.c_int * max(n, 1))()
+            flag_peers = sorted({peer for peer, _, _ in sends})
+            for i, (peer, ix, rng) in enumerate(sends):
+                peer_vec[i] = peer_ptr(peer, pl["vec"])
+                if ix is not None:
+                    arr = np.ascontiguousarray(ix, np.int32)
+                    self._keep.append(arr)
+                    idx[i] = self.capi.iptr(arr); count[i] = len(arr); range0[i] = 0
+                else:
+                    idx[i] = self.capi.c_int_p(); count[i] = rng[1] - rng[0]; range0[i] = rng[0]
+            flags = (C.c_void_p * max(len(flag_peers), 1))()
+            for i, peer in enumerate(flag_peers):
+                flags[i] = peer_ptr(peer, "flags") + 4 * (pid * 64 + rank)
+            srcs = (C.c_int * max(len(pl["srcs"]), 1))(*pl["srcs"]) if pl["srcs"] else (C.c_int * 1)()
+            L.amgb200_peer_plan(self.h, pid, n, C.c_void_p(local[pl["vec"]]), peer_vec, idx, count, range0, len(flag_peers), flags,
+                                len(pl["srcs"]), srcs)
+        dist.barrier()        # every rank's plans (and flag words) exist before anybody runs one
+
+    def peer_run(self, plan):
+        self.L.amgb200_peer_run(self.h, plan)
 
     def order(self):
         o = np.zeros(self._shape["n"], np.int32)

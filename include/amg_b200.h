@@ -226,6 +226,19 @@ void amgb200_cycle_from(amgb200_hier *h, int level);
 void amgb200_vec_to_schedule(amgb200_hier *h, int level, const double *d_nat, double *d_sched);
 void amgb200_vec_to_natural(amgb200_hier *h, int level, const double *d_sched, double *d_nat);
 void amgb200_sync(amgb200_hier *h);
+/* Peer-memory exchange over NVLink / NVSwitch (CUDA IPC, one process per GPU): ghost entries are stored straight into the peer's
+ * vector and an epoch into the peer's flag word; the receiving stream waits on its own flag words.  No host round trip.
+ *   amgb200_ipc_export: 64-byte handle of a level vector (which: 0 x, 1 b, 2 wp) or of this rank's flag words (which = 3)
+ *   amgb200_ipc_open:   map a peer's handle (closed by amgb200_free)
+ *   amgb200_peer_plan:  plan 0..7 = npush transfers my_vec[idx] -> peer_vec[idx] (idx[i] NULL: contiguous range starting at
+ *                       range0[i], count[i] long), nflag flag slots to raise afterwards (addresses peer_flags + plan*64 + my rank),
+ *                       nsrc source ranks to wait for
+ *   amgb200_peer_run:   enqueue push + flags + wait on the hierarchy's stream; all ranks run their plans in the same global order */
+void amgb200_ipc_export(amgb200_hier *h, int level, int which, unsigned char *handle);
+void *amgb200_ipc_open(amgb200_hier *h, const unsigned char *handle);
+void amgb200_peer_plan(amgb200_hier *h, int plan, int npush, const double *my_vec, void *const *peer_vec, const int *const *idx, const int *count,
+                       const int *range0, int nflag, void *const *flag_slot, int nsrc, const int *src);
+void amgb200_peer_run(amgb200_hier *h, int plan);
 
 /* ---- 3. host-side helpers (pure C++, no device): synthetic operators + RS setup ---------- */
 /* Synthetic level-0 operators of SURVEY.md Appendix B, CSR with ascending columns:

@@ -25,9 +25,9 @@ def write_mtx(path, A):
             f.write(f"{r + 1} {c + 1} {v:.17g}\n")
 
 
-def run_dropin(path):
+def run_dropin(path, **env):
     out = subprocess.run([EXE, path], capture_output=True, text=True, timeout=300,
-                         env=dict(os.environ, AMGB200_VERBOSE="1"))
+                         env=dict(os.environ, AMGB200_VERBOSE="1", **env))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     return out.stdout
 
@@ -57,6 +57,14 @@ def test_reference_host_with_libamgb200_on_generated_poisson(tmp_path, oracle):
     for (_, rel, absr), want in zip(table[1:], hist):
         assert abs(absr - want) <= 1e-6 * want             # printed with %13.6e
     assert "AMG solve time:" in stdout and "AMG totally time:" in stdout
+    # BASELINE.json's metric (tol 1e-8) through the unmodified C host: AMGB200_TOL overrides the 1e-6 of SSS_main.c:33.  The coarse
+    # tolerance follows it (SSS_cycle.cu:858), so the iterates differ from the 1e-6 run from the first cycle on.
+    its8, res8, table8, _ = parse(run_dropin(p, AMGB200_TOL="1e-8"))
+    hier8 = HostHierarchy(A, tol=1e-8)
+    rtn8, x8, hist8 = oracle.solve(hier8, np.ones(A.nrows), np.ones(A.nrows), 0)
+    assert its8 == rtn8.nits and its8 > its
+    for (_, rel, absr), want in zip(table8[1:], hist8):
+        assert abs(absr - want) <= 1e-6 * want
 
 
 @pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/amg_dropin not built (needs /root/reference)")
