@@ -5,4 +5,4 @@ ctypes host mirror used by tests/ and bench.py.  There is no CPU fallback.
 """
 from . import capi  # noqa: F401
 from .host import (CsrMatrix, DeviceHierarchy, HostHierarchy, generate, read_mtx,  # noqa: F401
-                   solve_dropin)
+                   read_mtx_fast, solve_dropin)

@@ -77,7 +77,7 @@ EXPORTS = [
     "amgb200_set_stream", "amgb200_level_vec", "amgb200_level_order", "amgb200_l0_shape", "amgb200_l0_gs_pass",
     "amgb200_l0_residual", "amgb200_l0_prolong", "amgb200_restrict_from", "amgb200_cycle_from",
     "amgb200_vec_to_schedule", "amgb200_vec_to_natural", "amgb200_sync", "amgb200_setup_ex", "amgb200_interp_device",
-    "amgb200_ipc_export", "amgb200_ipc_open", "amgb200_peer_plan", "amgb200_peer_run",
+    "amgb200_ipc_export", "amgb200_ipc_open", "amgb200_peer_plan", "amgb200_peer_run", "amgb200_read_mtx",
 ]
 
 _lib = None
@@ -126,6 +126,8 @@ def lib():
         L.amgb200_generate.restype = C.c_int
         L.amgb200_generate.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(Mat)]
         L.amgb200_mat_free.argtypes = [C.POINTER(Mat)]
+        L.amgb200_read_mtx.restype = C.c_int
+        L.amgb200_read_mtx.argtypes = [C.c_char_p, C.POINTER(Mat)]
         L.amgb200_setup.argtypes = [C.POINTER(Amg), C.POINTER(Mat), C.POINTER(Pars), C.c_int]
         L.amgb200_setup_ex.argtypes = [C.POINTER(Amg), C.POINTER(Mat), C.POINTER(Pars), C.c_int, C.c_int]
         L.amgb200_interp_device.restype = C.c_int

@@ -1764,8 +1764,9 @@ __device__ __forceinline__ double spmv_store(double t, double alpha, const doubl
     return out;
 }
 
+// (thread-per-row instances with rows of <= 8 entries -- level-0 residual / transfers: gather-latency bound, 32 registers give 64 warps per SM)
 template <int KIND, int MODE, int RED, bool EXACT, bool ONE = false>
-__global__ void __launch_bounds__(BLOCK) spmv_kernel(DMat A, const double *__restrict__ x, double *y, const double *__restrict__ b,
+__global__ void __launch_bounds__(BLOCK, (KIND == 0 && ONE) ? 8 : 1) spmv_kernel(DMat A, const double *__restrict__ x, double *y, const double *__restrict__ b,
                                                      double alpha, double *partial, int item0, int item1) {
     __shared__ double red[32];
     __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * STAGE : 1];

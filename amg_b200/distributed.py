@@ -82,6 +82,35 @@ def ghost_lists(A_nat, order, part, rank):
     return out
 
 
+def all_ghost_lists(A_nat, order, part):
+    """ghost_lists for every rank in ONE vectorised pass over the matrix: out[rank][which][src] (same content as ghost_lists(.., rank)).
+    Every entry (row, col) whose row and column are owned by different ranks makes the column a ghost of the row's owner."""
+    n = part.n
+    pos = np.empty(n, np.int64)
+    pos[order] = np.arange(n)
+    owner_of_pos = part.owner(np.arange(n)).astype(np.int16)
+    lens = np.diff(A_nat.row_ptr)
+    reader = np.repeat(owner_of_pos[pos], lens)                  # owner of the row of every entry
+    cpos = pos[A_nat.col_idx]
+    src = owner_of_pos[cpos]
+    m = reader != src
+    reader, src, cpos = reader[m], src[m], cpos[m]
+    out = {r: {0: {}, 1: {}} for r in range(part.world)}
+    if len(cpos):
+        key = (reader.astype(np.int64) * part.world + src) * 2 + (cpos >= part.nF)
+        o = np.lexsort((cpos, key))
+        key, cpos = key[o], cpos[o]
+        keep = np.ones(len(key), bool)
+        keep[1:] = (key[1:] != key[:-1]) | (cpos[1:] != cpos[:-1])
+        key, cpos = key[keep], cpos[keep]
+        cuts = np.flatnonzero(np.concatenate(([True], key[1:] != key[:-1], [True])))
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            k = int(key[a])
+            which, rs = k & 1, k >> 1
+            out[rs // part.world][which][rs % part.world] = cpos[a:b]
+    return out
+
+
 class ShardedSolver:
     """V-cycle solve with level 0 sharded over `world` ranks (see module docstring).
 
@@ -105,13 +134,14 @@ class ShardedSolver:
         self.pre, self.post = pre, post
         order = backend.order()
         # what I need from each peer, and (same function evaluated for the peer) what each peer needs from me
-        mine = ghost_lists(A_nat, order, self.part, rank)
+        allg = all_ghost_lists(A_nat, order, self.part)
+        mine = allg[rank]
         self.recv_idx = {w: {src: torch.as_tensor(v, dtype=torch.long, device=backend.device) for src, v in mine[w].items()} for w in (0, 1)}
         self.send_idx = {0: {}, 1: {}}
         for peer in range(world):
             if peer == rank:
                 continue
-            theirs = ghost_lists(A_nat, order, self.part, peer)
+            theirs = allg[peer]
             for w in (0, 1):
                 if rank in theirs[w]:
                     self.send_idx[w][peer] = torch.as_tensor(theirs[w][rank], dtype=torch.long, device=backend.device)

@@ -51,6 +51,19 @@ def generate(kind, N, eps_z=1e-3):
     return out
 
 
+def read_mtx_fast(path):
+    """amgb200_read_mtx: the C loader fast path (one multi-threaded pass, the reference loader's semantics); returns CsrMatrix"""
+    L = capi.lib()
+    m = capi.Mat()
+    rc = L.amgb200_read_mtx(str(path).encode(), C.byref(m))
+    if rc != 0:
+        raise ValueError(f"amgb200_read_mtx({path}) failed: {rc}")
+    rp, ci, va = capi.mat_arrays(m)
+    out = CsrMatrix(rp.copy(), ci.copy(), va.copy(), ncols=m.num_cols)
+    L.amgb200_mat_free(C.byref(m))
+    return out
+
+
 def read_mtx(path):
     """MatrixMarket coordinate reader with the reference loader's semantics
     (amg/mmio_highlevel.h:144-305): entries stay in file order inside each row, symmetric

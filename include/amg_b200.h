@@ -246,6 +246,12 @@ void amgb200_peer_run(amgb200_hier *h, int plan);
  * Returns 0 on success; arrays are malloc'ed, release with amgb200_mat_free. */
 int amgb200_generate(int kind, int N, double eps_z, amgb200_mat *A);
 void amgb200_mat_free(amgb200_mat *A);
+/* Loader fast path for the kept C host: replaces the body of SSS_mat_read (amg/SSS_main.c:12-22: mmio_info +
+ * mmio_data, two fscanf passes over the file, amg/mmio_highlevel.h:10-305) by ONE multi-threaded pass with the same semantics
+ * entry for entry (file order inside each row, symmetric / hermitian expansion, pattern -> 1.0, imaginary parts dropped, no
+ * sorting, no duplicate merging).  Returns 0, or -1 / -2 / -4 / -5 (open / banner / size line / entries).
+ * AMGB200_MTX_CACHE=1 keeps a raw CSR cache `<file>.amgb200cache` validated against the file's size and mtime. */
+int amgb200_read_mtx(const char *filename, amgb200_mat *A);
 /* From-scratch restatement of the reference's setup phase (Setup/SSS_SETUP.cu:36-177 and below:
  * RS coarsening, direct interpolation + truncation, R = P^T, Galerkin RAP) producing a host
  * hierarchy that is bit-identical to the reference's.  Needed so the product runs without any
