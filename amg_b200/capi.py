@@ -77,7 +77,7 @@ EXPORTS = [
     "amgb200_set_stream", "amgb200_level_vec", "amgb200_level_order", "amgb200_l0_shape", "amgb200_l0_gs_pass",
     "amgb200_l0_residual", "amgb200_l0_prolong", "amgb200_restrict_from", "amgb200_cycle_from",
     "amgb200_vec_to_schedule", "amgb200_vec_to_natural", "amgb200_sync", "amgb200_setup_ex", "amgb200_interp_device",
-    "amgb200_ipc_export", "amgb200_ipc_open", "amgb200_peer_plan", "amgb200_peer_run", "amgb200_read_mtx",
+    "amgb200_ipc_export", "amgb200_ipc_open", "amgb200_peer_plan", "amgb200_peer_run", "amgb200_read_mtx", "amgb200_level_download",
 ]
 
 _lib = None
@@ -149,6 +149,7 @@ def lib():
         L.amgb200_level_vec.restype = C.c_void_p
         L.amgb200_level_vec.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.amgb200_level_order.argtypes = [C.c_void_p, C.c_int, c_int_p]
+        L.amgb200_level_download.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p]
         L.amgb200_l0_shape.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         L.amgb200_l0_gs_pass.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.amgb200_l0_residual.argtypes = [C.c_void_p, C.c_int, C.c_int]

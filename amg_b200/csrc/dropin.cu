@@ -83,6 +83,14 @@ void SSS_amg_cycle(amgb200_amg *mg) {
     amgb200_default_options(&opt);
     amgb200_hier *h = amgb200_upload(mg, &opt);
     amgb200_cycle(h, mg->cg[0].x.d, mg->cg[0].b.d);
+    // the reference leaves the coarse right-hand sides, corrections and residuals of the cycle in the host hierarchy
+    // (SSS_cycle.cu:916-929, :942): callers that keep its SSS_SOLVE.o may read them
+    for (int l = 0; l < mg->num_levels; ++l) {
+        amgb200_comp &c = mg->cg[l];
+        if (l > 0 && c.x.d) amgb200_level_download(h, l, 0, c.x.d);
+        if (l > 0 && c.b.d) amgb200_level_download(h, l, 1, c.b.d);
+        if (l < mg->num_levels - 1 && c.wp.d) amgb200_level_download(h, l, 2, c.wp.d);
+    }
     amgb200_free(h);
 }
 

@@ -8,8 +8,11 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include <omp.h>
@@ -148,6 +151,51 @@ struct Stager {
     }
 };
 Stager &stager() { static Stager *s = new Stager[MAX_DEVICES]; return s[current_device()]; }   // (its stream belongs to one device)
+Stager &prefetch_stager() { static Stager *s = new Stager[MAX_DEVICES]; return s[current_device()]; }
+
+// Raw CSR arrays of the matrices whose SELL layout is filled on the device, copied to the device by a helper thread WHILE the
+// calling thread runs the schedule analysis (both take ~40 ms at 128^3 and used to run one after the other).  upload_sell()
+// takes a finished copy from here or, if the matrix is not listed (or already taken), uploads it itself.
+struct RawPrefetch {
+    struct Item { const amgb200_mat *M; int *rp = nullptr; int *ci = nullptr; double *va = nullptr; std::atomic<int> ready{0}; bool taken = false; };
+    std::vector<std::unique_ptr<Item>> items;
+    std::thread worker;
+    void start(const std::vector<const amgb200_mat *> &mats, int device) {
+        for (const amgb200_mat *M : mats) { items.emplace_back(new Item()); items.back()->M = M; }
+        worker = std::thread([this, device]() {
+            CUDA_CHECK(cudaSetDevice(device));
+            for (auto &it : items) {
+                const amgb200_mat &M = *it->M;
+                const size_t nz = (size_t)M.row_ptr[M.num_rows];
+                auto put = [&](const void *src, size_t bytes) -> void * {
+                    void *d = dev_alloc<char>(std::max<size_t>(bytes, 1));
+                    if (bytes >= (4u << 20)) prefetch_stager().copy(d, src, bytes);
+                    else if (bytes) CUDA_CHECK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+                    return d;
+                };
+                it->rp = (int *)put(M.row_ptr, ((size_t)M.num_rows + 1) * sizeof(int));
+                it->ci = (int *)put(M.col_idx, nz * sizeof(int));
+                it->va = (double *)put(M.val, nz * sizeof(double));
+                it->ready.store(1, std::memory_order_release);
+            }
+        });
+    }
+    bool take(const amgb200_mat &M, int *&rp, int *&ci, double *&va) {
+        for (auto &it : items) {
+            if (it->M == &M && !it->taken) {
+                while (!it->ready.load(std::memory_order_acquire)) std::this_thread::yield();
+                it->taken = true; rp = it->rp; ci = it->ci; va = it->va;
+                return true;
+            }
+        }
+        return false;
+    }
+    void finish(std::vector<void *> &temps) {          // copies nobody asked for are released with the other temporaries
+        if (worker.joinable()) worker.join();
+        for (auto &it : items) if (!it->taken) { temps.push_back(it->rp); temps.push_back(it->ci); temps.push_back(it->va); }
+        items.clear();
+    }
+};
 
 template <class T>
 T *dev_upload_raw(const T *src, size_t n) {
@@ -183,7 +231,8 @@ struct DevMatOwner {
     // SELL layout filled on the device: L carries the slice structure only (build_sell_structure); the raw CSR arrays of M are
     // copied as they are and permuted / padded by sell_fill_kernel.  The temporaries are appended to `temps` and must stay
     // alive until the stream has been synchronised.
-    void upload_sell(const DevLayout &L, const amgb200_mat &M, const int *d_order, const int *d_colpos, cudaStream_t stream, std::vector<void *> &temps) {
+    void upload_sell(const DevLayout &L, const amgb200_mat &M, const int *d_order, const int *d_colpos, cudaStream_t stream, std::vector<void *> &temps,
+                     RawPrefetch *pre = nullptr) {
         const double t0 = now_s();
         v.kind = KIND_SELL; v.nrows = L.nrows; v.ncols = L.ncols; v.nitems = L.nitems(); v.max_row = L.max_row; v.recip = 0;
         v.rptr = nullptr; v.split = nullptr; v.late = nullptr;
@@ -194,9 +243,13 @@ struct DevMatOwner {
         v.col = d_col; v.val = d_val;
         if (total) {
             const size_t nz = (size_t)M.row_ptr[M.num_rows];
-            int *d_rp = dev_upload_raw(M.row_ptr, (size_t)M.num_rows + 1);
-            int *d_ci = dev_upload_raw(M.col_idx, nz);
-            double *d_va = dev_upload_raw(M.val, nz);
+            int *d_rp = nullptr, *d_ci = nullptr;
+            double *d_va = nullptr;
+            if (!(pre && pre->take(M, d_rp, d_ci, d_va))) {
+                d_rp = dev_upload_raw(M.row_ptr, (size_t)M.num_rows + 1);
+                d_ci = dev_upload_raw(M.col_idx, nz);
+                d_va = dev_upload_raw(M.val, nz);
+            }
             temps.push_back(d_rp); temps.push_back(d_ci); temps.push_back(d_va);
             const int ns = L.nitems();
             LAUNCH(sell_fill_kernel, std::max(1, std::min((ns + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 148 * 16)), BLOCK, stream,
@@ -240,6 +293,7 @@ struct Level {
     unsigned *d_hint = nullptr;        //   per-wavefront "closed" hint words of a launch,
     int hint_cap = 0;
     unsigned df_vbase = 0;             //   version base of the next launch (versions grow monotonically: records are never reset)
+    int dfw_cap = 0;                   // strategy 7 (data-flow, warp per row): staging doubles per warp
     int df_grid = 0, df_sch = 20;
     bool natural = false;              // natural-order Gauss-Seidel (cf_order = 0 or no cfmark): forward sweeps use this level's
     Level *bk = nullptr;               // schedule, backward sweeps (post-smoothing) the schedule/layout/vectors of *bk
@@ -392,6 +446,28 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
                        w, o[6], o[0] / ni, o[1] / ni, o[2] / ni, o[3] / ni, o[5] / ni, o[4] / ni); }
         }
 #endif
+        return;
+    }
+    if (lv.strategy == 7) {
+        const int need = nsweeps * lv.W;
+        if (need > lv.hint_cap) {
+            if (lv.d_hint) dev_free(lv.d_hint);
+            lv.d_hint = dev_alloc<unsigned>((size_t)need * DF_HINT_STRIDE);
+            lv.hint_cap = need;
+            CUDA_CHECK(cudaMemsetAsync(lv.d_hint, 0, (size_t)need * DF_HINT_STRIDE * sizeof(unsigned), h->stream));
+        }
+        if (first_use(7)) CUDA_CHECK(cudaFuncSetAttribute(gs_dataflow_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+        DMat A = lv.A.v;
+        const double *b = lv.b; double *x = lv.x; XRec *rec = lv.d_rec;
+        const int *wp = lv.d_wf_item_ptr, *iw = lv.d_item_wf;
+        unsigned *hint = lv.d_hint;
+        int W = lv.W, ns = nsweeps, ahead = h->df_ahead, cap = lv.dfw_cap;
+        unsigned vbase = lv.df_vbase;
+        void *args[] = {&A, &b, &x, &rec, &wp, &iw, &hint, &W, &ns, &ahead, &vbase, &cap};
+        CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)gs_dataflow_csr_kernel, dim3(lv.df_grid), dim3(DFW_BLOCK), args,
+                                               (size_t)(DFW_BLOCK / 32) * (cap + 16) * sizeof(double), h->stream));
+        ++g_launches;
+        lv.df_vbase += (unsigned)nsweeps;
         return;
     }
     if (lv.strategy == 5) {
@@ -926,10 +1002,22 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     const bool no_df = getenv("AMGB200_NO_DF") && atoi(getenv("AMGB200_NO_DF"));
     const bool df_all = getenv("AMGB200_DF_ALL") && atoi(getenv("AMGB200_DF_ALL"));       // also SELL levels the streaming kernels took
     if (getenv("AMGB200_DF_AHEAD")) h->df_ahead = std::max(1, atoi(getenv("AMGB200_DF_AHEAD")));
+    const double dfw_min_width = getenv("AMGB200_DFW_MIN_WIDTH") ? atof(getenv("AMGB200_DFW_MIN_WIDTH")) : 150.0;
 
     const double t0 = now_s();
     const int nl = h->nl;
     h->L.resize(nl);
+    const bool dev_fill = !(getenv("AMGB200_HOST_LAYOUT") && atoi(getenv("AMGB200_HOST_LAYOUT")));
+    RawPrefetch prefetch;
+    if (dev_fill && !(getenv("AMGB200_NO_PREFETCH") && atoi(getenv("AMGB200_NO_PREFETCH")))) {
+        std::vector<const amgb200_mat *> mats;                  // in the order the level loop below asks for them
+        for (int l = 0; l < nl; ++l) {
+            const amgb200_comp &c = mg->cg[l];
+            if (kind_of(c.A) == KIND_SELL) mats.push_back(&c.A);
+            if (l < nl - 1) { if (kind_of(c.P) == KIND_SELL) mats.push_back(&c.P); if (kind_of(c.R) == KIND_SELL) mats.push_back(&c.R); }
+        }
+        prefetch.start(mats, dev);
+    }
     std::vector<Schedule> sched(nl);
     int maxn = 0;
     // natural-order Gauss-Seidel (SSS_smooth.c:90-137) when cf_order = 0 or a level has no C/F marks (SSS_smooth.c:171-176):
@@ -1072,8 +1160,40 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             }
         }
     }
+    // data-flow smoother, warp-per-row form, for the levels with longer rows whose wavefronts are wide enough to feed the whole GPU (the
+    // streaming cluster kernel keeps them on 16 SMs): measured threshold AMGB200_DFW_MIN_WIDTH rows per wavefront on average
+    if (lv.ordered && h->exact && lay.kind == KIND_CSR && lv.A.valid && lv.strategy != 4 && !getenv("AMGB200_GS_STRATEGY") && !no_df &&
+        (double)S.n / std::max(1, lv.W) >= dfw_min_width) {
+        const int cap = (lay.max_row + 7) & ~7;
+        const size_t smem = (size_t)(DFW_BLOCK / 32) * (cap + 16) * sizeof(double);
+        if (smem <= (size_t)h->max_dyn_smem) {
+            const double tl = now_s();
+            int *d_missing = dev_alloc<int>(1);
+            CUDA_CHECK(cudaMemsetAsync(d_missing, 0, sizeof(int), (cudaStream_t)0));
+            LAUNCH(dfw_symmetry_kernel, std::max(1, (lv.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), BLOCK, (cudaStream_t)0, lv.A.v, d_missing);
+            int missing = 0;
+            CUDA_CHECK(cudaMemcpy(&missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost));
+            dev_free(d_missing);
+            if (missing == 0) {
+                lv.strategy = 7;
+                lv.dfw_cap = cap;
+                lv.d_rec = dev_alloc<XRec>((size_t)lv.n);
+                CUDA_CHECK(cudaMemsetAsync(lv.d_rec, 0, (size_t)lv.n * sizeof(XRec), (cudaStream_t)0));
+                lv.df_vbase = 0;
+                if (first_use(7)) CUDA_CHECK(cudaFuncSetAttribute(gs_dataflow_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+                int per_sm = 0;
+                CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_dataflow_csr_kernel, DFW_BLOCK, smem));
+                if (getenv("AMGB200_DF_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("AMGB200_DF_PER_SM"))));
+                lv.df_grid = std::max(1, std::min(per_sm * h->num_sms, (lv.n + DFW_BLOCK / 32 - 1) / (DFW_BLOCK / 32)));
+                if (lv.d_stream) { dev_free(lv.d_stream); dev_free(lv.d_blk_ptr); lv.d_stream = nullptr; lv.d_blk_ptr = nullptr; }
+                if (lv.d_wf_row_ptr) { dev_free(lv.d_wf_row_ptr); lv.d_wf_row_ptr = nullptr; }
+                if (h->opt.verbose >= 2) printf("      data-flow smoother (warp per row): %d CTAs x %d threads (%d per SM), staging %d doubles per warp\n", lv.df_grid, DFW_BLOCK, per_sm, cap + 16);
+            } else if (h->opt.verbose >= 2) printf("      data-flow smoother not used: %d entries without a mirror entry (non-symmetric pattern)\n", missing);
+            tl_note("symmetry", lv.n, now_s() - tl);
+        }
+    }
     // streaming cluster smoother: the other ordered levels (any layout; the packer works from the host matrix)
-    if (lv.ordered && h->exact && lv.strategy != 4 && lv.W >= 4 && !getenv("AMGB200_GS_STRATEGY") && !(getenv("AMGB200_NO_XC") && atoi(getenv("AMGB200_NO_XC")))) {
+    if (lv.ordered && h->exact && lv.strategy != 4 && lv.strategy != 7 && lv.W >= 4 && !getenv("AMGB200_GS_STRATEGY") && !(getenv("AMGB200_NO_XC") && atoi(getenv("AMGB200_NO_XC")))) {
         ClusterStreamLayout SL;
         const double tl = now_s();
         build_stream_cluster(Amat, S, XC_CTAS, SL, (long long)h->max_dyn_smem - XC_HDR - 128, getenv("AMGB200_XC_LD") ? atoi(getenv("AMGB200_XC_LD")) : 3);
@@ -1136,7 +1256,6 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
 
     // SELL layouts are permuted and padded on the device from the raw CSR arrays (sell_fill_kernel); the host only builds their
     // O(rows) slice tables.  AMGB200_HOST_LAYOUT=1 restores the host fill (debugging).
-    const bool dev_fill = !(getenv("AMGB200_HOST_LAYOUT") && atoi(getenv("AMGB200_HOST_LAYOUT")));
     std::vector<void *> temps;
     std::vector<int *> d_pos(nl, nullptr);
     for (int l = 0; l < nl; ++l) {
@@ -1152,7 +1271,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             tl_note(what, l, now_s() - tl);
             // (legacy default stream: ordered after the cudaMemcpy's of small pageable arrays, whose DMA may still be in flight
             // when the call returns; the library's own stream is non-blocking and would not wait for them)
-            dst.upload_sell(lay, M, d_row_order, d_col_pos, (cudaStream_t)0, temps);
+            dst.upload_sell(lay, M, d_row_order, d_col_pos, (cudaStream_t)0, temps, &prefetch);
         } else {
             build_layout(M, rowS.order.data(), colS ? colS->pos.data() : nullptr, kind, breaks, lay);
             tl_note(what, l, now_s() - tl);
@@ -1245,6 +1364,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     if (getenv("AMGB200_DEBUG_TIMING")) h->d_dbg = dev_alloc<long long>(16 * 8 + 8);
     h->d_xnat = dev_alloc<double>(maxn);
     h->d_bnat = dev_alloc<double>(maxn);
+    prefetch.finish(temps);
     CUDA_CHECK(cudaDeviceSynchronize());
     for (void *p : temps) dev_free(p);                  // raw CSR copies and numbering tables of the device-side fills
     h->upload_s = now_s() - t0;
@@ -1351,7 +1471,7 @@ const char *amgb200_level_kernel(const amgb200_hier *h, int level) {
     check_level(h, level);
     const Level &lv = h->L[level];
     if (!lv.smoothed) return "none";
-    static const char *names[7] = {"gs_pass_kernel", "-", "gs_ordered_cta_kernel", "gs_ordered_cluster_kernel", "gs_stream_cta_kernel", "gs_stream_cluster_kernel", "gs_dataflow_kernel"};
+    static const char *names[8] = {"gs_pass_kernel", "-", "gs_ordered_cta_kernel", "gs_ordered_cluster_kernel", "gs_stream_cta_kernel", "gs_stream_cluster_kernel", "gs_dataflow_kernel", "gs_dataflow_csr_kernel"};
     return names[lv.strategy];
 }
 
@@ -1553,6 +1673,15 @@ void *amgb200_level_vec(amgb200_hier *h, int level, int which) {
     check_level(h, level);
     Level &lv = h->L[level];
     return which == 0 ? (void *)lv.x : which == 1 ? (void *)lv.b : (void *)lv.wp;
+}
+// level vector (0 x, 1 b, 2 wp) in NATURAL numbering to a host array of n_level doubles
+void amgb200_level_download(amgb200_hier *h, int level, int which, double *host) {
+    check_level(h, level);
+    Level &lv = h->L[level];
+    const double *src = which == 0 ? lv.x : which == 1 ? lv.b : lv.wp;
+    to_natural(h, level, src, h->d_bnat);
+    CUDA_CHECK(cudaMemcpyAsync(host, h->d_bnat, (size_t)lv.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
 }
 void amgb200_level_order(const amgb200_hier *h, int level, int *order_host) {
     check_level(h, level);

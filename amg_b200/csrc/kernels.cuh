@@ -1751,6 +1751,152 @@ __global__ void __launch_bounds__(DF_BLOCK) gs_dataflow_kernel(DMat A, const dou
 #undef DF_CLK
 }
 
+// ---- the same data-flow scheme for levels with longer rows: a WARP per row (CSR layout in schedule numbering) ------------------
+// The 32 lanes request the records of the row's columns (8 loads in flight per lane), the separately rounded products go to a
+// per-warp staging area in shared memory in storage order, the in-order chain (chain_fold, 8.4 cycles per term) runs over them:
+// the part in front of the first operand that is still missing BEFORE the warp sleeps on its hint, the rest after the polling
+// rounds.  A product that is still missing is marked in the staging area by a reserved NaN bit pattern.
+constexpr int DFW_BLOCK = 256;
+constexpr unsigned long long DFW_MISSING = 0x7ff8dead0badc0deULL;
+__device__ __forceinline__ bool dfw_missing(double v) { return (unsigned long long)__double_as_longlong(v) == DFW_MISSING; }
+// upload: number of entries (k, j) of a CSR matrix without a stored mirror entry (j, k)
+__global__ void __launch_bounds__(BLOCK) dfw_symmetry_kernel(DMat A, int *missing) {
+    const int k = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= A.nrows) return;
+    int bad = 0;
+    for (int p = A.rptr[k] + lane; p < A.rptr[k + 1]; p += 32) {
+        const int j = A.col[p];
+        if (j == k) continue;
+        bool found = false;
+        for (int q = A.rptr[j]; q < A.rptr[j + 1] && !found; ++q) found = A.col[q] == k;
+        bad += !found;
+    }
+    bad = __reduce_add_sync(FULL, bad);
+    if (lane == 0 && bad) atomicAdd(missing, bad);
+}
+
+// dynamic shared memory: (blockDim.x / 32) staging areas of `cap` + 16 doubles (cap = longest row rounded up to 8)
+__global__ void __launch_bounds__(DFW_BLOCK, 2) gs_dataflow_csr_kernel(DMat A, const double *__restrict__ b, double *x, XRec *rec,
+                                                                    const int *__restrict__ wf_row_ptr, const int *__restrict__ row_wf,
+                                                                    unsigned *hint, int W, int nsweeps, int ahead, unsigned vbase, int cap) {
+    extern __shared__ __align__(16) double dfw_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *sp = dfw_smem + (size_t)wib * (cap + 16);
+    const unsigned sp_a = (unsigned)__cvta_generic_to_shared(sp);
+    const int TW = gridDim.x * (DFW_BLOCK / 32);
+    const int gw = wib * gridDim.x + blockIdx.x;                          // consecutive rows on different SMs
+    const int n = A.nrows;
+    const long long total = (long long)n * nsweeps;
+    int s = gw / n, k = gw - s * n;
+    for (long long t = gw; t < total; t += TW) {
+        const int p0 = A.rptr[k], len = A.rptr[k + 1] - p0, len8 = (len + 7) & ~7;
+        const int wf = row_wf[k];
+        const int gwf = s * W + wf;
+        const bool closes = k + 1 == wf_row_ptr[wf + 1];
+        const unsigned vold = vbase + (unsigned)s, vnew = vold + 1u;
+        const double bk = b[k];
+        // ---- first round: records of all columns, 8 loads in flight per lane; products (or the missing mark) to the staging area
+        double dl = 0.0;
+        int first_missing = len8;
+        for (int e0 = 0; e0 < len8 + 16; e0 += 256) {
+            int j[8];
+            double a[8], xo[8];
+            uint4 r[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * 32 + lane;
+                j[u] = -1; a[u] = 0.0;
+                if (e < len) { j[u] = A.col[p0 + e]; a[u] = A.val[p0 + e]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (j[u] >= 0 && j[u] != k) {
+                    if (s == 0 && j[u] > k) xo[u] = __ldcg(x + j[u]);          // not updated yet in this launch
+                    else ld_xrec_raw(rec + j[u], r[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * 32 + lane;
+                if (e < len8 + 16) {
+                    double prod = 0.0;                                          // padding and the diagonal: exact no-ops of the chain
+                    if (j[u] == k) dl = a[u];
+                    else if (j[u] >= 0) {
+                        double xv;
+                        if (s == 0 && j[u] > k) prod = __dmul_rn(a[u], xo[u]);
+                        else if (xrec_ok(r[u], j[u] < k ? vnew : vold, xv)) prod = __dmul_rn(a[u], xv);
+                        else { prod = __longlong_as_double((long long)DFW_MISSING); first_missing = min(first_missing, e); }
+                    }
+                    sp[e] = prod;
+                }
+            }
+        }
+        // diagonal (exactly one lane saw it), its reciprocal off the dependency path
+        const unsigned dm = __ballot_sync(FULL, dl != 0.0);
+        const double d = dm ? __shfl_sync(FULL, dl, __ffs(dm) - 1) : 0.0;
+        const double yrec = __ddiv_rn(1.0, d);
+        const bool dsafe = gs_quotient_dsafe(d);
+        first_missing = __reduce_min_sync(FULL, first_missing);
+        __syncwarp();
+        // ---- the chain in front of the first missing operand runs before the wait
+        const int pre = first_missing & ~7;
+        double tacc = chain_fold<true>(bk, reinterpret_cast<const double2 *>(sp), pre);
+        if (first_missing < len8) {
+            if (gwf >= ahead) {
+                if (lane == 0) {
+                    unsigned f;
+                    for (;;) {
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(hint + (size_t)(gwf - ahead) * DF_HINT_STRIDE) : "memory");
+                        if ((int)(f - vbase) > 0) break;
+                        __nanosleep(DF_GATE_NS);
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- polling rounds: every lane re-requests the records of its missing entries (matrix entries come from L1 / L2 again)
+            bool more = true;
+            while (more) {
+                bool mine = false;
+                for (int e0 = pre; e0 < len; e0 += 256) {
+                    int j[8];
+                    uint4 r[8];
+                    bool miss[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int e = e0 + u * 32 + lane;
+                        miss[u] = e < len && dfw_missing(sp[e]);
+                        if (miss[u]) { j[u] = A.col[p0 + e]; ld_xrec_raw(rec + j[u], r[u]); }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (miss[u]) {
+                            const int e = e0 + u * 32 + lane;
+                            double xv;
+                            if (xrec_ok(r[u], j[u] < k ? vnew : vold, xv)) sp[e] = __dmul_rn(A.val[p0 + e], xv);
+                            else mine = true;
+                        }
+                    }
+                }
+                more = __any_sync(FULL, mine);
+            }
+            __syncwarp();
+            tacc = chain_fold<true>(tacc, reinterpret_cast<const double2 *>(sp + pre), len8 - pre);
+        }
+        if (lane == 0) {
+            double xn;
+            if (fabs(d) > GS_TINY) xn = gs_quotient_pre(tacc, d, yrec, dsafe, A.recip);
+            else xn = __ldcg(x + k);                                       // row left as it is (SSS_smooth.c:32): only its version moves on
+            st_xrec(rec + k, xn, vnew);
+            if (s == nsweeps - 1 || fabs(d) <= GS_TINY) __stcg(x + k, xn);
+            if (closes) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(hint + (size_t)gwf * DF_HINT_STRIDE), "r"(vbase + 1u) : "memory");
+        }
+        __syncwarp();
+        k += TW;
+        while (k >= n) { k -= n; ++s; }
+    }
+    (void)sp_a;
+}
+
 // ------------------------------------------------------------------------------------------
 // SpMV family (amg/SSS_utils.c:161-201)
 // ------------------------------------------------------------------------------------------
@@ -1764,9 +1910,10 @@ __device__ __forceinline__ double spmv_store(double t, double alpha, const doubl
     return out;
 }
 
-// (thread-per-row instances with rows of <= 8 entries -- level-0 residual / transfers: gather-latency bound, 32 registers give 64 warps per SM)
+// (the thread-per-row prolongation-add with rows of <= 8 entries is gather-latency bound: 32 registers give 64 warps per SM, measured
+// 251 -> 238 us on level 0 of 256^3; the same bound costs the restriction 187 -> 213 us, so only this instance gets it)
 template <int KIND, int MODE, int RED, bool EXACT, bool ONE = false>
-__global__ void __launch_bounds__(BLOCK, (KIND == 0 && ONE) ? 8 : 1) spmv_kernel(DMat A, const double *__restrict__ x, double *y, const double *__restrict__ b,
+__global__ void __launch_bounds__(BLOCK, (KIND == 0 && ONE && MODE == MODE_AMXPY) ? 8 : 1) spmv_kernel(DMat A, const double *__restrict__ x, double *y, const double *__restrict__ b,
                                                      double alpha, double *partial, int item0, int item1) {
     __shared__ double red[32];
     __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * STAGE : 1];

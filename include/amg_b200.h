@@ -106,7 +106,9 @@ typedef struct amgb200_smtr_ {  /* SSS_SMTR, SSS_main.h:221-238 */
 AMGB200_T_RTN SSS_amg_solve(AMGB200_T_AMG *mg, AMGB200_T_VEC *x, AMGB200_T_VEC *b);
 
 /* Replaces amg/Solve/SSS_cycle.cu:848-967 (Solve/SSS_cycle.h:18): one V/W-cycle on the host
- * hierarchy (reads cg[0].b, cg[0].x; writes cg[l].x, cg[l].b, cg[l].wp like the reference). */
+ * hierarchy (reads cg[0].b, cg[0].x; writes cg[0].x and, like the reference, cg[l].x, cg[l].b (l >= 1) and the residuals cg[l].wp).
+ * Every call analyses and uploads the hierarchy again (the reference interface has no resident state): hosts that cycle repeatedly
+ * should use amgb200_upload / amgb200_cycle. */
 void SSS_amg_cycle(AMGB200_T_AMG *mg);
 
 /* Replaces amg/Solve/SSS_cycle.cu:819-846 (Solve/SSS_cycle.h:17): CG, then GMRES(30) on failure. */
@@ -217,6 +219,7 @@ const char *amgb200_version(void);
 void amgb200_set_stream(amgb200_hier *h, void *cuda_stream);            /* run on the caller's stream */
 void *amgb200_level_vec(amgb200_hier *h, int level, int which);         /* device ptr: 0 x, 1 b, 2 wp (schedule numbering) */
 void amgb200_level_order(const amgb200_hier *h, int level, int *order_host);   /* schedule position -> natural row */
+void amgb200_level_download(amgb200_hier *h, int level, int which, double *host);  /* level vector (0 x, 1 b, 2 wp), natural numbering */
 void amgb200_l0_shape(const amgb200_hier *h, long long info[8]);
 void amgb200_l0_gs_pass(amgb200_hier *h, int pass, int item0, int item1);
 void amgb200_l0_residual(amgb200_hier *h, int item0, int item1);

@@ -131,6 +131,7 @@ def test_dataflow_smoother_is_bit_identical(name, per_sm, oracle, monkeypatch):
     bit for 1, 2 and 3 sweeps per launch, with the grid the occupancy allows and with one CTA per SM (different item-to-warp
     mapping, wraps around the sweeps differently); AMGB200_DF_ALL=1 also sends the levels the streaming kernels would take to it"""
     monkeypatch.setenv("AMGB200_DF_ALL", "1")
+    monkeypatch.setenv("AMGB200_DFW_MIN_WIDTH", "4")           # (the warp-per-row form for every level with >= 4 rows per wavefront)
     if per_sm:
         monkeypatch.setenv("AMGB200_DF_PER_SM", per_sm)
     kind, N, eps = CASES[name]
@@ -148,6 +149,8 @@ def test_dataflow_smoother_is_bit_identical(name, per_sm, oracle, monkeypatch):
             want = oracle.gs_cf(c.A, hier.cfmark(l), x0, b, sweeps, 1)
             check_vec(dev, l, got, want, f"GS x{sweeps} ({dev.gs_kernel(l)})")
     assert "gs_dataflow_kernel" in used, f"data-flow kernel not exercised (kernels used: {sorted(used)})"
+    if name in ("p3d32", "aniso32"):      # (the other two hierarchies have no warp-per-row level that does not fit the single-SM streaming kernel)
+        assert "gs_dataflow_csr_kernel" in used, f"warp-per-row data-flow kernel not exercised (kernels used: {sorted(used)})"
     n0 = hier.level(0).A.num_rows
     rtn, x, hist = dev.solve(np.ones(n0), np.ones(n0))
     rtn_o, x_o, hist_o = oracle.solve(hier, np.ones(n0), np.ones(n0), 0)
