@@ -86,14 +86,15 @@ std::mutex &global_mutex() { static std::mutex *m = new std::mutex(); return *m;
 int current_device() { int d = 0; cudaGetDevice(&d); return d < 0 || d >= MAX_DEVICES ? 0 : d; }
 DevPool &pool(int dev) { static DevPool *p = new DevPool[MAX_DEVICES]; return p[dev]; }                 // intentionally leaked: the driver reclaims at process exit
 std::vector<double *> &pinned_scalars() { static std::vector<double *> *v = new std::vector<double *>(); return *v; }   // 64-byte pinned slots (host memory: device independent)
-// true exactly once per (call site id, device): cudaFuncSetAttribute has to be repeated on every device
-bool first_use(int id) {
-    static bool seen[16][MAX_DEVICES];
+// true exactly once per (kernel, device): cudaFuncSetAttribute has to be repeated on every device, and for every template
+// instance of a kernel
+bool first_use(const void *kernel) {
+    static std::vector<std::pair<const void *, int>> *seen = new std::vector<std::pair<const void *, int>>();
     std::lock_guard<std::mutex> lk(global_mutex());
-    bool &b = seen[id][current_device()];
-    const bool first = !b;
-    b = true;
-    return first;
+    const std::pair<const void *, int> key(kernel, current_device());
+    for (const auto &e : *seen) if (e == key) return false;
+    seen->push_back(key);
+    return true;
 }
 void dev_free(const void *p) {
     if (!p) return;
@@ -456,7 +457,7 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
             lv.hint_cap = need;
             CUDA_CHECK(cudaMemsetAsync(lv.d_hint, 0, (size_t)need * DF_HINT_STRIDE * sizeof(unsigned), h->stream));
         }
-        if (first_use(7)) CUDA_CHECK(cudaFuncSetAttribute(gs_dataflow_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+        if (first_use((const void *)gs_dataflow_csr_kernel)) CUDA_CHECK(cudaFuncSetAttribute(gs_dataflow_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
         DMat A = lv.A.v;
         const double *b = lv.b; double *x = lv.x; XRec *rec = lv.d_rec;
         const int *wp = lv.d_wf_item_ptr, *iw = lv.d_item_wf;
@@ -471,9 +472,9 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         return;
     }
     if (lv.strategy == 5) {
-        if (first_use(0)) {
-            auto k3 = &gs_stream_cluster_kernel<3>;
-            auto k4 = &gs_stream_cluster_kernel<4>;
+        auto k3 = &gs_stream_cluster_kernel<3>;
+        auto k4 = &gs_stream_cluster_kernel<4>;
+        if (first_use((const void *)k3)) {
             CUDA_CHECK(cudaFuncSetAttribute(k3, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             CUDA_CHECK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
             CUDA_CHECK(cudaFuncSetAttribute(k4, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -512,7 +513,7 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         return;
     }
     if (lv.strategy == 4) {
-        if (first_use(1)) {
+        if (first_use((const void *)gs_stream_cta_kernel)) {
             CUDA_CHECK(cudaFuncSetAttribute(gs_stream_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
         }
         const size_t xb = ((size_t)lv.n * 8 + 127) & ~(size_t)127;
@@ -544,12 +545,12 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         const size_t stage = (size_t)nw * (STAGE + (cap ? cap + 24 + 2 * LATE_CAP : 0)) * sizeof(double);
         const size_t xbytes = (size_t)((lv.n + 1) & ~1) * sizeof(double);
         if (lv.x_in_smem) {
-            if (first_use(2)) {
+            if (first_use((const void *)gs_ordered_cta_kernel<KIND, EXACT, true>)) {
                 CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cta_kernel<KIND, EXACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
             }
             gs_ordered_cta_kernel<KIND, EXACT, true><<<1, 32 * nw, xbytes + stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D, cap, h->d_dbg);
         } else {
-            if (first_use(3)) {
+            if (first_use((const void *)gs_ordered_cta_kernel<KIND, EXACT, false>)) {
                 CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cta_kernel<KIND, EXACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
             }
             gs_ordered_cta_kernel<KIND, EXACT, false><<<1, 32 * nw, stage, h->stream>>>(lv.A.v, lv.b, lv.x, lv.d_wf_item_ptr, lv.W, nsweeps, G, D, cap, h->d_dbg);
@@ -578,7 +579,7 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         return;
     }
     if (lv.strategy == 3) {
-        if (first_use(4)) {
+        if (first_use((const void *)gs_ordered_cluster_kernel<KIND, EXACT>)) {
             CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cluster_kernel<KIND, EXACT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         }
         cudaLaunchConfig_t cfg = {};
@@ -597,13 +598,13 @@ void smooth_k(amgb200_hier *h, Level &lv, int nsweeps) {
         cfg.attrs = at;
         cfg.numAttrs = 1;
         if (KIND == 0 && lv.A.v.max_row <= 20) {
-            if (first_use(5)) {
+            if (first_use((const void *)gs_ordered_cluster_kernel<KIND, EXACT, true>)) {
                 CUDA_CHECK(cudaFuncSetAttribute(gs_ordered_cluster_kernel<KIND, EXACT, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             }
             CUDA_CHECK(cudaLaunchKernelEx(&cfg, gs_ordered_cluster_kernel<KIND, EXACT, true>, lv.A.v, (const double *)lv.b, lv.x, (const int *)lv.d_wf_item_ptr, lv.W, nsweeps, h->d_dbg));
         } else if (KIND == 0 && lv.A.v.max_row <= 28) {
             auto k28 = &gs_ordered_cluster_kernel<KIND, EXACT, true, 28>;
-            if (first_use(6)) {
+            if (first_use((const void *)k28)) {
                 CUDA_CHECK(cudaFuncSetAttribute(k28, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             }
             CUDA_CHECK(cudaLaunchKernelEx(&cfg, k28, lv.A.v, (const double *)lv.b, lv.x, (const int *)lv.d_wf_item_ptr, lv.W, nsweeps, h->d_dbg));
@@ -1180,7 +1181,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                 lv.d_rec = dev_alloc<XRec>((size_t)lv.n);
                 CUDA_CHECK(cudaMemsetAsync(lv.d_rec, 0, (size_t)lv.n * sizeof(XRec), (cudaStream_t)0));
                 lv.df_vbase = 0;
-                if (first_use(7)) CUDA_CHECK(cudaFuncSetAttribute(gs_dataflow_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+                if (first_use((const void *)gs_dataflow_csr_kernel)) CUDA_CHECK(cudaFuncSetAttribute(gs_dataflow_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
                 int per_sm = 0;
                 CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_dataflow_csr_kernel, DFW_BLOCK, smem));
                 if (getenv("AMGB200_DF_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("AMGB200_DF_PER_SM"))));

@@ -1542,6 +1542,9 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CLUSTER_WARPS_SELL : 32 * CLU
 struct __align__(16) XRec { unsigned lo, v0, hi, v1; };
 constexpr int DF_BLOCK = 128;
 constexpr int DF_BATCH = 10;          // operand loads in flight per thread
+#ifndef DF_MINB
+#define DF_MINB 1
+#endif
 constexpr int DF_HINT_STRIDE = 32;    // one hint word per 128-byte line: the words of consecutive wavefronts live in different L2 slices
 #ifndef DF_GATE_NS
 #define DF_GATE_NS 400
@@ -1600,7 +1603,7 @@ __global__ void __launch_bounds__(BLOCK) df_symmetry_kernel(DMat A, const int *_
 
 __device__ __noinline__ void tacc_sink(long long *p) { if (p) p[127] = 1; }
 template <int SCH>
-__global__ void __launch_bounds__(DF_BLOCK) gs_dataflow_kernel(DMat A, const double *__restrict__ b, double *x, XRec *rec,
+__global__ void __launch_bounds__(DF_BLOCK, DF_MINB) gs_dataflow_kernel(DMat A, const double *__restrict__ b, double *x, XRec *rec,
                                                                const int *__restrict__ item_wf, const int *__restrict__ wf_item_ptr, unsigned *hint,
                                                                int W, int nsweeps, int ahead, unsigned vbase, long long *dbg) {
 #ifdef AMGB200_DF_TIMING

@@ -1,5 +1,5 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "dataflow" 2>&1 | tail -2
+(time python -m pytest tests -m gpu -x -q) > gpurun_out/r2_pytest_gpu_c.log 2>&1; tail -4 gpurun_out/r2_pytest_gpu_c.log
 export AMGB200_TIMEOP_SWEEPS=2
-python tools/sweep.py p3d 256 1,2,3 "AMGB200_DFW_MIN_WIDTH=100000" 2>&1 | tail -2
-python tools/sweep.py aniso3d 256 1,2,3,4 "AMGB200_DFW_MIN_WIDTH=100000" 2>&1 | tail -2
-python tools/sweep.py v27 192 0,1,2 "AMGB200_DFW_MIN_WIDTH=100000 AMGB200_NO_DF=1" "AMGB200_DFW_MIN_WIDTH=100" 2>&1 | tail -3
+python tools/sweep.py v27 96 0 2>&1 | tail -1; AMGB200_LIB=$PWD/build_tl/libamgb200_minb3.so python tools/sweep.py v27 96 0 2>&1 | tail -1
+python tools/sweep.py p3d 128 1 2>&1 | tail -1; AMGB200_LIB=$PWD/build_tl/libamgb200_minb3.so python tools/sweep.py p3d 128 1 2>&1 | tail -1
+python tools/sweep.py aniso3d 128 0 2>&1 | tail -1; AMGB200_LIB=$PWD/build_tl/libamgb200_minb3.so python tools/sweep.py aniso3d 128 0 2>&1 | tail -1
