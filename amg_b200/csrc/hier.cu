@@ -298,6 +298,9 @@ struct Level {
     int df_grid = 0, df_sch = 20;
     bool natural = false;              // natural-order Gauss-Seidel (cf_order = 0 or no cfmark): forward sweeps use this level's
     Level *bk = nullptr;               // schedule, backward sweeps (post-smoothing) the schedule/layout/vectors of *bk
+    Level *lo = nullptr;               // pre-smoothing from x = 0 (levels >= 1): the first sweep only sees the entries whose column has already
+                                       // been updated -- the strictly lower triangle in schedule numbering; same schedule, shares x and b
+    bool x_is_zero = false;            // x was zero-filled by the cycle and not touched since
     int *d_fb = nullptr;               // position in this level's numbering of row k of bk's numbering
 };
 
@@ -716,14 +719,17 @@ int coarse_cg(amgb200_hier *h, const DMat &A, const double *b, double *u, double
     temp1 = h->last_sumsq;                                          // (z, r) with z = r
 
     while (iter++ < maxit) {
+        // one read-back per iteration: (t, p) stays on the device, the update kernel forms alpha from it (and does nothing when
+        // |(t, p)| <= 1e-40, in which case the host leaves the loop below exactly like SSS_cycle.cu:190)
         spmv(h, A, MODE_MXY, RED_NONE, p, t, nullptr, 0.0);          // t = A p
-        temp2 = dev_dot(h, m, t, p);                                 // (t, p)
-        if (fabs(temp2) > SMALLF2) alpha = temp1 / temp2;
-        else goto restore;
-        LAUNCH(cg_update_kernel, ug, BLOCK, h->stream, m, alpha, p, t, u, r, h->d_partial, h->partial_stride);
+        launch_dot(h, m, t, p, h->d_scal + 4);                       // (t, p)
+        LAUNCH(cg_update_kernel, ug, BLOCK, h->stream, m, temp1, (const double *)(h->d_scal + 4), p, t, u, r, h->d_partial, h->partial_stride);
         LAUNCH(reduce_partials_kernel, 1, BLOCK, h->stream, h->d_partial, ug, h->partial_stride, 2, 1, h->d_scal + 1);
         launch_dot(h, m, r, r, h->d_scal);                           // (r, r): absres^2 and the next (z, r)
-        fetch_scalars(h, 4);
+        fetch_scalars(h, 5);
+        temp2 = h->h_scal[4];
+        if (fabs(temp2) > SMALLF2) alpha = temp1 / temp2;
+        else goto restore;
         const double rr = h->h_scal[0], uu = h->h_scal[1], pp = h->h_scal[2];
         infnormu = h->h_scal[3];
         absres = sqrt(rr);
@@ -894,11 +900,19 @@ void cycle_from(amgb200_hier *h, int lstart) {
         while (l < nl - 1) {
             Level &lv = h->L[l];
             visits[l]++;
-            { PhaseTimer pt(h, 0, l); smooth(h, l, h->pars.pre_iter); }
+            {
+                PhaseTimer pt(h, 0, l);
+                if (lv.lo && lv.x_is_zero && h->pars.pre_iter >= 1) {        // first sweep from x = 0: lower triangle only (bit-identical, see upload)
+                    smooth_level(h, *lv.lo, 1);
+                    smooth(h, l, h->pars.pre_iter - 1);
+                } else smooth(h, l, h->pars.pre_iter);
+                lv.x_is_zero = false;
+            }
             { PhaseTimer pt(h, 1, l); spmv(h, lv.spmvA(), MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0); }
             { PhaseTimer pt(h, 2, l); spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[l + 1].b, nullptr, 0.0); }
             l++;
             dev_zero(h, h->L[l].n, h->L[l].x);
+            h->L[l].x_is_zero = true;
         }
         { PhaseTimer pt(h, 4); coarse_solve(h, h->L[nl - 1].A.v, h->L[nl - 1].b, h->L[nl - 1].x, tol, nullptr); }
         while (l > lstart) {
@@ -1004,6 +1018,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     const bool df_all = getenv("AMGB200_DF_ALL") && atoi(getenv("AMGB200_DF_ALL"));       // also SELL levels the streaming kernels took
     if (getenv("AMGB200_DF_AHEAD")) h->df_ahead = std::max(1, atoi(getenv("AMGB200_DF_AHEAD")));
     const double dfw_min_width = getenv("AMGB200_DFW_MIN_WIDTH") ? atof(getenv("AMGB200_DFW_MIN_WIDTH")) : 150.0;
+    const bool use_lower = !(getenv("AMGB200_NO_LOWER") && atoi(getenv("AMGB200_NO_LOWER")));
 
     const double t0 = now_s();
     const int nl = h->nl;
@@ -1318,6 +1333,47 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         lv.pattern_symmetric = S.pattern_symmetric;
         if (lv.smoothed) {
             setup_smoother(lv, lay, S, c.A);
+            // Pre-smoothing on a coarse level starts from x = 0 (SSS_cycle.cu:929).  In its first sweep every column that has not been
+            // updated yet contributes a*0 = +-0 and t - (+-0) = t exactly (t is never -0: b comes out of sums that start at +0.0, and a
+            // difference that cancels is +0), so those entries can leave the in-order chain: the first sweep is a forward substitution
+            // with the lower triangle of the schedule numbering.  Built for the chain-bound levels (streaming kernels) only.
+            if (l >= 1 && !natural[l] && use_lower && (lv.strategy == 4 || lv.strategy == 5)) {
+                const double tl = now_s();
+                const int n = c.A.num_rows;
+                std::vector<int> rp((size_t)n + 1, 0);
+#pragma omp parallel for schedule(static)
+                for (int i = 0; i < n; ++i) {
+                    int cnt = 0;
+                    const int pi = S.pos[i];
+                    for (int q = c.A.row_ptr[i]; q < c.A.row_ptr[i + 1]; ++q) cnt += S.pos[c.A.col_idx[q]] <= pi;
+                    rp[i + 1] = cnt;
+                }
+                for (int i = 0; i < n; ++i) rp[i + 1] += rp[i];
+                std::vector<int> ci((size_t)rp[n]);
+                std::vector<double> va((size_t)rp[n]);
+#pragma omp parallel for schedule(static)
+                for (int i = 0; i < n; ++i) {
+                    int w = rp[i];
+                    const int pi = S.pos[i];
+                    for (int q = c.A.row_ptr[i]; q < c.A.row_ptr[i + 1]; ++q)
+                        if (S.pos[c.A.col_idx[q]] <= pi) { ci[w] = c.A.col_idx[q]; va[w] = c.A.val[q]; ++w; }
+                }
+                amgb200_mat Alow = {n, n, rp[n], rp.data(), ci.data(), va.data()};
+                Level *lo = new Level();
+                lo->n = lv.n; lo->smoothed = true;
+                lo->x = lv.x; lo->b = lv.b;                                  // shared, not owned
+                DevLayout llo;
+                put_matrix(lo->A, llo, Alow, S, lv.d_order, &S, d_pos[l], KIND_CSR, &S.wf_row_ptr, "A(lower)", l);
+                setup_smoother(*lo, llo, S, Alow);
+                if (lo->strategy == 4 || lo->strategy == 5) lv.lo = lo;
+                else {                                                       // (would fall back to a barrier kernel: not worth it)
+                    lo->A.release();
+                    dev_free(lo->d_item_wf); dev_free(lo->d_wf_item_ptr); dev_free(lo->d_stream); dev_free(lo->d_blk_ptr); dev_free(lo->d_wf_row_ptr);
+                    dev_free(lo->d_rec); dev_free(lo->d_hint);
+                    delete lo;
+                }
+                tl_note("lower", l, now_s() - tl);
+            }
             if (natural[l]) {
                 // backward sweeps: own schedule, layout and vectors; d_fb maps its numbering into this level's
                 lv.natural = true;
@@ -1391,6 +1447,11 @@ void amgb200_free(amgb200_hier *h) {
         dev_free(lv.d_order); dev_free(lv.x); dev_free(lv.b); dev_free(lv.wp);
         dev_free(lv.d_item_wf); dev_free(lv.d_wf_item_ptr); dev_free(lv.d_fb); dev_free(lv.d_stream); dev_free(lv.d_blk_ptr); dev_free(lv.d_wf_row_ptr);
         dev_free(lv.d_rec); dev_free(lv.d_hint);
+        if (lv.lo) {
+            lv.lo->A.release();
+            dev_free(lv.lo->d_item_wf); dev_free(lv.lo->d_wf_item_ptr); dev_free(lv.lo->d_stream); dev_free(lv.lo->d_blk_ptr); dev_free(lv.lo->d_wf_row_ptr);
+            delete lv.lo;
+        }
         if (lv.bk) {
             dev_free(lv.bk->d_rec); dev_free(lv.bk->d_hint);
             lv.bk->A.release();
@@ -1466,7 +1527,10 @@ long long amgb200_device_bytes(const amgb200_hier *h) {
 }
 long long amgb200_level_chain_terms(const amgb200_hier *h, int level) {
     check_level(h, level);
-    return h->L[level].chain_terms;
+    const Level &lv = h->L[level];
+    const int sweeps = h->pars.pre_iter + h->pars.post_iter;
+    if (lv.lo && sweeps > 0) return (lv.chain_terms * (sweeps - 1) + lv.lo->chain_terms) / sweeps;     // (mean per sweep of a cycle: the first one runs on the lower triangle)
+    return lv.chain_terms;
 }
 const char *amgb200_level_kernel(const amgb200_hier *h, int level) {
     check_level(h, level);
@@ -1739,6 +1803,7 @@ void amgb200_restrict_from(amgb200_hier *h, int level) {
     if (!lv.R.valid) { fprintf(stderr, "libamgb200: level %d has no transfer operators\n", level); exit(72); }
     spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[level + 1].b, nullptr, 0.0);
     dev_zero(h, h->L[level + 1].n, h->L[level + 1].x);
+    h->L[level + 1].x_is_zero = true;
 }
 // the cycle on levels >= level (b_level and x_level already set), V-cycle only when level > 0
 void amgb200_cycle_from(amgb200_hier *h, int level) {

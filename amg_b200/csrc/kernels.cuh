@@ -2007,10 +2007,15 @@ __global__ void __launch_bounds__(1024) dot_seq_kernel(int n, const double *__re
 
 // CG update (amg/Solve/SSS_cycle.cu:196-250): u += alpha p ; r += (-alpha) t ; tree partials of
 // u.u, p.p and max|u| (they only steer the safeguards) -> partial[q*stride + block], q = 0..2
-__global__ void __launch_bounds__(BLOCK) cg_update_kernel(int n, double alpha, const double *__restrict__ p, const double *__restrict__ t,
-                                                          double *u, double *r, double *partial, int stride) {
+// alpha = temp1 / (t, p) is formed ON THE DEVICE from the dot product the previous kernel left in *tp (the same IEEE division the
+// host would do), so that one iteration needs a single read-back; |(t, p)| <= 1e-40 (SSS_cycle.cu:190: leave the loop) -> no update
+__global__ void __launch_bounds__(BLOCK) cg_update_kernel(int n, double temp1, const double *__restrict__ tp, const double *__restrict__ p,
+                                                          const double *__restrict__ t, double *u, double *r, double *partial, int stride) {
     __shared__ double red[32];
     double uu = 0.0, pp = 0.0, um = 0.0;
+    const double temp2 = *tp;
+    if (!(fabs(temp2) > 1e-40)) return;
+    const double alpha = __ddiv_rn(temp1, temp2);
     const double nalpha = -alpha;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double pi = p[i];
