@@ -78,6 +78,7 @@ EXPORTS = [
     "amgb200_l0_residual", "amgb200_l0_prolong", "amgb200_restrict_from", "amgb200_cycle_from",
     "amgb200_vec_to_schedule", "amgb200_vec_to_natural", "amgb200_sync", "amgb200_setup_ex", "amgb200_interp_device",
     "amgb200_ipc_export", "amgb200_ipc_open", "amgb200_peer_plan", "amgb200_peer_run", "amgb200_read_mtx", "amgb200_level_download",
+    "amgb200_level_resid_restrict",
 ]
 
 _lib = None
@@ -111,6 +112,8 @@ def lib():
         L.amgb200_level_smooth.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p]
         L.amgb200_level_residual.restype = C.c_double
         L.amgb200_level_residual.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]
+        L.amgb200_level_resid_restrict.restype = C.c_int
+        L.amgb200_level_resid_restrict.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]
         L.amgb200_coarse_solve.restype = C.c_int
         L.amgb200_coarse_solve.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_double, c_int_p]
         L.amgb200_num_levels.restype = C.c_int

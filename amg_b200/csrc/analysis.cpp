@@ -406,4 +406,84 @@ void build_stream_cluster(const amgb200_mat &A, const Schedule &S, int C, Cluste
     }
 }
 
+void build_fused_plan(const DevLayout &la, const DevLayout &lr, const Schedule &Sf, const Schedule &Sc, const amgb200_mat &Rm, int nch, int lag, int tickets, FusedPlan &F) {
+    const int nA = la.nitems(), nR = lr.nitems(), nf = Sf.n;
+    nch = std::max(1, std::min(nch, 32767));
+    tickets = std::max(1, tickets);
+    F.nch = nch; F.tickets = tickets;
+    F.slice_chunk.assign((size_t)nA, 0);
+    // per 128-byte line of r (16 consecutive schedule positions): first and last chunk that write into it.  A slice of R waits for
+    // every chunk that owns a part of a line it touches, so a line is final when an SM first loads it and may stay in its
+    // (non-coherent) L1 for the rest of the launch.
+    const int nlines = (nf + 15) / 16;
+    std::vector<unsigned short> pos_chunk((size_t)nf);
+#pragma omp parallel for schedule(static)
+    for (int s = 0; s < nA; ++s) {
+        const int c = (int)std::min<long long>(nch - 1, (long long)Sf.order[la.slice_row[s]] * nch / std::max(1, nf));
+        F.slice_chunk[s] = c;
+        for (int p = la.slice_row[s]; p < la.slice_row[s + 1]; ++p) pos_chunk[p] = (unsigned short)c;
+    }
+    std::vector<unsigned> line_need((size_t)nlines);
+#pragma omp parallel for schedule(static)
+    for (int ln = 0; ln < nlines; ++ln) {
+        unsigned lo = 0xffffu, hi = 0;
+        for (int p = ln * 16; p < std::min(nf, ln * 16 + 16); ++p) { lo = std::min<unsigned>(lo, pos_chunk[p]); hi = std::max<unsigned>(hi, pos_chunk[p]); }
+        line_need[ln] = lo | hi << 16;
+    }
+    F.rneed.assign((size_t)nR, 0u);
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < nR; ++t) {
+        unsigned lo = 0xffffu, hi = 0;
+        for (int p = lr.slice_row[t]; p < lr.slice_row[t + 1]; ++p) {
+            const int j = Sc.order[p];
+            for (int q = Rm.row_ptr[j]; q < Rm.row_ptr[j + 1]; ++q) {
+                const unsigned nd = line_need[Sf.pos[Rm.col_idx[q]] >> 4];
+                lo = std::min(lo, nd & 0xffffu); hi = std::max(hi, nd >> 16);
+            }
+        }
+        if (lo > hi) lo = hi = 0;                                           // (slice of empty rows)
+        F.rneed[t] = lo | hi << 16;
+    }
+    F.chunk_items.assign((size_t)nch, 0u);
+    for (int s = 0; s < nA; ++s) F.chunk_items[F.slice_chunk[s]]++;
+    std::vector<int> a_ptr((size_t)nch + 1, 0), r_ptr((size_t)nch + 2, 0);
+    for (int c = 0; c < nch; ++c) a_ptr[c + 1] = a_ptr[c] + (int)F.chunk_items[c];
+    auto r_key = [&](int t) { const unsigned lo = F.rneed[t] & 0xffffu, hi = F.rneed[t] >> 16; return hi - lo >= 32u ? nch : (int)hi; };
+    for (int t = 0; t < nR; ++t) r_ptr[r_key(t) + 1]++;
+    for (int c = 0; c <= nch; ++c) r_ptr[c + 1] += r_ptr[c];
+    std::vector<int> a_sorted((size_t)nA), r_sorted((size_t)nR);
+    {
+        std::vector<int> fa(a_ptr.begin(), a_ptr.end() - 1), fr(r_ptr.begin(), r_ptr.end() - 1);
+        for (int s = 0; s < nA; ++s) a_sorted[fa[F.slice_chunk[s]]++] = s;
+        for (int t = 0; t < nR; ++t) r_sorted[fr[r_key(t)]++] = t;
+    }
+    F.work.clear();
+    F.block_info.clear();
+    F.work.reserve((size_t)nA + nR + (size_t)tickets * (2 * nch + 2));
+    auto emit_a = [&](int c) {
+        for (int q0 = a_ptr[c]; q0 < a_ptr[c + 1]; q0 += tickets) {
+            const int cnt = std::min(tickets, a_ptr[c + 1] - q0);
+            for (int q = 0; q < tickets; ++q) F.work.push_back(q < cnt ? a_sorted[q0 + q] : FUSED_NOP);
+            F.block_info.push_back(c | cnt << 16);
+        }
+    };
+    auto emit_r = [&](int key) {
+        for (int q0 = r_ptr[key]; q0 < r_ptr[key + 1]; q0 += tickets) {
+            const int cnt = std::min(tickets, r_ptr[key + 1] - q0);
+            unsigned lo = 0xffffu, hi = 0;
+            for (int q = 0; q < tickets; ++q) {
+                F.work.push_back(q < cnt ? ~r_sorted[q0 + q] : FUSED_NOP);
+                if (q < cnt) { lo = std::min(lo, F.rneed[r_sorted[q0 + q]] & 0xffffu); hi = std::max(hi, F.rneed[r_sorted[q0 + q]] >> 16); }
+            }
+            if (key == nch) { lo = 0; hi = (unsigned)nch - 1; }
+            F.block_info.push_back((int)(0x80000000u | lo | hi << 16));
+        }
+    };
+    for (int c = 0; c < nch + lag; ++c) {
+        if (c < nch) emit_a(c);
+        if (c - lag >= 0 && c - lag < nch) emit_r(c - lag);
+    }
+    emit_r(nch);
+}
+
 }  // namespace amgb200

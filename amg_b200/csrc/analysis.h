@@ -132,4 +132,21 @@ void build_sell_structure(const amgb200_mat &M, const int *row_order, const std:
 
 int choose_kind(const amgb200_mat &M, double sell_max_mean);
 
+// Ticket list of the fused residual (+) restriction launch (kernels.cuh, resid_restrict_kernel).  la: SELL layout of A_l (rows in
+// schedule Sf), lr: SELL layout of R_l (rows in schedule Sc of level l+1), Rm: R_l as the reference stores it (natural numbering).
+// The slices of A are binned into nch chunks by the natural index of their first row; a slice of R is keyed by the last chunk
+// whose residual rows it reads; tickets: A(chunk 0) .. A(chunk c), R(last chunk c - lag) ..; slices of R that read 32 chunks or
+// more wait for everything and come last.  The list is cut into blocks of `tickets` entries that are all slices of A of one chunk
+// or all slices of R (padded with FUSED_NOP).  Invariant: every block only depends on blocks with smaller numbers.
+constexpr int FUSED_NOP = 0x7fffffff;
+struct FusedPlan {
+    std::vector<int> work;             // >= 0: slice of A, < 0: ~slice of R, FUSED_NOP: padding
+    std::vector<int> block_info;       // A: chunk | count << 16 ; R: 0x80000000 | first chunk | last chunk << 16
+    std::vector<int> slice_chunk;      // slice of A -> chunk
+    std::vector<unsigned> rneed;       // slice of R -> first chunk | last chunk << 16
+    std::vector<unsigned> chunk_items; // slices of A per chunk
+    int nch = 0, tickets = 0;
+};
+void build_fused_plan(const DevLayout &la, const DevLayout &lr, const Schedule &Sf, const Schedule &Sc, const amgb200_mat &Rm, int nch, int lag, int tickets, FusedPlan &F);
+
 }  // namespace amgb200

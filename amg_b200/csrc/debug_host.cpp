@@ -3,6 +3,7 @@
 // Gauss-Seidel rows wavefront by wavefront in REVERSE intra-wavefront order.  If the schedule is
 // right (rows of one wavefront are independent) the result is bit-identical to the reference's
 // sequential sweep.  Not a compute path of the product: nothing in hier.cu calls these.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -228,6 +229,80 @@ void amgb200_debug_spmv_walk(const amgb200_mat *M, int kind, const double *x, do
             y[k] = t;
         }
     }
+}
+
+// The fused residual (+) restriction launch (kernels.cuh, resid_restrict_kernel) executed on the CPU through the device layouts and
+// the ticket list: tickets in list order (the legal execution of a single warp), r poisoned with NaN beforehand.  Checks the
+// invariants the kernel relies on -- every slice exactly once, a slice of R only after every slice of A in the chunks it declares,
+// every residual row it reads inside those chunks.  x, b, r (n_l) and bc (n_{l+1}) in natural numbering.  Ac / markC describe level
+// l+1 (markC == NULL: its schedule is the identity, as on the coarsest level).  Returns 0, or a negative code naming the invariant.
+int amgb200_debug_fused_walk(const amgb200_mat *A, const int *markA, const amgb200_mat *Ac, const int *markC, int coarsest, const amgb200_mat *R,
+                             int nch, int lag, int tickets, const double *x, const double *b, double *r, double *bc) {
+    Schedule Sf, Sc;
+    build_schedule(*A, markA, Sf);
+    if (coarsest) identity_schedule(Ac->num_rows, Sc); else build_schedule(*Ac, markC, Sc);
+    DevLayout la, lr;
+    build_layout(*A, Sf.order.data(), Sf.pos.data(), KIND_SELL, nullptr, la);
+    build_layout(*R, Sc.order.data(), Sf.pos.data(), KIND_SELL, nullptr, lr);
+    FusedPlan F;
+    build_fused_plan(la, lr, Sf, Sc, *R, nch, lag, tickets, F);
+    const int nA = la.nitems(), nR = lr.nitems(), n = Sf.n, nc = Sc.n;
+    if (F.work.size() != F.block_info.size() * (size_t)F.tickets) return -1;
+    std::vector<double> xs(n), bs(n), rs(n, std::nan("")), bcs(nc, std::nan(""));
+    for (int k = 0; k < n; ++k) { xs[k] = x[Sf.order[k]]; bs[k] = b[Sf.order[k]]; }
+    std::vector<unsigned> cnt((size_t)F.nch, 0u);
+    std::vector<char> seenA(nA, 0), seenR(nR, 0);
+    std::vector<int> slice_of(n);
+    for (int s = 0; s < nA; ++s) for (int k = la.slice_row[s]; k < la.slice_row[s + 1]; ++k) slice_of[k] = s;
+    auto row_sum = [](const DevLayout &L, int s, int k, const std::vector<double> &v, auto &&visit) {
+        const long long p0 = L.slice_ptr[s];
+        const int width = (int)((L.slice_ptr[s + 1] - p0) / 32), lane = k - L.slice_row[s];
+        double t = 0.0;
+        for (int e = 0; e < width; ++e) {
+            const int j = L.col[(size_t)(p0 + 32LL * e + lane)];
+            if (j >= 0) { visit(j); t += L.val[(size_t)(p0 + 32LL * e + lane)] * v[j]; }
+        }
+        return t;
+    };
+    for (size_t blk = 0; blk < F.block_info.size(); ++blk) {
+        const unsigned info = (unsigned)F.block_info[blk];
+        const int *wk = F.work.data() + blk * (size_t)F.tickets;
+        if (!(info >> 31)) {
+            const unsigned c = info & 0xffffu;
+            unsigned done = 0;
+            for (int q = 0; q < F.tickets; ++q) {
+                const int w = wk[q];
+                if (w == FUSED_NOP) continue;
+                if (w < 0 || w >= nA || seenA[w] || (unsigned)F.slice_chunk[w] != c) return -2;
+                seenA[w] = 1; ++done;
+                for (int k = la.slice_row[w]; k < la.slice_row[w + 1]; ++k) rs[k] = bs[k] + row_sum(la, w, k, xs, [](int) {}) * -1.0;
+            }
+            if (done != info >> 16) return -6;
+            cnt[c] += done;
+        } else {
+            const unsigned lo = info & 0xffffu, hi = (info >> 16) & 0x7fffu;
+            for (unsigned c = lo; c <= hi; ++c)
+                if (cnt[c] != F.chunk_items[c]) return -4;                     // the kernel would wait here for a LARGER block: deadlock
+            for (int q = 0; q < F.tickets; ++q) {
+                const int w = wk[q];
+                if (w == FUSED_NOP) continue;
+                const int t = ~w;
+                if (w >= 0 || t >= nR || seenR[t]) return -3;
+                seenR[t] = 1;
+                int bad = 0;
+                for (int k = lr.slice_row[t]; k < lr.slice_row[t + 1]; ++k)
+                    bcs[k] = row_sum(lr, t, k, rs, [&](int j) {                 // every row of the 128-byte line of r_j must be final (lines stay in L1)
+                        for (int p = j & ~15; p < std::min(n, (j & ~15) + 16); ++p) { const unsigned c = (unsigned)F.slice_chunk[slice_of[p]]; if (c < lo || c > hi) bad = 1; }
+                    });
+                if (bad) return -5;
+            }
+        }
+    }
+    for (int s = 0; s < nA; ++s) if (!seenA[s]) return -7;
+    for (int t = 0; t < nR; ++t) if (!seenR[t]) return -7;
+    for (int k = 0; k < n; ++k) r[Sf.order[k]] = rs[k];
+    for (int k = 0; k < nc; ++k) bc[Sc.order[k]] = bcs[k];
+    return 0;
 }
 
 }  // extern "C"

@@ -302,6 +302,16 @@ struct Level {
                                        // been updated -- the strictly lower triangle in schedule numbering; same schedule, shares x and b
     bool x_is_zero = false;            // x was zero-filled by the cycle and not touched since
     int *d_fb = nullptr;               // position in this level's numbering of row k of bk's numbering
+    // residual (+) restriction in one launch (resid_restrict_kernel): ticket list, chunk tables, completion counters
+    struct Fused {
+        bool valid = false;
+        int *d_work = nullptr, *d_block_info = nullptr;
+        unsigned *d_chunk_items = nullptr, *d_cnt = nullptr;
+        int nblocks = 0, nch = 0, grid = 0;
+        unsigned epoch = 0;
+        bool one_a = false, one_r = false;
+        void release() { dev_free(d_work); dev_free(d_block_info); dev_free(d_chunk_items); dev_free(d_cnt); valid = false; }
+    } rr;
 };
 
 }  // namespace
@@ -395,6 +405,27 @@ void spmv(amgb200_hier *h, const DMat &A, int mode, int red, const double *x, do
     if (A.kind == KIND_SELL) spmv_k<0, true>(h, A, mode, red, x, y, b, alpha);
     else if (h->exact) spmv_k<1, true>(h, A, mode, red, x, y, b, alpha);
     else spmv_k<1, false>(h, A, mode, red, x, y, b, alpha);
+}
+
+static_assert(RR_NOP == FUSED_NOP, "padding ticket of the fused launch");
+// wp = b - A x ; b_{l+1} = R wp ; x_{l+1} = 0 in one launch (levels whose A and R are both thread-per-row layouts)
+const void *rr_kernel(bool one_a, bool one_r) {
+    return one_a ? (one_r ? (const void *)resid_restrict_kernel<true, true> : (const void *)resid_restrict_kernel<true, false>)
+                 : (one_r ? (const void *)resid_restrict_kernel<false, true> : (const void *)resid_restrict_kernel<false, false>);
+}
+void resid_restrict(amgb200_hier *h, int l, bool zero_xc) {
+    Level &lv = h->L[l];
+    Level &lc = h->L[l + 1];
+    Level::Fused &f = lv.rr;
+    RRPlan pl;
+    pl.work = f.d_work; pl.nblocks = f.nblocks; pl.block_info = f.d_block_info; pl.chunk_items = f.d_chunk_items;
+    pl.cnt = f.d_cnt; pl.nch = f.nch; pl.epoch = ++f.epoch;
+    DMat A = lv.spmvA(), R = lv.R.v;
+    const double *x = lv.x, *b = lv.b;
+    double *r = lv.wp, *bc = lc.b, *xc = zero_xc ? lc.x : nullptr;
+    void *args[] = {&A, &R, &pl, &x, &b, &r, &bc, &xc};
+    CUDA_CHECK(cudaLaunchCooperativeKernel(rr_kernel(f.one_a, f.one_r), dim3(f.grid), dim3(BLOCK), args, 0, h->stream));
+    ++g_launches;
 }
 
 const void *df_kernel(int sch) {
@@ -908,10 +939,16 @@ void cycle_from(amgb200_hier *h, int lstart) {
                 } else smooth(h, l, h->pars.pre_iter);
                 lv.x_is_zero = false;
             }
-            { PhaseTimer pt(h, 1, l); spmv(h, lv.spmvA(), MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0); }
-            { PhaseTimer pt(h, 2, l); spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[l + 1].b, nullptr, 0.0); }
-            l++;
-            dev_zero(h, h->L[l].n, h->L[l].x);
+            if (lv.rr.valid) {
+                PhaseTimer pt(h, 1, l);
+                resid_restrict(h, l, true);
+                l++;
+            } else {
+                { PhaseTimer pt(h, 1, l); spmv(h, lv.spmvA(), MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0); }
+                { PhaseTimer pt(h, 2, l); spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[l + 1].b, nullptr, 0.0); }
+                l++;
+                dev_zero(h, h->L[l].n, h->L[l].x);
+            }
             h->L[l].x_is_zero = true;
         }
         { PhaseTimer pt(h, 4); coarse_solve(h, h->L[nl - 1].A.v, h->L[nl - 1].b, h->L[nl - 1].x, tol, nullptr); }
@@ -1278,6 +1315,37 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         h->L[l].d_order = dev_upload(sched[l].order);
         if (dev_fill) { d_pos[l] = dev_upload(sched[l].pos); temps.push_back(d_pos[l]); }
     }
+    // ticket list and chunk tables of the fused residual (+) restriction launch (kernels.cuh, resid_restrict_kernel)
+    const bool use_fused = !(getenv("AMGB200_NO_FUSED") && atoi(getenv("AMGB200_NO_FUSED")));
+    // (a cooperative launch with in-kernel hand-offs loses on small levels: 2D 256^2 level 0, 65 536 rows, 13.6 vs 11.5 us)
+    const int rr_min_rows = getenv("AMGB200_RR_MIN_ROWS") ? atoi(getenv("AMGB200_RR_MIN_ROWS")) : 262144;
+    const bool rr_all = getenv("AMGB200_RR_ALL") && atoi(getenv("AMGB200_RR_ALL"));
+    auto build_fused = [&](Level &lv, const DevLayout &la, const DevLayout &lr, const Schedule &Sf, const Schedule &Sc, const amgb200_mat &Rm) {
+        const int nA = la.nitems(), nR = lr.nitems();
+        bool f_one_a, f_one_r;
+        // chunks: 1/32 of the level, at least 4 ticket blocks each; lag: twice the blocks of A the resident grid holds in flight, in chunks, + 2
+        f_one_a = la.max_row <= 8; f_one_r = lr.max_row <= 8;
+        int per_sm = 0;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rr_kernel(f_one_a, f_one_r), BLOCK, 0));
+        if (getenv("AMGB200_RR_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("AMGB200_RR_PER_SM"))));
+        int nch = std::max(1, std::min(32, nA / (4 * RR_TICKETS)));
+        if (getenv("AMGB200_RR_CHUNKS")) nch = std::max(1, std::min(4096, atoi(getenv("AMGB200_RR_CHUNKS"))));
+        const int blocks_per_chunk = std::max(1, nA / nch / RR_TICKETS);
+        int lag = 2 * ((per_sm * h->num_sms + blocks_per_chunk - 1) / blocks_per_chunk) + 2;   // (measured at 256^3: lag 3 482 us, 5 480, 8 470)
+        if (getenv("AMGB200_RR_LAG")) lag = std::max(0, atoi(getenv("AMGB200_RR_LAG")));
+        FusedPlan P;
+        build_fused_plan(la, lr, Sf, Sc, Rm, nch, lag, RR_TICKETS, P);
+        Level::Fused &f = lv.rr;
+        f.nblocks = (int)P.block_info.size(); f.nch = P.nch; f.epoch = 0;
+        f.one_a = f_one_a; f.one_r = f_one_r;
+        f.d_work = dev_upload(P.work); f.d_block_info = dev_upload(P.block_info); f.d_chunk_items = dev_upload(P.chunk_items);
+        f.d_cnt = dev_alloc<unsigned>((size_t)P.nch);
+        CUDA_CHECK(cudaMemset(f.d_cnt, 0, (size_t)P.nch * sizeof(unsigned)));
+        f.grid = std::max(1, std::min(per_sm * h->num_sms, f.nblocks));
+        f.valid = true;
+        if (h->opt.verbose >= 2) printf("      fused residual+restriction: %d + %d slices in %d chunks (lag %d), %d blocks of %d tickets, %d CTAs (%d per SM)\n", nA, nR, P.nch, lag, f.nblocks, RR_TICKETS, f.grid, per_sm);
+    };
+
     // one matrix: host layout + copy, or slice table + device fill
     auto put_matrix = [&](DevMatOwner &dst, DevLayout &lay, const amgb200_mat &M, const Schedule &rowS, const int *d_row_order, const Schedule *colS,
                           const int *d_col_pos, int kind, const std::vector<int> *breaks, const char *what, int l) {
@@ -1320,8 +1388,9 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         }
         put_matrix(lv.A, lay, c.A, S, lv.d_order, &S, d_pos[l], gs_kind, lv.smoothed ? &S.wf_row_ptr : nullptr, "A", l);
         max_items = std::max(max_items, lay.nitems());
+        DevLayout lsp_keep;
         if (gs_kind != kind_of(c.A)) {
-            DevLayout lsp;
+            DevLayout &lsp = lsp_keep;
             put_matrix(lv.Asp, lsp, c.A, S, lv.d_order, &S, d_pos[l], kind_of(c.A), nullptr, "A(spmv)", l);
             max_items = std::max(max_items, lsp.nitems());
         }
@@ -1406,6 +1475,16 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             max_items = std::max(max_items, lp.nitems());
             put_matrix(lv.R, lr, c.R, sched[l + 1], h->L[l + 1].d_order, &S, d_pos[l], kind_of(c.R), nullptr, "R", l);
             max_items = std::max(max_items, lr.nitems());
+            // residual (+) restriction in one launch: both operators thread-per-row (the levels that carry the bytes)
+            const DevLayout &la = lv.Asp.valid ? lsp_keep : lay;
+            // (measured: the instances for rows longer than one register chunk need 80-114 registers and lose to the separate kernels --
+            // 256^3 level 1: 691 vs 586 us -- so only single-chunk operators, i.e. level 0 of the 5-/7-point problems, take it by default)
+            const bool rr_short = la.max_row <= 8 && lr.max_row <= 8;
+            if (use_fused && (rr_short || rr_all) && la.kind == KIND_SELL && lr.kind == KIND_SELL && lv.n >= rr_min_rows && la.nitems() >= 1 && lr.nitems() >= 1) {
+                const double tl = now_s();
+                build_fused(lv, la, lr, S, sched[l + 1], c.R);
+                tl_note("fused", l, now_s() - tl);
+            }
         }
     }
     h->partial_stride = std::max(1184, (max_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
@@ -1447,6 +1526,7 @@ void amgb200_free(amgb200_hier *h) {
         dev_free(lv.d_order); dev_free(lv.x); dev_free(lv.b); dev_free(lv.wp);
         dev_free(lv.d_item_wf); dev_free(lv.d_wf_item_ptr); dev_free(lv.d_fb); dev_free(lv.d_stream); dev_free(lv.d_blk_ptr); dev_free(lv.d_wf_row_ptr);
         dev_free(lv.d_rec); dev_free(lv.d_hint);
+        lv.rr.release();
         if (lv.lo) {
             lv.lo->A.release();
             dev_free(lv.lo->d_item_wf); dev_free(lv.lo->d_wf_item_ptr); dev_free(lv.lo->d_stream); dev_free(lv.lo->d_blk_ptr); dev_free(lv.lo->d_wf_row_ptr);
@@ -1493,6 +1573,7 @@ double amgb200_algorithmic_bytes(const amgb200_hier *h, int level, int op) {
             case 2: return lv.R.valid ? S(lv.R.nnz, (long long)nc) + 8 * n + 8 * nc : 0;   // b_c = R r
             case 3: return lv.P.valid ? S(lv.P.nnz, lv.n) + 8 * nc + 16 * n : 0;           // x += P e
             case 4: return SA + 16 * n;                                       // y = A x
+            case 6: return lv.R.valid ? SA + 16 * n + S(lv.R.nnz, (long long)nc) + 8 * nc + 8 * nc : 0;   // residual (+) restriction (+ x_c = 0), r not counted
             default: return 0;
         }
     };
@@ -1685,6 +1766,33 @@ double amgb200_level_residual(amgb200_hier *h, int level, const double *x, const
     return nrm;
 }
 
+// wp = b - A x and b_{level+1} = R wp from host vectors in natural numbering, the way the cycle computes them (one fused launch
+// where the level has one, else two); returns 1 when the fused kernel ran
+int amgb200_level_resid_restrict(amgb200_hier *h, int level, const double *x, const double *b, double *r, double *bc) {
+    check_level(h, level);
+    check_level(h, level + 1);
+    Level &lv = h->L[level];
+    Level &lc = h->L[level + 1];
+    if (!lv.R.valid) { fprintf(stderr, "libamgb200: level %d has no transfer operators\n", level); exit(72); }
+    CUDA_CHECK(cudaMemcpyAsync(h->d_xnat, x, (size_t)lv.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h->d_bnat, b, (size_t)lv.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    to_schedule(h, level, h->d_xnat, lv.x);
+    to_schedule(h, level, h->d_bnat, lv.b);
+    if (lv.rr.valid) resid_restrict(h, level, true);
+    else {
+        spmv(h, lv.spmvA(), MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0);
+        spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, lc.b, nullptr, 0.0);
+        dev_zero(h, lc.n, lc.x);
+    }
+    lc.x_is_zero = true;
+    to_natural(h, level, lv.wp, h->d_xnat);
+    CUDA_CHECK(cudaMemcpyAsync(r, h->d_xnat, (size_t)lv.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    to_natural(h, level + 1, lc.b, h->d_bnat);
+    CUDA_CHECK(cudaMemcpyAsync(bc, h->d_bnat, (size_t)lc.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return lv.rr.valid ? 1 : 0;
+}
+
 int amgb200_coarse_solve(amgb200_hier *h, double *x, const double *b, double tol, int its[2]) {
     Level &lv = h->L[h->nl - 1];
     CUDA_CHECK(cudaMemcpyAsync(h->d_xnat, x, (size_t)lv.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -1702,7 +1810,7 @@ double amgb200_time_op(amgb200_hier *h, int level, int op, int reps) {
     check_level(h, level);
     Level &lv = h->L[level];
     if (reps < 1) reps = 1;
-    if ((op == 0 && !lv.smoothed) || ((op == 2 || op == 3) && !lv.P.valid)) return 0.0;
+    if ((op == 0 && !lv.smoothed) || ((op == 2 || op == 3 || op == 6) && !lv.P.valid)) return 0.0;
     cudaEvent_t a, b;
     CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
     const int nsw = getenv("AMGB200_TIMEOP_SWEEPS") ? std::max(1, atoi(getenv("AMGB200_TIMEOP_SWEEPS"))) : 1;   // (developer probe: sweeps per launch)
@@ -1712,6 +1820,14 @@ double amgb200_time_op(amgb200_hier *h, int level, int op, int reps) {
             case 1: spmv(h, lv.spmvA(), MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0); break;
             case 2: spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[level + 1].b, nullptr, 0.0); break;
             case 3: spmv(h, lv.P.v, MODE_AMXPY, RED_NONE, h->L[level + 1].x, lv.x, nullptr, 1.0); break;
+            case 6:                                  // what the cycle runs between pre-smoothing and the next level: fused, or three launches
+                if (lv.rr.valid) resid_restrict(h, level, true);
+                else {
+                    spmv(h, lv.spmvA(), MODE_RESID, RED_NONE, lv.x, lv.wp, lv.b, -1.0);
+                    spmv(h, lv.R.v, MODE_MXY, RED_NONE, lv.wp, h->L[level + 1].b, nullptr, 0.0);
+                    dev_zero(h, h->L[level + 1].n, h->L[level + 1].x);
+                }
+                break;
             default: spmv(h, lv.spmvA(), MODE_MXY, RED_NONE, lv.x, lv.wp, nullptr, 0.0); break;
         }
     };

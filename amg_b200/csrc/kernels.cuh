@@ -183,12 +183,12 @@ __device__ __forceinline__ void gs_finish_sell_one(SellItem<SCH> &it, double *x)
     }
     if (it.k < it.r1 && fabs(d) > GS_TINY) x[it.k] = gs_quotient(t, d, it.recip);
 }
-template <int SCH>
+template <int SCH, bool COH = false>
 __device__ __forceinline__ double spmv_finish_sell_one(SellItem<SCH> &it, const double *__restrict__ x) {
     double t = 0.0;
     double xv[SCH];
 #pragma unroll
-    for (int u = 0; u < SCH; ++u) xv[u] = it.j[u] >= 0 ? x[it.j[u]] : 0.0;
+    for (int u = 0; u < SCH; ++u) xv[u] = it.j[u] >= 0 ? ld_x<COH>(x + it.j[u]) : 0.0;
 #pragma unroll
     for (int u = 0; u < SCH; ++u)
         if (it.j[u] >= 0) t = __dadd_rn(t, __dmul_rn(it.a[u], xv[u]));
@@ -227,13 +227,13 @@ __device__ __forceinline__ void gs_finish_sell(SellItem<SCH> &it, double *x) {
 }
 
 // row sum t = sum_k a_k x_{j_k} from 0.0 in storage order (amg/SSS_utils.c:169-177, :190-200)
-template <int SCH>
+template <int SCH, bool COH = false>
 __device__ __forceinline__ double spmv_finish_sell(SellItem<SCH> &it, const double *__restrict__ x) {
     double t = 0.0;
     for (int e0 = 0; e0 < it.width; e0 += SCH) {
         double xv[SCH];
 #pragma unroll
-        for (int u = 0; u < SCH; ++u) xv[u] = it.j[u] >= 0 ? x[it.j[u]] : 0.0;
+        for (int u = 0; u < SCH; ++u) xv[u] = it.j[u] >= 0 ? ld_x<COH>(x + it.j[u]) : 0.0;
         int jn[SCH];
         double an[SCH];
         const bool more = e0 + SCH < it.width;
@@ -1947,6 +1947,92 @@ __global__ void __launch_bounds__(BLOCK, (KIND == 0 && ONE && MODE == MODE_AMXPY
     if (RED != RED_NONE) {
         const double s = block_sum(contrib, red);
         if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Residual (+) restriction in ONE launch (amg/Solve/SSS_cycle.cu:916-921: wp = b - A x ; b_{l+1} = R wp ; :929 x_{l+1} = 0).
+// Exactness fixes the arithmetic: every coarse entry sums its w_u * r_{i_u} in R's storage order in one thread, so the fine
+// residuals must exist as numbers before a coarse row starts; what fusion can remove is the second trip of r through HBM and
+// the launch boundary.  The work of both operators is therefore dealt to ONE persistent grid as a single ticket list in which
+// locality, not the schedule numbering, decides the order: the slices of A are binned into `nch` chunks by the NATURAL index of
+// their first row (the schedule numbering is wavefront-major, natural indices follow the grid), the slices of R are keyed by the
+// last chunk whose residual rows they read, and the list is  A(chunk 0), A(chunk 1), R(last chunk 0), A(chunk 2), R(last chunk 1) ...
+// cut into blocks of RR_TICKETS tickets that are all slices of A of ONE chunk or all slices of R (padded with no-ops).  A CTA takes
+// blocks round-robin in increasing order: after a block of A one thread publishes it (__syncthreads, fence, one atomic on the
+// chunk's completion counter -- the other warps are already in the next block); before a block of R one warp polls the counters of
+// the chunks the block reads (complete in the steady state because of the lag, which covers the blocks in flight), then the rows
+// gather r while its lines are still in L2 (a chunk is 1/32 of the vector: 4 MB at 256^3).  The chunk range of a block covers
+// every chunk that writes into a 128-byte line the block touches, so the lines are final and the gathers may use L1.  Every block only waits for blocks with smaller numbers and
+// the grid is co-resident (cooperative launch), so the earliest unfinished block is always runnable.  Counters are never reset:
+// launch `epoch` completes chunk c at epoch * items(c) (mod 2^32).
+// ------------------------------------------------------------------------------------------
+constexpr int RR_PER_WARP = 4;
+constexpr int RR_TICKETS = WARPS_PER_BLOCK * RR_PER_WARP;
+constexpr int RR_NOP = 0x7fffffff;
+#ifndef AMGB200_RR_COH
+#define AMGB200_RR_COH 0
+#endif
+constexpr bool RR_COH = AMGB200_RR_COH != 0;   // 1: gather r at L2 (developer build); 0: through L1 -- every line a slice of R touches is final before it starts (analysis.cpp)
+struct RRPlan {
+    const int *work;               // tickets: >= 0 slice of A (residual), < 0: ~slice of R (restriction), RR_NOP: padding
+    int nblocks;                   // blocks of RR_TICKETS tickets
+    const int *block_info;         // per block: slices of A -> chunk | count << 16 ; slices of R -> 0x80000000 | first chunk | last chunk << 16 (bits 16..30)
+    const unsigned *chunk_items;   // slices of A per chunk
+    unsigned *cnt;                 // [nch]: completed slices per chunk
+    int nch;
+    unsigned epoch;
+};
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <bool ONE_A, bool ONE_R>
+__global__ void __launch_bounds__(BLOCK) resid_restrict_kernel(DMat A, DMat R, RRPlan pl, const double *__restrict__ x, const double *__restrict__ b,
+                                                               double *r, double *bc, double *xc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int blk = blockIdx.x; blk < pl.nblocks; blk += gridDim.x) {
+        const unsigned info = (unsigned)pl.block_info[blk];
+        const int *wk = pl.work + (size_t)blk * RR_TICKETS;
+        if (!(info >> 31)) {
+#pragma unroll 1
+            for (int u = 0; u < RR_PER_WARP; ++u) {
+                const int w = wk[u * WARPS_PER_BLOCK + warp];
+                if (w == RR_NOP) continue;
+                SellItem<8> it;
+                it.prologue(A, w, lane);
+                const double s = ONE_A ? spmv_finish_sell_one(it, x) : spmv_finish_sell(it, x);
+                if (it.k < it.r1) __stcg(r + it.k, __dadd_rn(b[it.k], __dmul_rn(s, -1.0)));
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(pl.cnt + (info & 0xffffu), info >> 16);
+            }
+        } else {
+            const unsigned lo = info & 0xffffu, hi = (info >> 16) & 0x7fffu;
+            if (warp == 0) {
+                for (unsigned c0 = lo; c0 <= hi; c0 += 32) {
+                    const unsigned c = c0 + lane;
+                    for (;;) {
+                        const bool ok = c > hi || (int)(ld_acquire_u32(pl.cnt + c) - pl.epoch * pl.chunk_items[c]) >= 0;
+                        if (__all_sync(FULL, ok)) break;
+                        __nanosleep(256);
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int u = 0; u < RR_PER_WARP; ++u) {
+                const int w = wk[u * WARPS_PER_BLOCK + warp];
+                if (w == RR_NOP) continue;
+                SellItem<8> it;
+                it.prologue(R, ~w, lane);
+                const double acc = ONE_R ? spmv_finish_sell_one<8, RR_COH>(it, r) : spmv_finish_sell<8, RR_COH>(it, r);
+                if (it.k < it.r1) { bc[it.k] = acc; if (xc) xc[it.k] = 0.0; }
+            }
+        }
     }
 }
 

@@ -237,6 +237,15 @@ class DeviceHierarchy:
         nrm = self._lib.amgb200_level_residual(self.h, l, capi.dptr(xx), capi.dptr(bb), capi.dptr(r))
         return r, nrm
 
+    def resid_restrict(self, l, x, b):
+        """r = b - A_l x, bc = R_l r the way the cycle computes them; returns (r, bc, fused?)"""
+        xx = np.ascontiguousarray(x, np.float64)
+        bb = np.ascontiguousarray(b, np.float64)
+        r = np.zeros(len(bb))
+        bc = np.zeros(self.info(l + 1)["rows"])
+        fused = self._lib.amgb200_level_resid_restrict(self.h, l, capi.dptr(xx), capi.dptr(bb), capi.dptr(r), capi.dptr(bc))
+        return r, bc, bool(fused)
+
     def coarse_solve(self, x0, b, tol):
         x = np.array(x0, np.float64, copy=True)
         bb = np.ascontiguousarray(b, np.float64)

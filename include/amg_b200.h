@@ -170,6 +170,10 @@ void amgb200_level_spmv(amgb200_hier *h, int level, int which, double alpha, con
 void amgb200_level_smooth(amgb200_hier *h, int level, int nsweeps, double *x, const double *b);
 /* r = b - A_l x, returns ||r||_2 */
 double amgb200_level_residual(amgb200_hier *h, int level, const double *x, const double *b, double *r);
+/* what the cycle does between pre-smoothing and the next level (SSS_cycle.cu:916-921, 929): r = b - A_l x, bc = R_l r (and
+ * x_{l+1} = 0) -- ONE launch on levels whose A and R are thread-per-row layouts (resid_restrict_kernel; r is written once and
+ * re-read from L2), else the separate kernels; returns 1 when the fused kernel ran.  r: n_l doubles, bc: n_{l+1} doubles */
+int amgb200_level_resid_restrict(amgb200_hier *h, int level, const double *x, const double *b, double *r, double *bc);
 /* coarsest-level solve on the resident coarsest matrix; returns the Krylov status
  * (iterations, or a negative SSS error code) of the last solver that ran; its[0]=CG its/status,
  * its[1]=GMRES its/status or 0 if not run */
@@ -182,9 +186,10 @@ int amgb200_num_levels(const amgb200_hier *h);
  * info[6]=P nnz info[7]=R nnz */
 void amgb200_level_info(const amgb200_hier *h, int level, long long info[8]);
 /* algorithmic bytes (SURVEY.md section 8d formulas) of: op 0 = one GS sweep, 1 = residual,
- * 2 = restrict, 3 = prolong-add, 4 = y=A x  on that level; op 5 (level ignored) = one V-cycle */
+ * 2 = restrict, 3 = prolong-add, 4 = y=A x  on that level; op 5 (level ignored) = one V-cycle;
+ * op 6 = residual (+) restriction (+ zero-fill of the coarse x) with r not counted (the fused figure of SURVEY.md 8d) */
 double amgb200_algorithmic_bytes(const amgb200_hier *h, int level, int op);
-/* time `reps` back-to-back launches of op (as above, 0..4) on level l with CUDA events on the
+/* time `reps` back-to-back launches of op (as above, 0..4, 6) on level l with CUDA events on the
  * library's stream; returns average milliseconds per launch (ops run on scratch vectors) */
 double amgb200_time_op(amgb200_hier *h, int level, int op, int reps);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */

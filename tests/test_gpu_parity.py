@@ -173,6 +173,37 @@ def test_residual_and_norm(name, oracle):
         assert abs(nrm - np.sqrt(np.sum(want * want))) <= 1e-13 * nrm
 
 
+@pytest.mark.parametrize("name", ["p2d64", "p2d256", "p3d16", "p3d32", "aniso32", "v27_12"])
+@pytest.mark.parametrize("env", [{}, {"AMGB200_RR_ALL": "1"}, {"AMGB200_RR_ALL": "1", "AMGB200_RR_CHUNKS": "7", "AMGB200_RR_LAG": "0"},
+                                 {"AMGB200_RR_CHUNKS": "300", "AMGB200_RR_LAG": "2", "AMGB200_RR_PER_SM": "1"}, {"AMGB200_NO_FUSED": "1"}])
+def test_fused_residual_restriction(name, env, oracle, monkeypatch):
+    """r = b - A x and b_{l+1} = R r (amg/Solve/SSS_cycle.cu:916-921) in ONE launch (resid_restrict_kernel) on every level whose A and
+    R are thread-per-row layouts, the separate kernels elsewhere: both vectors bit-identical to the oracle, repeated launches
+    (the completion counters are never reset) included"""
+    monkeypatch.setenv("AMGB200_RR_MIN_ROWS", "0")                # (by default only levels of >= 262 144 rows take it)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    A, hier, _ = case(name)
+    dev = DeviceHierarchy(hier)
+    fused_levels = 0
+    for l in range(hier.num_levels - 1):
+        c = hier.level(l)
+        n = c.A.num_rows
+        for rep in range(3):
+            x = rng_vec(n, 130 + 7 * l + rep)
+            b = rng_vec(n, 140 + 7 * l + rep)
+            r, bc, fused = dev.resid_restrict(l, x, b)
+            want_r = oracle.amxpy(-1.0, c.A, x, b)
+            check_vec(dev, l, r, want_r, "residual (fused)" if fused else "residual")
+            assert bc.tobytes() == oracle.mxy(c.R, want_r).tobytes(), f"restricted residual, level {l}, fused={fused}"
+        fused_levels += fused
+    if "AMGB200_NO_FUSED" in env:
+        assert fused_levels == 0
+    elif name != "v27_12" or "AMGB200_RR_ALL" in env:             # (27-point rows need the long-row instances: opt-in)
+        assert fused_levels >= 1, "level 0 must take the fused launch"
+    dev.close()
+
+
 @pytest.mark.parametrize("name", ["p2d64", "p3d16", "aniso32", "v27_12"])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_coarse_solve(name, mode, oracle):

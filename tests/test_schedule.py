@@ -103,3 +103,32 @@ def test_layout_spmv_walk(kind, oracle):
             y = np.zeros(m.num_rows)
             L.amgb200_debug_spmv_walk(C.byref(m), kind, capi.dptr(x), capi.dptr(y))
             assert y.tobytes() == oracle.mxy(m, x).tobytes()
+
+
+L.amgb200_debug_fused_walk.restype = C.c_int
+L.amgb200_debug_fused_walk.argtypes = [C.POINTER(capi.Mat), capi.c_int_p, C.POINTER(capi.Mat), capi.c_int_p, C.c_int, C.POINTER(capi.Mat),
+                                       C.c_int, C.c_int, C.c_int, capi.c_double_p, capi.c_double_p, capi.c_double_p, capi.c_double_p]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("nch,lag,tickets", [(1, 0, 32), (5, 1, 32), (16, 0, 3), (64, 1, 32), (64, 3, 8), (200, 1, 1)])
+def test_fused_residual_restriction_ticket_list(case, nch, lag, tickets, oracle):
+    """the ticket list of the fused residual (+) restriction launch (amg/Solve/SSS_cycle.cu:916-921), executed on the CPU through the
+    device layouts: every ticket depends on smaller tickets only, every slice runs once, the declared chunk ranges cover what a
+    slice of R reads, and r / b_{l+1} are the reference's bit for bit"""
+    hier = HostHierarchy(generate(*case), tol=1e-8)
+    for l in range(hier.num_levels - 1):
+        c, cc = hier.level(l), hier.level(l + 1)
+        n, ncoarse = c.A.num_rows, cc.A.num_rows
+        coarsest = l + 1 == hier.num_levels - 1
+        mark = np.ascontiguousarray(hier.cfmark(l))
+        markc = None if coarsest else np.ascontiguousarray(hier.cfmark(l + 1))
+        rng = np.random.default_rng(40 + l)
+        x, b = rng.standard_normal(n), rng.standard_normal(n)
+        r, bc = np.zeros(n), np.zeros(ncoarse)
+        rc = L.amgb200_debug_fused_walk(C.byref(c.A), capi.iptr(mark), C.byref(cc.A), capi.iptr(markc) if markc is not None else None, int(coarsest),
+                                        C.byref(c.R), nch, lag, tickets, capi.dptr(x), capi.dptr(b), capi.dptr(r), capi.dptr(bc))
+        assert rc == 0, f"level {l}: invariant {rc} of the ticket list violated"
+        want_r = oracle.amxpy(-1.0, c.A, x, b)
+        assert r.tobytes() == want_r.tobytes()
+        assert bc.tobytes() == oracle.mxy(c.R, want_r).tobytes()

@@ -1,8 +1,5 @@
-(time python -m pytest tests -m gpu -x -q) > gpurun_out/r2_pytest_gpu_d.log 2>&1; tail -3 gpurun_out/r2_pytest_gpu_d.log
-python tools/quick_time.py p3d 128 2>&1 | grep -E "profiled solve|^solve|phases" | cut -c1-150
-AMGB200_NO_LOWER=1 python tools/quick_time.py p3d 128 2>&1 | grep -E "^solve" | tail -1
-export AMGB200_TIMEOP_SWEEPS=2
-python tools/sweep.py v27 96 0 2>&1 | tail -1; AMGB200_LIB=$PWD/build_tl/libamgb200_minb3.so python tools/sweep.py v27 96 0 2>&1 | tail -1
-python tools/sweep.py p3d 128 1 2>&1 | tail -1; AMGB200_LIB=$PWD/build_tl/libamgb200_minb3.so python tools/sweep.py p3d 128 1 2>&1 | tail -1
-python tools/sweep.py p3d 256 3 "AMGB200_DFW_MIN_WIDTH=80" 2>&1 | tail -2
-python tools/sweep.py v27 192 3 "AMGB200_DFW_MIN_WIDTH=80" 2>&1 | tail -2
+(time python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fused or vcycle or history") > gpurun_out/r2_pytest_fused.log 2>&1; tail -5 gpurun_out/r2_pytest_fused.log
+python tools/fused_probe.py p3d 256 0,1 "AMGB200_NO_FUSED=1" "AMGB200_RR_ALL=1" "AMGB200_RR_CHUNKS=16" "AMGB200_RR_CHUNKS=64" "AMGB200_RR_LAG=3" "AMGB200_RR_LAG=8" 2>&1 | tail -20
+python tools/fused_probe.py p3d 128 0,1 "AMGB200_NO_FUSED=1" "AMGB200_RR_ALL=1" "AMGB200_RR_CHUNKS=16" "AMGB200_RR_LAG=40" 2>&1 | tail -12
+python tools/fused_probe.py aniso3d 128 0 "AMGB200_NO_FUSED=1" 2>&1 | tail -12
+python tools/fused_probe.py p2d 256 0 "AMGB200_NO_FUSED=1" 2>&1 | tail -12
