@@ -78,7 +78,7 @@ EXPORTS = [
     "amgb200_l0_residual", "amgb200_l0_prolong", "amgb200_restrict_from", "amgb200_cycle_from",
     "amgb200_vec_to_schedule", "amgb200_vec_to_natural", "amgb200_sync", "amgb200_setup_ex", "amgb200_interp_device",
     "amgb200_ipc_export", "amgb200_ipc_open", "amgb200_peer_plan", "amgb200_peer_run", "amgb200_read_mtx", "amgb200_level_download",
-    "amgb200_level_resid_restrict",
+    "amgb200_level_resid_restrict", "amgb200_level_fused",
 ]
 
 _lib = None
@@ -144,6 +144,8 @@ def lib():
         L.amgb200_device_bytes.argtypes = [C.c_void_p]
         L.amgb200_level_chain_terms.restype = C.c_longlong
         L.amgb200_level_chain_terms.argtypes = [C.c_void_p, C.c_int]
+        L.amgb200_level_fused.restype = C.c_int
+        L.amgb200_level_fused.argtypes = [C.c_void_p, C.c_int]
         L.amgb200_level_kernel.restype = C.c_char_p
         L.amgb200_level_kernel.argtypes = [C.c_void_p, C.c_int]
         L.amgb200_bench_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

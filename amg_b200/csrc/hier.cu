@@ -1613,6 +1613,10 @@ long long amgb200_level_chain_terms(const amgb200_hier *h, int level) {
     if (lv.lo && sweeps > 0) return (lv.chain_terms * (sweeps - 1) + lv.lo->chain_terms) / sweeps;     // (mean per sweep of a cycle: the first one runs on the lower triangle)
     return lv.chain_terms;
 }
+int amgb200_level_fused(const amgb200_hier *h, int level) {
+    check_level(h, level);
+    return h->L[level].rr.valid ? 1 : 0;
+}
 const char *amgb200_level_kernel(const amgb200_hier *h, int level) {
     check_level(h, level);
     const Level &lv = h->L[level];

@@ -283,6 +283,9 @@ class DeviceHierarchy:
     def chain_terms(self, l):
         return self._lib.amgb200_level_chain_terms(self.h, l)
 
+    def fused(self, l):
+        return bool(self._lib.amgb200_level_fused(self.h, l))
+
     def gs_kernel(self, l):
         return self._lib.amgb200_level_kernel(self.h, l).decode()
 

@@ -244,13 +244,18 @@ def single_gpu_report(dev, hier, workload, n, hbm, hbm_src):
     top = kernels[0]
     ordered = top["kernel"] != "gs_pass_kernel"
     # the HBM-bound kernels of the path (level 0; the north-star's >= 70 % target applies to these)
-    ops = {"gs_sweep": 0, "residual": 1, "restrict": 2, "prolong": 3, "spmv": 4}
+    # (resid_restrict = what the cycle runs between pre-smoothing and the next level -- one fused launch where the level has one --
+    # against the FUSED byte count of SURVEY.md 8d: S(A) + 16 n + S(R) + 8 n_c + 8 n_c, r not counted)
+    ops = {"gs_sweep": 0, "residual": 1, "restrict": 2, "resid_restrict": 6, "prolong": 3, "spmv": 4}
     hbm_kernels = {}
     for name, op in ops.items():
         ms = dev.time_op(0, op, 20)
         if ms > 0:
             gbs = dev.bytes(0, op) / ms / 1e6
-            hbm_kernels[name] = {"kernel": dev.gs_kernel(0) if op == 0 else "spmv_kernel", "gbs": gbs, "frac": gbs / hbm, "ms": ms,
+            kname = dev.gs_kernel(0) if op == 0 else "spmv_kernel"
+            if op == 6:
+                kname = "resid_restrict_kernel" if dev.fused(0) else "spmv_kernel x2 + memset"
+            hbm_kernels[name] = {"kernel": kname, "gbs": gbs, "frac": gbs / hbm, "ms": ms,
                                  "algorithmic_bytes": dev.bytes(0, op),
                                  "traffic": measured_traffic(workload, name, 0)}
     roofline = {"bound": "latency (fp64 dependency chain of the reference's row order)" if ordered else "hbm",

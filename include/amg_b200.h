@@ -206,6 +206,8 @@ void amgb200_upload_seconds(const amgb200_hier *h, double s[2]);
 long long amgb200_device_bytes(const amgb200_hier *h);
 /* name of the Gauss-Seidel kernel chosen for that level */
 const char *amgb200_level_kernel(const amgb200_hier *h, int level);
+/* 1 when the cycle runs residual (+) restriction of this level as one launch (resid_restrict_kernel) */
+int amgb200_level_fused(const amgb200_hier *h, int level);
 /* ordered (row-order Gauss-Seidel) levels: sum over the dependency wavefronts of one sweep of the longest in-order chain that can
  * only start once the previous wavefront is complete, in terms (one dependent fp64 subtraction each): the latency floor of a
  * sweep under the reference's rounding order (Solve/SSS_smooth.c:22-29) is this many terms x the fp64 add latency; 0 for
