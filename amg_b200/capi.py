@@ -78,7 +78,7 @@ EXPORTS = [
     "amgb200_l0_residual", "amgb200_l0_prolong", "amgb200_restrict_from", "amgb200_cycle_from",
     "amgb200_vec_to_schedule", "amgb200_vec_to_natural", "amgb200_sync", "amgb200_setup_ex", "amgb200_interp_device",
     "amgb200_ipc_export", "amgb200_ipc_open", "amgb200_peer_plan", "amgb200_peer_run", "amgb200_read_mtx", "amgb200_level_download",
-    "amgb200_level_resid_restrict", "amgb200_level_fused",
+    "amgb200_level_resid_restrict", "amgb200_level_fused", "amgb200_rap_device",
 ]
 
 _lib = None

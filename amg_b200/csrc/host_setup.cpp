@@ -458,8 +458,8 @@ extern "C" void amgb200_default_pars(amgb200_pars *p) {      // SSS_main.c:25-64
 }
 
 extern "C" void amgb200_setup(amgb200_amg *mg, const amgb200_mat *A, const amgb200_pars *pars, int verbose) {
-    const char *e = getenv("AMGB200_DEVICE_INTERP");
-    amgb200_setup_ex(mg, A, pars, verbose, e && atoi(e) ? AMGB200_SETUP_DEVICE_INTERP : 0);
+    const char *e = getenv("AMGB200_DEVICE_INTERP"), *e2 = getenv("AMGB200_DEVICE_RAP");
+    amgb200_setup_ex(mg, A, pars, verbose, (e && atoi(e) ? AMGB200_SETUP_DEVICE_INTERP : 0) | (e2 && atoi(e2) ? AMGB200_SETUP_DEVICE_RAP : 0));
 }
 
 extern "C" void amgb200_setup_ex(amgb200_amg *mg, const amgb200_mat *A, const amgb200_pars *pars, int verbose, int flags) {
@@ -510,9 +510,13 @@ extern "C" void amgb200_setup_ex(amgb200_amg *mg, const amgb200_mat *A, const am
         if (!((flags & AMGB200_SETUP_DEVICE_INTERP) && amgb200_interp_device(&L.A, mark.data(), &L.P, pars->trunc_threshold) == 0))
             interp_direct(L.A, mark.data(), L.P, *pars);
         const double tt4 = omp_get_wtime();
-        L.R = transpose(L.P);
-        const double tt5 = omp_get_wtime();
-        mg->cg[lvl + 1].A = galerkin(L.R, L.A, L.P);
+        double tt5;
+        if ((flags & AMGB200_SETUP_DEVICE_RAP) && amgb200_rap_device(&L.A, &L.P, &L.R, &mg->cg[lvl + 1].A) == 0) tt5 = omp_get_wtime();
+        else {
+            L.R = transpose(L.P);
+            tt5 = omp_get_wtime();
+            mg->cg[lvl + 1].A = galerkin(L.R, L.A, L.P);
+        }
         if (verbose >= 2) printf("[setup] level %d: strength %.3f split %.3f clean+pattern %.3f interp %.3f transpose %.3f galerkin %.3f s\n", lvl, tt1 - tt0, tt2 - tt1, tt3 - tt2, tt4 - tt3, tt5 - tt4, omp_get_wtime() - tt5);
         if (L.A.num_nnzs / L.A.num_rows > L.A.num_cols * 0.2) {       // (sic) tests the *fine* level, integer division
             if (verbose) { printf("### WARNING: Coarse matrix is too dense!\n"); printf("### WARNING: m = n = %d, nnz = %d!\n", L.A.num_cols, L.A.num_nnzs); }

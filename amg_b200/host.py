@@ -102,16 +102,17 @@ def read_mtx(path):
 class HostHierarchy:
     """Host AMG hierarchy (an SSS_AMG) built by amgb200_setup."""
 
-    def __init__(self, A, tol=1e-8, verbose=0, device_interp=False, **par_overrides):
-        """device_interp: interpolation weights + truncation on the GPU (amgb200_interp_device; same hierarchy bit for bit)"""
+    def __init__(self, A, tol=1e-8, verbose=0, device_interp=False, device_rap=False, **par_overrides):
+        """device_interp: interpolation weights + truncation on the GPU (amgb200_interp_device; same hierarchy bit for bit)
+        device_rap: R = P^T and the Galerkin product on the GPU (amgb200_rap_device; same arrays entry for entry)"""
         self.A = A
         self.pars = capi.default_pars(tol)
         for k, v in par_overrides.items():
             setattr(self.pars, k, v)
         self.mg = capi.Amg()
         self._lib = capi.lib()
-        if device_interp:
-            self._lib.amgb200_setup_ex(C.byref(self.mg), C.byref(A.c), C.byref(self.pars), int(verbose), 1)
+        if device_interp or device_rap:
+            self._lib.amgb200_setup_ex(C.byref(self.mg), C.byref(A.c), C.byref(self.pars), int(verbose), (1 if device_interp else 0) | (2 if device_rap else 0))
         else:
             self._lib.amgb200_setup(C.byref(self.mg), C.byref(A.c), C.byref(self.pars), int(verbose))
         self._alive = True

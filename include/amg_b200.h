@@ -270,6 +270,9 @@ void amgb200_setup(amgb200_amg *mg, const amgb200_mat *A, const amgb200_pars *pa
 /* flags & AMGB200_SETUP_DEVICE_INTERP: the interpolation weights, the coarse renumbering and the truncation of P are computed on
  * the device (amgb200_interp_device) instead of the host loop -- the same hierarchy, bit for bit. */
 #define AMGB200_SETUP_DEVICE_INTERP 1
+/* flags & AMGB200_SETUP_DEVICE_RAP: R = P^T and the Galerkin product R A P are computed on the device (amgb200_rap_device) -- the same
+ * arrays, entry for entry. */
+#define AMGB200_SETUP_DEVICE_RAP 2
 void amgb200_setup_ex(amgb200_amg *mg, const amgb200_mat *A, const amgb200_pars *pars, int verbose, int flags);
 /* ---- 3b. setup step next to the hot path, on the device ---------
  * Direct-interpolation weights + coarse numbering + truncation: replaces interp_DIR / interp_DIR_cuda + SSS_amg_interp_trunc
@@ -277,6 +280,13 @@ void amgb200_setup_ex(amgb200_amg *mg, const amgb200_mat *A, const amgb200_pars 
  * P enters with the pattern the coarsening produced (col_idx = FINE indices of the interpolatory C points, val allocated) and
  * leaves exactly as interp_DIR leaves it.  mark: 0 F, 1 C, 2 isolated.  Returns 0; 1 = a row has no stored diagonal, nothing done. */
 int amgb200_interp_device(const amgb200_mat *A, const int *mark, amgb200_mat *P, double trunc_threshold);
+/* ---- 3c. the operators of the next level, on the device ---------
+ * R = P^T (replaces SSS_mat_trans, amg/SSS_matvec.c:330-387) and Ac = R A P (replaces SSS_blas_mat_rap, amg/SSS_matvec.c:398-534) with the
+ * reference's output ORDER -- rows of R by ascending fine row; rows of Ac: diagonal slot first, then the columns in discovery order of
+ * the triple loop, values accumulated in traversal order as (r*a)*p without FMA -- because that order is the summation order of the
+ * solve phase.  R_out / Ac_out receive calloc'ed host CSR arrays owned by the caller (freed by SSS_amg_data_destroy like the
+ * reference's).  Returns 0; 1 = a product row exceeds 8192 columns or the product 2^31 entries: nothing returned, use the host loops. */
+int amgb200_rap_device(const amgb200_mat *A, const amgb200_mat *P, amgb200_mat *R_out, amgb200_mat *Ac_out);
 void amgb200_amg_destroy(amgb200_amg *mg);
 void amgb200_default_pars(amgb200_pars *p);   /* SSS_main.c:25-64 */
 

@@ -443,6 +443,43 @@ def test_device_interpolation_builds_the_same_hierarchy(case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", [("p2d", 96, 0.0), ("p2d", 256, 0.0), ("p3d", 40, 0.0), ("aniso3d", 32, 1e-3), ("v27", 20, 0.0), ("p3d", 128, 0.0)])
+def test_device_transpose_and_galerkin_build_the_same_hierarchy(case):
+    """R = P^T and A_{l+1} = R A P on the device (amgb200_rap_device, setup_rap.cu) against the host loops that are byte-pinned to the
+    reference's SSS_mat_trans / SSS_blas_mat_rap (SSS_matvec.c:330-387, :398-534; tests/test_setup_parity.py): every array of every level
+    is byte-identical -- row order of R, diagonal-first discovery order and accumulation order of the product included, since they are
+    the summation order of the solve phase.  For the sizes with a fixture the sha256 of every A and R array is also compared with the
+    one of the reference's own setup (tests/golden/golden.json)."""
+    import hashlib
+    import json
+    import os
+    kind, N, eps = case
+    A = generate(kind, N, eps)
+    host = HostHierarchy(A, tol=1e-8)
+    devh = HostHierarchy(A, tol=1e-8, device_rap=True, device_interp=True)
+    assert host.table() == devh.table()
+    for l in range(host.num_levels):
+        for which in ("A", "P", "R"):
+            if which != "A" and l == host.num_levels - 1:
+                continue
+            a, b = host.level_matrix(l, which), devh.level_matrix(l, which)
+            assert a.row_ptr.tobytes() == b.row_ptr.tobytes(), (l, which, "row_ptr")
+            assert a.col_idx.tobytes() == b.col_idx.tobytes(), (l, which, "col_idx")
+            assert a.val.tobytes() == b.val.tobytes(), (l, which, "val")
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json")))
+    name = f"{kind}{N}"
+    if name in gold:
+        for l in range(devh.num_levels):
+            for which in ("A", "R"):
+                if which not in gold[name]["levels"][l]:
+                    continue
+                M = devh.level_matrix(l, which)
+                for arr in ("row_ptr", "col_idx", "val"):
+                    assert hashlib.sha256(getattr(M, arr).tobytes()).hexdigest() == gold[name]["levels"][l][which][arr], (l, which, arr)
+    host.close(); devh.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["p3d16", "v27_12"])
 def test_host_and_device_sell_fill_agree(name, oracle, monkeypatch):
     """SELL-32 layouts permuted/padded on the device (sell_fill_kernel, the default) and on the host
