@@ -327,6 +327,7 @@ struct amgb200_hier {
     int max_dyn_smem = 0;
     int cluster_block = 256;
     int df_ahead = 2;                  // data-flow smoother: wavefronts ahead of the completed frontier that poll their records
+    int pcg_ctas = 0;                  // coarsest-level CG in one cooperative launch: CTAs at most (0 = host-driven loop)
     double *d_partial = nullptr;       // 4 x partial_stride block partials
     int partial_stride = 0;
     double *d_scal = nullptr;          // 8 reduced scalars
@@ -738,9 +739,32 @@ int coarse_cg(amgb200_hier *h, const DMat &A, const double *b, double *u, double
     int iter = 0, stag = 1, more_step = 1, iter_best = 0;
     double absres0, absres = BIGF, relres, normu, normr0, absres_best = BIGF;
     double alpha, beta, temp1, temp2, reldiff, infnormu;
-    ensure_krylov(h, (size_t)5 * m);
+    ensure_krylov(h, (size_t)6 * m);
     double *p = h->kry, *r = p + m, *t = r + m, *u_best = t + m;   // z == r (no preconditioner): not materialised
     const int ug = red_grid(h, m);
+
+    // the whole iteration in one cooperative launch (coarse_cg_kernel); the rarely taken safeguard branches make it stop with
+    // CG_FALLBACK, and the host-driven loop below redoes the solve from the saved initial guess
+    if (h->exact && h->opt.coarse_mode == AMGB200_BETA_FIX && h->pcg_ctas > 0) {
+        double *u0 = h->kry + (size_t)5 * m;
+        dev_copy(h, m, u, u0);
+        CgArgs a;
+        a.A = A; a.b = b; a.u = u; a.p = p; a.r = r; a.t = t; a.u_best = u_best; a.tol = tol; a.maxit = maxit; a.beta_fix = 1;
+        a.scal = h->d_scal; a.partial = h->d_partial; a.status = reinterpret_cast<int *>(h->d_scal + 7);
+        a.barrier = reinterpret_cast<unsigned *>(h->d_scal + 6); a.barrier_gen = 0;
+        CUDA_CHECK(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned), h->stream));
+        const void *kern = A.kind == KIND_SELL ? (const void *)coarse_cg_kernel<0> : (const void *)coarse_cg_kernel<1>;
+        // (a few dozen rows -- the coarsest matrices of the 2D and the anisotropic problems: ONE CTA, whose barrier is __syncthreads)
+        const int grid = A.nitems <= 128 ? 1 : std::max(1, std::min(h->pcg_ctas, (A.nitems + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
+        void *args[] = {&a};
+        CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(BLOCK), args, 0, h->stream));
+        ++g_launches;
+        fetch_scalars(h, 8);
+        int status;
+        memcpy(&status, h->h_scal + 7, sizeof(int));
+        if (status != CG_FALLBACK) return status;
+        dev_copy(h, m, u0, u);
+    }
 
     absres0 = krylov_residual(h, A, u, b, r);
     normr0 = std::max(SMALLF, absres0);
@@ -1045,6 +1069,12 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         if (!coop) { fprintf(stderr, "libamgb200: device lacks cooperative launch\n"); exit(70); }
     }
     h->exact = !opt.fast;
+    {
+        int per_sm = 0;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_cg_kernel<1>, BLOCK, 0));
+        h->pcg_ctas = std::min(per_sm, 2) * h->num_sms;
+        if (getenv("AMGB200_PCG_CTAS")) h->pcg_ctas = std::max(0, std::min(per_sm * h->num_sms, atoi(getenv("AMGB200_PCG_CTAS"))));
+    }
     const double sell_max_mean = getenv("AMGB200_SELL_MAX_MEAN") ? atof(getenv("AMGB200_SELL_MAX_MEAN")) : (h->exact ? 48.0 : 24.0);
     const double cta_max_avg = getenv("AMGB200_CTA_MAX_AVG") ? atof(getenv("AMGB200_CTA_MAX_AVG")) : 6.0;
     const double stream_max_avg = getenv("AMGB200_STREAM_MAX_AVG") ? atof(getenv("AMGB200_STREAM_MAX_AVG")) : 12.0;

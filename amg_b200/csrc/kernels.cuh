@@ -2117,6 +2117,195 @@ __global__ void __launch_bounds__(BLOCK) cg_update_kernel(int n, double temp1, c
     um = block_max(um, red); if (threadIdx.x == 0) partial[2 * stride + blockIdx.x] = um;
 }
 
+// ------------------------------------------------------------------------------------------
+// The whole coarsest-level CG in ONE cooperative launch (amg/Solve/SSS_cycle.cu:15-437, stop_type = STOP_REL_RES, no preconditioner):
+// the host-driven version above costs 6 launches and a read-back per iteration (~70 us on a 2 120-row matrix, 230 iterations per
+// 128^3 solve; on the 39-row coarsest matrix of the 2D problem the launches ARE the solve).  Here the grid keeps the vectors in L2,
+// grid-wide barriers separate the phases, and the scalar recurrences are recomputed redundantly by every thread from four numbers in
+// global memory, so the control flow stays uniform without a host.  The arithmetic is the host-driven path's, operation for
+// operation: rows of A p summed in storage order (warp per row / thread per row), (t, p) and (r, r) folded left to right by one
+// thread, alpha = (z, r) / (t, p) and beta by IEEE division, u += alpha p, r += (-alpha) t, p = 1.0 r + beta p without FMA.
+// The safeguard branches that are (almost) never taken -- stagnation restarts, the second chance after a false convergence,
+// a vanishing iterate -- are NOT in the kernel: it stops with status CG_FALLBACK and the host redoes the solve from the saved
+// initial guess with the host-driven code, which is bit-identical by construction.
+// ------------------------------------------------------------------------------------------
+constexpr int CG_FALLBACK = -1000;
+struct CgArgs {
+    DMat A;
+    const double *b;
+    double *u, *p, *r, *t, *u_best;
+    double tol;
+    int maxit, beta_fix;
+    double *scal;          // [0] (t, p) | (r, r)  [1] u.u  [2] p.p  [3] max|u|   (written by block 0 between two grid barriers)
+    double *partial;       // 3 x gridDim.x block partials
+    int *status;           // [0] iterations or a negative SSS error code or CG_FALLBACK
+    unsigned *barrier;     // arrival counter of the grid barrier (never reset) and the number of barriers earlier launches went through
+    unsigned barrier_gen;
+};
+// out = sum_i x_i y_i from 0.0, left to right (SSS_blas_array_dot): block-wide staging of the separately rounded products, one thread
+// folds.  Called by ONE block; result valid in thread 0.
+__device__ __forceinline__ double cg_dot_seq(int n, const double *x, const double *y, double *prod) {
+    double acc = 0.0;
+    for (int base = 0; base < n; base += DOT_TILE) {
+        const int m = min(DOT_TILE, n - base), m8 = (m + 7) & ~7;
+        for (int i = threadIdx.x; i < m8 + 16; i += blockDim.x) prod[i] = i < m ? __dmul_rn(__ldcg(x + base + i), __ldcg(y + base + i)) : 0.0;   // (+0.0: exact no-ops)
+        __syncthreads();
+        if (threadIdx.x < 32) acc = chain_fold<false>(acc, reinterpret_cast<const double2 *>(prod), m8);   // (all lanes of warp 0: broadcast loads, 8.4 cycles per term)
+        __syncthreads();
+    }
+    return acc;
+}
+// grid-wide barrier of the cooperative launch: one arrival counter that only grows (target = generation x CTAs), ~1 us against the
+// 4-5 us measured for cooperative_groups' grid.sync(); a single-CTA launch (coarsest matrices of a few dozen rows) needs no more than
+// __syncthreads().  Vectors are read and written at L2 (__ldcg / __stcg), so the fence + acquire pair orders them.
+struct GridBarrier {
+    unsigned *counter;
+    unsigned gen;
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        if (gridDim.x > 1) {
+            if (threadIdx.x == 0) {
+                ++gen;
+                __threadfence();
+                atomicAdd(counter, 1u);
+                const unsigned target = gen * gridDim.x;
+                while ((int)(ld_acquire_u32(counter) - target) < 0) { }
+                __threadfence();
+            }
+            __syncthreads();
+        }
+    }
+};
+// y = A x (RESID = false) or y = b - A x, every row exactly like spmv_kernel; x and y live in L2 (other SMs wrote x in this launch)
+template <int KIND, bool RESID>
+__device__ __forceinline__ void cg_spmv(const DMat &A, const double *x, const double *b, double *y, double *sprod) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * WARPS_PER_BLOCK + warp, nw = gridDim.x * WARPS_PER_BLOCK;
+    for (int it = gw; it < A.nitems; it += nw) {
+        if constexpr (KIND == 0) {
+            SellItem<8> w;
+            w.prologue(A, it, lane);
+            const double t = spmv_finish_sell<8, true>(w, x);
+            if (w.k < w.r1) __stcg(y + w.k, RESID ? __dadd_rn(__ldcg(b + w.k), __dmul_rn(t, -1.0)) : t);
+        } else {
+            CsrItem w;
+            w.prologue(A, it, lane, nullptr);
+            double d;
+            const double t = csr_row_exact<true, false>(A, w, x, 0.0, d, lane, sprod + warp * STAGE);
+            if (lane == 0) __stcg(y + it, RESID ? __dadd_rn(__ldcg(b + it), __dmul_rn(t, -1.0)) : t);
+        }
+    }
+}
+template <int KIND>
+__global__ void __launch_bounds__(BLOCK) coarse_cg_kernel(CgArgs a) {
+    GridBarrier grid{a.barrier, a.barrier_gen};
+    __shared__ __align__(16) double prod[DOT_TILE + 16];
+    __shared__ double sprod[KIND == 1 ? WARPS_PER_BLOCK * STAGE : 1];
+    __shared__ double red[32];
+    const int m = a.A.nrows;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const double maxdiff = a.tol * 1e-4;
+    int iter = 0, iter_best = 0;
+    double absres = 1e+20, absres_best = 1e+20, relres, normr0, temp1, temp2, alpha, beta;
+
+    // r = b - A u ; (r, r)
+    cg_spmv<KIND, true>(a.A, a.u, a.b, a.r, sprod);
+    grid.sync();
+    if (blockIdx.x == 0) { const double rr = cg_dot_seq(m, a.r, a.r, prod); if (threadIdx.x == 0) __stcg(a.scal, rr); }
+    grid.sync();
+    {
+        const double rr = __ldcg(a.scal);
+        const double absres0 = sqrt(rr);
+        normr0 = fmax(1e-20, absres0);
+        relres = absres0 / normr0;
+        temp1 = rr;
+    }
+    if (relres < a.tol) { if (tid == 0) a.status[0] = 0; return; }
+    for (int i = tid; i < m; i += nthr) __stcg(a.p + i, __ldcg(a.r + i));
+    grid.sync();
+
+    bool stopped = false;                                    // left the loop through a break (no restore needed when iter == iter_best)
+    while (iter++ < a.maxit) {
+        cg_spmv<KIND, false>(a.A, a.p, nullptr, a.t, sprod);  // t = A p
+        grid.sync();
+        if (blockIdx.x == 0) { const double tp = cg_dot_seq(m, a.t, a.p, prod); if (threadIdx.x == 0) __stcg(a.scal, tp); }
+        grid.sync();
+        temp2 = __ldcg(a.scal);
+        if (!(fabs(temp2) > 1e-40)) break;                    // SSS_cycle.cu:190 -> restore
+        alpha = __ddiv_rn(temp1, temp2);
+        {
+            const double nalpha = -alpha;
+            double uu = 0.0, pp = 0.0, um = 0.0;
+            for (int i = tid; i < m; i += nthr) {
+                const double pi = __ldcg(a.p + i);
+                const double ui = __dadd_rn(__ldcg(a.u + i), __dmul_rn(alpha, pi));
+                __stcg(a.r + i, __dadd_rn(__ldcg(a.r + i), __dmul_rn(nalpha, __ldcg(a.t + i))));
+                __stcg(a.u + i, ui);
+                uu = __dadd_rn(uu, __dmul_rn(ui, ui));
+                pp = __dadd_rn(pp, __dmul_rn(pi, pi));
+                um = fmax(um, fabs(ui));
+            }
+            uu = block_sum(uu, red); if (threadIdx.x == 0) __stcg(a.partial + 0 * gridDim.x + blockIdx.x, uu);
+            pp = block_sum(pp, red); if (threadIdx.x == 0) __stcg(a.partial + 1 * gridDim.x + blockIdx.x, pp);
+            um = block_max(um, red); if (threadIdx.x == 0) __stcg(a.partial + 2 * gridDim.x + blockIdx.x, um);
+        }
+        grid.sync();
+        if (blockIdx.x == 0) {
+            const double rr = cg_dot_seq(m, a.r, a.r, prod);
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+                v0 = __dadd_rn(v0, __ldcg(a.partial + i));
+                v1 = __dadd_rn(v1, __ldcg(a.partial + gridDim.x + i));
+                v2 = fmax(v2, __ldcg(a.partial + 2 * gridDim.x + i));
+            }
+            v0 = block_sum(v0, red); v1 = block_sum(v1, red); v2 = block_max(v2, red);
+            if (threadIdx.x == 0) { __stcg(a.scal, rr); __stcg(a.scal + 1, v0); __stcg(a.scal + 2, v1); __stcg(a.scal + 3, v2); }
+        }
+        grid.sync();
+        const double rr = __ldcg(a.scal), uu = __ldcg(a.scal + 1), pp = __ldcg(a.scal + 2), infnormu = __ldcg(a.scal + 3);
+        absres = sqrt(rr);
+        relres = absres / normr0;
+        if (absres < absres_best - maxdiff) {
+            absres_best = absres;
+            iter_best = iter;
+            for (int i = tid; i < m; i += nthr) __stcg(a.u_best + i, __ldcg(a.u + i));      // (the thread that wrote u_i copies it)
+        }
+        if (infnormu <= 1e-20) { if (tid == 0) a.status[0] = CG_FALLBACK; return; }
+        const double reldiff = fabs(alpha) * sqrt(pp) / sqrt(uu);
+        if (reldiff < maxdiff) { if (tid == 0) a.status[0] = CG_FALLBACK; return; }         // stagnation handling: host
+        if (relres < a.tol) {
+            grid.sync();                                                                      // u complete everywhere
+            cg_spmv<KIND, true>(a.A, a.u, a.b, a.r, sprod);
+            grid.sync();
+            if (blockIdx.x == 0) { const double r2 = cg_dot_seq(m, a.r, a.r, prod); if (threadIdx.x == 0) __stcg(a.scal, r2); }
+            grid.sync();
+            absres = sqrt(__ldcg(a.scal));
+            relres = absres / normr0;
+            if (relres < a.tol) { stopped = true; break; }
+            if (tid == 0) a.status[0] = CG_FALLBACK;                                         // false convergence: host
+            return;
+        }
+        temp2 = rr;
+        if (a.beta_fix) { beta = __ddiv_rn(temp2, temp1); temp1 = temp2; }
+        else beta = __ddiv_rn(temp1, temp1);
+        for (int i = tid; i < m; i += nthr) __stcg(a.p + i, __dadd_rn(__dmul_rn(1.0, __ldcg(a.r + i)), __dmul_rn(beta, __ldcg(a.p + i))));
+        grid.sync();
+    }
+    (void)stopped;
+    // restore the best iterate seen if the last one is worse (SSS_cycle.cu:400-420)
+    if (iter != iter_best) {
+        grid.sync();
+        cg_spmv<KIND, true>(a.A, a.u_best, a.b, a.r, sprod);
+        grid.sync();
+        if (blockIdx.x == 0) { const double r2 = cg_dot_seq(m, a.r, a.r, prod); if (threadIdx.x == 0) __stcg(a.scal, r2); }
+        grid.sync();
+        absres_best = sqrt(__ldcg(a.scal));
+        if (absres > absres_best + maxdiff)
+            for (int i = tid; i < m; i += nthr) __stcg(a.u + i, __ldcg(a.u_best + i));
+    }
+    if (tid == 0) a.status[0] = iter > a.maxit ? -48 : iter;
+}
+
 // y = a*x + b*y   (SSS_blas_array_axpby, SSS_utils.c:248-253)
 __global__ void __launch_bounds__(BLOCK) axpby_kernel(int n, double a, const double *__restrict__ x, double b, double *y) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
