@@ -126,7 +126,9 @@ struct Stager {
         for (int i = 0; i < NBUF; ++i) { CUDA_CHECK(cudaMallocHost((void **)&buf[i], CHUNK)); CUDA_CHECK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)); }
         ok = true;
     }
+    std::mutex mu;                                       // (uploads from helper threads share the ring)
     void copy(void *dst, const void *src, size_t bytes) {
+        std::lock_guard<std::mutex> lk(mu);
         init();
         size_t off = 0;
         int slot = 0;
@@ -215,10 +217,11 @@ struct DevMatOwner {
     int max_row = 0;
     bool valid = false;
     static double &t_upload() { static double t = 0; return t; }
+    static void add_upload_time(double dt) { static std::mutex *m = new std::mutex(); std::lock_guard<std::mutex> lk(*m); t_upload() += dt; }
     void upload(const DevLayout &L) {
         const double t0 = now_s();
         upload_impl(L);
-        t_upload() += now_s() - t0;
+        add_upload_time(now_s() - t0);
     }
     void upload_impl(const DevLayout &L) {
         v.kind = L.kind; v.nrows = L.nrows; v.ncols = L.ncols; v.nitems = L.nitems(); v.max_row = L.max_row; v.recip = 0;
@@ -257,7 +260,7 @@ struct DevMatOwner {
                    ns, v.slice_row, v.slice_ptr, d_order, d_colpos, (const int *)d_rp, (const int *)d_ci, (const double *)d_va, d_col, d_val);
         }
         nnz = L.nnz; padded = (long long)total; max_row = L.max_row; valid = true;
-        t_upload() += now_s() - t0;
+        add_upload_time(now_s() - t0);
     }
     void release() {
         if (!valid) return;
@@ -1146,7 +1149,12 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     h->analysis_s = now_s() - t0;
     DevMatOwner::t_upload() = 0;
     double t_layout = 0;
-    auto tl_note = [&](const char *what, int l, double dt) { t_layout += dt; if (opt.verbose >= 3) printf("      [layout] level %d %-8s %.1f ms\n", l, what, 1e3 * dt); };
+    std::mutex tl_mutex;
+    auto tl_note = [&](const char *what, int l, double dt) {
+        std::lock_guard<std::mutex> lk(tl_mutex);
+        t_layout += dt;
+        if (opt.verbose >= 3) printf("      [layout] level %d %-8s %.1f ms\n", l, what, 1e3 * dt);
+    };
 
     int max_items = 1;
     // wavefront tables and launch strategy of one level's smoother (used for the level itself and, in natural
@@ -1393,6 +1401,8 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         }
     };
 
+    std::vector<std::thread> lower_threads;
+    const bool lower_async = !(getenv("AMGB200_LOWER_SYNC") && atoi(getenv("AMGB200_LOWER_SYNC")));
     for (int l = 0; l < nl; ++l) {
         const amgb200_comp &c = mg->cg[l];
         Level &lv = h->L[l];
@@ -1437,6 +1447,12 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             // difference that cancels is +0), so those entries can leave the in-order chain: the first sweep is a forward substitution
             // with the lower triangle of the schedule numbering.  Built for the chain-bound levels (streaming kernels) only.
             if (l >= 1 && !natural[l] && use_lower && (lv.strategy == 4 || lv.strategy == 5)) {
+              // (on a helper thread per level, next to the layouts of the following levels: host packing + its own uploads)
+              auto build_lower = [&, l]() {
+                CUDA_CHECK(cudaSetDevice(dev));
+                const amgb200_comp &c = mg->cg[l];
+                Level &lv = h->L[l];
+                const Schedule &S = sched[l];
                 const double tl = now_s();
                 const int n = c.A.num_rows;
                 std::vector<int> rp((size_t)n + 1, 0);
@@ -1472,6 +1488,8 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                     delete lo;
                 }
                 tl_note("lower", l, now_s() - tl);
+              };
+              if (lower_async) lower_threads.emplace_back(build_lower); else build_lower();
             }
             if (natural[l]) {
                 // backward sweeps: own schedule, layout and vectors; d_fb maps its numbering into this level's
@@ -1517,6 +1535,7 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             }
         }
     }
+    for (std::thread &t : lower_threads) t.join();
     h->partial_stride = std::max(1184, (max_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     h->d_partial = dev_alloc<double>((size_t)4 * h->partial_stride);
     h->d_scal = dev_alloc<double>(8);

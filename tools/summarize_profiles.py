@@ -56,22 +56,27 @@ def main():
     recs = raw("r2_l0_256.ncu-rep")
     n, z, nc, zr = 16777216, 117047296, 8388608, 58523648
     S = lambda zz, nn: 12 * zz + 4 * (nn + 1)
-    algo = {"gs_sweep": S(z, n) + 28 * n, "residual": S(z, n) + 24 * n, "restrict": S(zr, nc) + 8 * n + 8 * nc, "prolong": S(zr, n) + 8 * nc + 16 * n, "spmv": S(z, n) + 16 * n}
+    algo = {"gs_sweep": S(z, n) + 28 * n, "residual": S(z, n) + 24 * n, "restrict": S(zr, nc) + 8 * n + 8 * nc, "prolong": S(zr, n) + 8 * nc + 16 * n, "spmv": S(z, n) + 16 * n,
+            "resid_restrict": S(z, n) + 16 * n + S(zr, nc) + 8 * nc + 8 * nc}
     md += ["## Level 0 of 3D 7-point Poisson 256^3 (BASELINE configs[2]): the HBM-bound kernels of the path", "",
            "| op | kernel | launches | time per launch (us) | DRAM read + write per launch (MB) | algorithmic (MB) | traffic/algo | frac of HBM (algorithmic) | L1/TEX % | L2 % | warps active % | long-scoreboard stall | lg-throttle |", "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     groups = [("gs_sweep", recs[4:6], 2), ("residual", recs[8:9], 1), ("restrict", recs[11:12], 1), ("prolong", recs[14:15], 1), ("spmv", recs[17:18], 1)]
+    if len(recs) >= 21:
+        groups.append(("resid_restrict", recs[20:21], 1))
     for name, rs, per in groups:
         t = sum(num(r, "gpu__time_duration.sum") for r in rs)
         dr = sum(num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum") for r in rs)
         s = line(rs[-1])
         traffic[f"p3d256/{name}/0"] = dr
         md.append(f"| {name} | `{s['kernel']}` | {per} | {t*1e6/per:.1f} | {dr/1e6/per:.1f} | {algo[name]/1e6/per:.1f} | {dr/algo[name]:.2f} | **{algo[name]/t/1e9/HBM:.2f}** ({algo[name]/t/1e9:.0f} GB/s) | {s['l1tex_pct']:.0f} | {s['lts_pct']:.0f} | {s['warps_active_pct']:.0f} | {s.get('stall_long_scoreboard', 0):.1f} | {s.get('stall_lg_throttle', 0):.1f} |")
-    md += ["", "(every launch of the capture gives the same numbers to 1 %: 6 `gs_pass_kernel` launches 169.9-171.4 us, 3 x each `spmv_kernel` mode.)", ""]
+    md += ["", "(every launch of the capture gives the same numbers to 1 %: 6 `gs_pass_kernel` launches, 3 x each `spmv_kernel` mode, 3 x `resid_restrict_kernel`.  `resid_restrict` = residual + restriction + zero-fill of the coarse x in ONE launch; its algorithmic bytes are the fused figure of SURVEY.md 8d, which does not count r -- the kernel writes r once (134 MB) and re-reads it from L2, so traffic/algo > 1 by that write.)", ""]
     # ---- ordered smoothers of 128^3
     md += ["## Ordered Gauss-Seidel kernels of 3D 7-point Poisson 128^3 (BASELINE configs[1]): one 1-sweep launch each", "",
            "| level | kernel | time (ms) | DRAM read + write (MB) | algorithmic (MB) | traffic/algo | DRAM GB/s | regs | grid | warps active % | stalls per issue: long-scoreboard / barrier / membar / wait |", "|---|---|---|---|---|---|---|---|---|---|---|"]
-    lv = {6: (3886, 2051444), 1: (1048576, 19628800), 2: (182755, 6302457)}
-    for rep, level in (("r2_stream_cta_l6.ncu-rep", 6), ("r2_dataflow_l1.ncu-rep", 1), ("r2_stream_cluster_l2.ncu-rep", 2)):
+    lv = {6: (3886, 2051444), 1: (1048576, 19628800), 2: (182755, 6302457), 3: (34885, 2290653)}
+    for rep, level in (("r2_stream_cta_l6.ncu-rep", 6), ("r2_dataflow_l1.ncu-rep", 1), ("r2_dataflow_csr_l2.ncu-rep", 2), ("r2_stream_cluster_l3.ncu-rep", 3)):
+        if not os.path.exists(os.path.join(GO, rep)):
+            continue
         r = raw(rep)[0]
         nn, zz = lv[level]
         ab = S(zz, nn) + 28 * nn
@@ -79,6 +84,14 @@ def main():
         traffic[f"p3d128/{s['kernel'].split('<')[0]}/{level}"] = (s["dram_read_MB"] + s["dram_write_MB"]) * 1e6
         md.append(f"| {level} | `{s['kernel']}` | {s['time_us']/1e3:.3f} | {s['dram_read_MB'] + s['dram_write_MB']:.1f} | {ab/1e6:.1f} | {s['traffic_over_algorithmic']:.2f} | {s['dram_GBs']:.1f} | {s['regs']} | {s['grid']} | {s['warps_active_pct']:.0f} | {s.get('stall_long_scoreboard', 0):.1f} / {s.get('stall_barrier', 0):.1f} / {s.get('stall_membar', 0):.1f} / {s.get('stall_wait', 0):.1f} |")
     md += ["", "These sweeps are bound by the dependency chain of the reference's row order (DESIGN.md section 2), not by DRAM: their DRAM throughput is 1-3 % of the peak while the traffic stays at the algorithmic bytes (no wasted re-reads).", ""]
+    # ---- coarsest-level CG in one launch
+    if os.path.exists(os.path.join(GO, "r2_coarse_cg.ncu-rep")):
+        r = raw("r2_coarse_cg.ncu-rep")[0]
+        s = line(r)
+        md += ["## Coarsest-level CG of 128^3 in one cooperative launch (`coarse_cg_kernel`, 2 120 rows, 1 414 166 entries; `tools/prof_coarse.py`)", "",
+               "| kernel | time (ms) | DRAM read + write (MB) | regs | grid | warps active % | stalls per issue: long-scoreboard / barrier / membar / wait |", "|---|---|---|---|---|---|---|",
+               f"| `{s['kernel']}` | {s['time_us']/1e3:.3f} | {s['dram_read_MB'] + s['dram_write_MB']:.1f} | {s['regs']} | {s['grid']} | {s['warps_active_pct']:.0f} | {s.get('stall_long_scoreboard', 0):.1f} / {s.get('stall_barrier', 0):.1f} / {s.get('stall_membar', 0):.1f} / {s.get('stall_wait', 0):.1f} |",
+               "", "The matrix (17 MB) and the vectors stay in L2: DRAM traffic is the first touch only.  The kernel is bound by the two in-order dot products and the grid barriers of every iteration (DESIGN.md section 5).", ""]
     open(os.path.join(ROOT, "profiles", "r2_ncu_summary.md"), "w").write("\n".join(md) + "\n")
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "r2_traffic.json"), "w"), indent=1)
     # ---- launch list of the bench command
