@@ -1227,7 +1227,11 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             const double tl = now_s();
             build_stream(lay, SL);
             tl_note("stream", lv.n, now_s() - tl);
-            if ((long long)SL.max_block * 2 <= ring) {
+            // (a block larger than half the ring is loaded alone -- the loader drains the ring first -- so its wavefront runs without
+            // overlap; accepted as long as the MEAN block fits three times: 256^3 level 8, 9 585 rows, 30.7 -> 27.9 ms per sweep against
+            // the cluster kernel; AMGB200_STREAM_RELAX=0 restores the strict rule)
+            const bool relax = !(getenv("AMGB200_STREAM_RELAX") && !atoi(getenv("AMGB200_STREAM_RELAX")));
+            if ((long long)SL.max_block * 2 <= ring || (relax && (long long)SL.max_block <= ring && SL.mean_block * 3 <= ring)) {
                 lv.strategy = 4;
                 lv.stream_ring = (int)(ring & ~127LL);
                 // product warps per group (1, 2 or 4) and row slots of the folding warp (the widest wavefront in one

@@ -298,6 +298,22 @@ class ShardedSolver:
         self.collect_solution()
         return len(hist), np.array(hist), (self.be.get_solution() if self.rank == 0 else None)
 
+    def solve_resident(self, d_x0, d_b, sumb, tol, d_out, max_it=100):
+        """the same outer iteration on vectors that already live on every rank's GPU (torch tensors, natural numbering); the solution
+        stays on the device (rank 0: d_out).  Nothing crosses PCIe except the 8-byte norm of every V-cycle."""
+        self.be.set_problem(d_x0, d_b)
+        hist = []
+        for it in range(1, max_it + 1):
+            self.cycle()
+            absres = self.residual_norm()
+            hist.append(absres)
+            if absres / sumb < tol:
+                break
+        self.collect_solution()
+        if self.rank == 0:
+            self.be.get_solution_device(d_out)
+        return len(hist), np.array(hist)
+
 
 class _CudaArray:
     """zero-copy torch view of a device pointer owned by libamgb200 (via __cuda_array_interface__)"""
@@ -396,10 +412,19 @@ class GpuBackend:
         self.L.amgb200_cycle_from(self.h, 1)
 
     def set_problem(self, x_nat, b_nat):
+        """x_nat, b_nat: host arrays, or torch tensors already resident on this rank's GPU (natural numbering)"""
         t = self.torch
         for src, dst in ((x_nat, self._x0), (b_nat, self._b0)):
-            self._nat.copy_(t.as_tensor(np.asarray(src, dtype=np.float64)))
+            if t.is_tensor(src):
+                self._nat.copy_(src)
+            else:
+                self._nat.copy_(t.as_tensor(np.asarray(src, dtype=np.float64)))
             self.L.amgb200_vec_to_schedule(self.h, 0, self.C.c_void_p(self._nat.data_ptr()), self.C.c_void_p(dst.data_ptr()))
+
+    def get_solution_device(self, out):
+        """level-0 x in natural numbering into the resident tensor `out` (no host copy)"""
+        self.L.amgb200_vec_to_natural(self.h, 0, self.C.c_void_p(self._x0.data_ptr()), self.C.c_void_p(out.data_ptr()))
+        return out
 
     def get_solution(self):
         self.L.amgb200_vec_to_natural(self.h, 0, self.C.c_void_p(self._x0.data_ptr()), self.C.c_void_p(self._nat.data_ptr()))
