@@ -59,7 +59,7 @@ class Smtr(C.Structure):         # SSS_SMTR
 
 class Options(C.Structure):      # amgb200_options
     _fields_ = [("coarse_mode", C.c_int), ("verbose", C.c_int), ("device", C.c_int), ("fast", C.c_int),
-                ("reserved", C.c_int * 4)]
+                ("level0_worker", C.c_int), ("reserved", C.c_int * 3)]
 
 
 assert C.sizeof(Mat) == 40 and C.sizeof(Vec) == 16 and C.sizeof(Rtn) == 24
@@ -78,7 +78,7 @@ EXPORTS = [
     "amgb200_l0_residual", "amgb200_l0_prolong", "amgb200_restrict_from", "amgb200_cycle_from",
     "amgb200_vec_to_schedule", "amgb200_vec_to_natural", "amgb200_sync", "amgb200_setup_ex", "amgb200_interp_device",
     "amgb200_ipc_export", "amgb200_ipc_open", "amgb200_peer_plan", "amgb200_peer_run", "amgb200_read_mtx", "amgb200_level_download",
-    "amgb200_level_resid_restrict", "amgb200_level_fused", "amgb200_rap_device",
+    "amgb200_level_resid_restrict", "amgb200_level_fused", "amgb200_rap_device", "amgb200_ghost_lists",
 ]
 
 _lib = None

@@ -1052,7 +1052,10 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
     }
     if (mg->num_levels < 1 || mg->num_levels > 64) { fprintf(stderr, "libamgb200: %d levels (supported: 1..64)\n", mg->num_levels); exit(72); }
     amgb200_hier *h = new amgb200_hier();
-    h->nl = mg->num_levels;
+    // level-0 worker of the sharded solve: levels 0 and 1 only, and of level 1 nothing but its vectors in its REAL schedule numbering
+    // (P_0's columns and the coarse correction that rank 0 stores into x_1 use it)
+    const bool worker = opt.level0_worker && mg->num_levels >= 2;
+    h->nl = worker ? 2 : mg->num_levels;
     h->pars = mg->pars;
     h->opt = opt;
     h->profile = getenv("AMGB200_PROFILE") && atoi(getenv("AMGB200_PROFILE")) > 0;
@@ -1099,8 +1102,8 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         std::vector<const amgb200_mat *> mats;                  // in the order the level loop below asks for them
         for (int l = 0; l < nl; ++l) {
             const amgb200_comp &c = mg->cg[l];
-            if (kind_of(c.A) == KIND_SELL) mats.push_back(&c.A);
-            if (l < nl - 1) { if (kind_of(c.P) == KIND_SELL) mats.push_back(&c.P); if (kind_of(c.R) == KIND_SELL) mats.push_back(&c.R); }
+            if (kind_of(c.A) == KIND_SELL && !(worker && l == 1)) mats.push_back(&c.A);
+            if (l < nl - 1) { if (kind_of(c.P) == KIND_SELL) mats.push_back(&c.P); if (kind_of(c.R) == KIND_SELL && !worker) mats.push_back(&c.R); }
         }
         prefetch.start(mats, dev);
     }
@@ -1141,6 +1144,8 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
                                 "diagonal (SSS_smooth.c:13,30) cannot be reproduced in parallel\n", l, sched[l].rows_without_diag);
                 exit(-22);
             }
+        } else if (worker && l + 1 < mg->num_levels) {
+            build_schedule(c.A, (mg->pars.cf_order && c.cfmark.d) ? c.cfmark.d : nullptr, sched[l]);      // level 1 as rank 0 numbers it
         } else {
             identity_schedule(c.A.num_rows, sched[l]);
         }
@@ -1430,10 +1435,13 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             const bool one_chunk = max_len <= 28 && (size_t)c.A.num_rows * 8 > (size_t)h->max_dyn_smem && kind_of(c.A) == KIND_SELL;
             if (!one_chunk) gs_kind = KIND_CSR;
         }
-        put_matrix(lv.A, lay, c.A, S, lv.d_order, &S, d_pos[l], gs_kind, lv.smoothed ? &S.wf_row_ptr : nullptr, "A", l);
-        max_items = std::max(max_items, lay.nitems());
+        const bool vectors_only = worker && l == 1;            // (level-0 worker: level 1 only lends its numbering and its vectors)
+        if (!vectors_only) {
+            put_matrix(lv.A, lay, c.A, S, lv.d_order, &S, d_pos[l], gs_kind, lv.smoothed ? &S.wf_row_ptr : nullptr, "A", l);
+            max_items = std::max(max_items, lay.nitems());
+        }
         DevLayout lsp_keep;
-        if (gs_kind != kind_of(c.A)) {
+        if (gs_kind != kind_of(c.A) && !vectors_only) {
             DevLayout &lsp = lsp_keep;
             put_matrix(lv.Asp, lsp, c.A, S, lv.d_order, &S, d_pos[l], kind_of(c.A), nullptr, "A(spmv)", l);
             max_items = std::max(max_items, lsp.nitems());
@@ -1525,14 +1533,16 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
             DevLayout lp, lr;
             put_matrix(lv.P, lp, c.P, S, lv.d_order, &sched[l + 1], d_pos[l + 1], kind_of(c.P), nullptr, "P", l);
             max_items = std::max(max_items, lp.nitems());
-            put_matrix(lv.R, lr, c.R, sched[l + 1], h->L[l + 1].d_order, &S, d_pos[l], kind_of(c.R), nullptr, "R", l);
-            max_items = std::max(max_items, lr.nitems());
+            if (!worker) {                                      // (restriction and everything below it run on rank 0)
+                put_matrix(lv.R, lr, c.R, sched[l + 1], h->L[l + 1].d_order, &S, d_pos[l], kind_of(c.R), nullptr, "R", l);
+                max_items = std::max(max_items, lr.nitems());
+            }
             // residual (+) restriction in one launch: both operators thread-per-row (the levels that carry the bytes)
             const DevLayout &la = lv.Asp.valid ? lsp_keep : lay;
             // (measured: the instances for rows longer than one register chunk need 80-114 registers and lose to the separate kernels --
             // 256^3 level 1: 691 vs 586 us -- so only single-chunk operators, i.e. level 0 of the 5-/7-point problems, take it by default)
             const bool rr_short = la.max_row <= 8 && lr.max_row <= 8;
-            if (use_fused && (rr_short || rr_all) && la.kind == KIND_SELL && lr.kind == KIND_SELL && lv.n >= rr_min_rows && la.nitems() >= 1 && lr.nitems() >= 1) {
+            if (use_fused && !worker && (rr_short || rr_all) && la.kind == KIND_SELL && lr.kind == KIND_SELL && lv.n >= rr_min_rows && la.nitems() >= 1 && lr.nitems() >= 1) {
                 const double tl = now_s();
                 build_fused(lv, la, lr, S, sched[l + 1], c.R);
                 tl_note("fused", l, now_s() - tl);

@@ -164,11 +164,13 @@ def solve_dropin(hier, x0, b):
 class DeviceHierarchy:
     """Resident device mirror (amgb200_upload)."""
 
-    def __init__(self, hier, coarse_mode=0, verbose=0, device=-1, fast=None):
+    def __init__(self, hier, coarse_mode=0, verbose=0, device=-1, fast=None, level0_worker=False):
+        """level0_worker: only what the row-block kernels of level 0 need becomes resident (ranks >= 1 of the sharded solve)"""
         self._lib = capi.lib()
         opt = capi.Options()
         self._lib.amgb200_default_options(C.byref(opt))
         opt.coarse_mode = coarse_mode
+        opt.level0_worker = 1 if level0_worker else 0
         if fast is not None:
             opt.fast = int(fast)
         opt.verbose = verbose

@@ -400,7 +400,7 @@ def main():
                "definition": "SSS_amg_solve(mg, x, b) with host buffers: schedule analysis + layout build + H2D of the hierarchy + solve + D2H; "
                              "value = mean of the calls after the first"}
 
-    dev = DeviceHierarchy(hier, device=local_rank, fast=1 if args.fast else None)
+    dev = DeviceHierarchy(hier, device=local_rank, fast=1 if args.fast else None, level0_worker=bool(dist) and rank > 0)
     if e2e is not None:
         e2e["h2d_bytes_per_step"] = dev.device_bytes() + 2 * 8 * n
         e2e["d2h_bytes_per_step"] = 8 * n + 8 * (e2e["vcycles"] + 1)
@@ -472,19 +472,24 @@ def main():
         for rep in range(1 + 1):
             dist.barrier(); torch.cuda.synchronize()
             t0 = time.perf_counter()
-            dev2 = DeviceHierarchy(hier, device=local_rank)
+            dev2 = DeviceHierarchy(hier, device=local_rank, level0_worker=rank > 0)
+            t1 = time.perf_counter()
             be2 = GpuBackend(dev2, torch)
             sh2 = ShardedSolver(be2, A, dist, rank, world, hier.pars.pre_iter, hier.pars.post_iter)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
             nits2, hist2, x2 = sh2.solve(ones, ones, TOL)
             torch.cuda.synchronize()
-            dt = torch.tensor([1e3 * (time.perf_counter() - t0)], dtype=torch.float64, device="cuda")
+            t3 = time.perf_counter()
+            dt = torch.tensor([1e3 * (t3 - t0), 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2)], dtype=torch.float64, device="cuda")
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             if rep:
-                e2e_t.append(float(dt.item()))
+                e2e_t.append(float(dt[0].item()))
+                e2e_parts = {"upload_ms": float(dt[1].item()), "partition_ghost_lists_peer_setup_ms": float(dt[2].item()), "solve_from_host_buffers_ms": float(dt[3].item())}
             del sh2, be2
             dev2.close()
         e2e = {"value": sum(e2e_t) / len(e2e_t), "unit": "ms", "h2d_bytes_per_step": dev.device_bytes() + 2 * 8 * n, "d2h_bytes_per_step": 8 * n,
-               "calls": len(e2e_t), "warmup_calls": 1, "vcycles": int(nits2),
+               "calls": len(e2e_t), "warmup_calls": 1, "vcycles": int(nits2), "breakdown_max_over_ranks": e2e_parts,
                "definition": "per rank: schedule analysis + layout build + H2D of the hierarchy + partition / ghost lists, then the sharded solve from host "
                              "buffers and x back on the host of rank 0; max over ranks (same content as the N = 1 e2e)"}
         ms_step = ms_total / args.steps

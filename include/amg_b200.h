@@ -140,7 +140,10 @@ typedef struct amgb200_options_ {
                                     1: FAST -- long rows and Krylov dot products use tree reductions (~1e-16 per
                                     operation, amplified by |x|/|r| to ~1e-7 in the last residuals).
                                     env AMGB200_FAST=1 overrides */
-    int reserved[4];
+    int level0_worker;           /* multi-GPU: 1 = this device only runs the row-block kernels of level 0 (ranks >= 1 of the sharded
+                                    solve): A_0, P_0 and the vectors of levels 0 and 1 (in level 1's real schedule numbering) become
+                                    resident, nothing below; amgb200_num_levels() returns 2 */
+    int reserved[3];
 } amgb200_options;
 
 void amgb200_default_options(amgb200_options *o);
@@ -287,6 +290,12 @@ int amgb200_interp_device(const amgb200_mat *A, const int *mark, amgb200_mat *P,
  * solve phase.  R_out / Ac_out receive calloc'ed host CSR arrays owned by the caller (freed by SSS_amg_data_destroy like the
  * reference's).  Returns 0; 1 = a product row exceeds 8192 columns or the product 2^31 entries: nothing returned, use the host loops. */
 int amgb200_rap_device(const amgb200_mat *A, const amgb200_mat *P, amgb200_mat *R_out, amgb200_mat *Ac_out);
+/* multi-GPU harness helper (host only, no reference counterpart): ghost lists of a row-block partition of level 0.  order[n]: schedule
+ * position -> natural row; f_bounds / c_bounds: world + 1 ascending schedule-row offsets of the ranks' F / C blocks.  *idx receives the
+ * concatenated lists (malloc'ed; free()), ptr[world*world*2 + 1] their offsets, list key = (reader * world + owner) * 2 + pass of the
+ * ghost entry (0 F, 1 C); every list holds ascending, distinct schedule indices.  Returns the total length. */
+long long amgb200_ghost_lists(const amgb200_mat *A, const int *order, int nF, int world, const long long *f_bounds, const long long *c_bounds, int **idx,
+                              long long *ptr);
 void amgb200_amg_destroy(amgb200_amg *mg);
 void amgb200_default_pars(amgb200_pars *p);   /* SSS_main.c:25-64 */
 

@@ -179,3 +179,24 @@ def test_partition_and_ghost_lists_cover_every_read():
             for src, idx in g[w].items():
                 assert (part.owner(idx) == src).all()
     assert owned_total == sh["n"]
+
+
+@pytest.mark.parametrize("kind,N,world", [("p3d", 12, 2), ("p3d", 14, 3), ("p2d", 40, 4), ("p3d", 16, 8)])
+def test_native_ghost_lists_equal_the_numpy_ones(kind, N, world):
+    """amgb200_ghost_lists (one OpenMP pass in libamgb200.so's host part) against the per-rank and the vectorised numpy versions"""
+    from amg_b200 import HostHierarchy, generate
+    from amg_b200.distributed import Partition, all_ghost_lists, all_ghost_lists_native, ghost_lists
+    A = generate(kind, N)
+    hier = HostHierarchy(A, tol=1e-8)
+    import torch
+    be = CpuBackend(hier, torch)
+    sh = be.shape()
+    part = Partition(sh["n"], sh["nF"], sh["itemsF"], sh["itemsC"], 32, world)
+    order = be.order()
+    a, b = all_ghost_lists(A, order, part), all_ghost_lists_native(A, order, part)
+    for r in range(world):
+        g = ghost_lists(A, order, part, r)
+        for w in (0, 1):
+            assert sorted(a[r][w]) == sorted(b[r][w]) == sorted(g[w])
+            for src in a[r][w]:
+                assert np.array_equal(a[r][w][src], b[r][w][src]) and np.array_equal(g[w][src], b[r][w][src])

@@ -22,7 +22,7 @@ if rank == 0:
     rtn1, x1, hist1 = dev1.solve(np.ones(n), np.ones(n))
     dev1.close()
     ref = (rtn1.nits, x1, hist1)
-dev = DeviceHierarchy(hier, device=lr)
+dev = DeviceHierarchy(hier, device=lr, level0_worker=rank > 0)
 solver = ShardedSolver(GpuBackend(dev, torch), A, dist, rank, world)
 for rep in range(3):
     dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
