@@ -170,28 +170,38 @@ struct SellItem {
 // order; x_i = t / a_ii when |a_ii| > 1e-20
 // rows no longer than one chunk (max row length <= SCH, e.g. level 0 of the 5-/7-point problems): no loop,
 // no next-chunk registers -> ~40 registers, 6 blocks/SM for the HBM-bound kernels
+// Branch-free on purpose: written as `if (valid) t -= a * x` per entry, ptxas turns every entry into its own divergence region
+// (BSSY / BRA / DMUL / DADD / BSYNC: ~125 cycles per entry ON the dependency chain, 2 700 cycles for a 20-slot row against 145 for the
+// division -- tools/ubench5.cu).  Instead all products are formed first (independent, pipelined), padding and the diagonal slot get the
+// neutral element -- t - (+0.0) = t and t + (-0.0) = t bit for bit, for every t including the signed zeros -- and the chain is SCH
+// dependent DSUB / DADD and nothing else (8.1 cycles each).
 template <bool COH, int SCH>
 __device__ __forceinline__ void gs_finish_sell_one(SellItem<SCH> &it, double *x) {
     double t = it.bk, d = 0.0;
-    double xv[SCH];
-#pragma unroll
-    for (int u = 0; u < SCH; ++u) xv[u] = (it.j[u] >= 0 && it.j[u] != it.k) ? ld_x<COH>(x + it.j[u]) : 0.0;
+    double pr[SCH];
 #pragma unroll
     for (int u = 0; u < SCH; ++u) {
-        if (it.j[u] == it.k) d = it.a[u];
-        else if (it.j[u] >= 0) t = __dsub_rn(t, __dmul_rn(it.a[u], xv[u]));
+        const bool off = it.j[u] >= 0 && it.j[u] != it.k;
+        const double xv = off ? ld_x<COH>(x + it.j[u]) : 0.0;
+        pr[u] = off ? __dmul_rn(it.a[u], xv) : 0.0;
+        d = it.j[u] == it.k ? it.a[u] : d;
     }
+#pragma unroll
+    for (int u = 0; u < SCH; ++u) t = __dsub_rn(t, pr[u]);
     if (it.k < it.r1 && fabs(d) > GS_TINY) x[it.k] = gs_quotient(t, d, it.recip);
 }
 template <int SCH, bool COH = false>
 __device__ __forceinline__ double spmv_finish_sell_one(SellItem<SCH> &it, const double *__restrict__ x) {
     double t = 0.0;
-    double xv[SCH];
+    double pr[SCH];
 #pragma unroll
-    for (int u = 0; u < SCH; ++u) xv[u] = it.j[u] >= 0 ? ld_x<COH>(x + it.j[u]) : 0.0;
+    for (int u = 0; u < SCH; ++u) {
+        const bool on = it.j[u] >= 0;
+        const double xv = on ? ld_x<COH>(x + it.j[u]) : 0.0;
+        pr[u] = on ? __dmul_rn(it.a[u], xv) : -0.0;
+    }
 #pragma unroll
-    for (int u = 0; u < SCH; ++u)
-        if (it.j[u] >= 0) t = __dadd_rn(t, __dmul_rn(it.a[u], xv[u]));
+    for (int u = 0; u < SCH; ++u) t = __dadd_rn(t, pr[u]);
     return t;
 }
 
@@ -200,9 +210,14 @@ __device__ __forceinline__ void gs_finish_sell(SellItem<SCH> &it, double *x) {
     const bool active = it.k < it.r1;
     double t = it.bk, d = 0.0;
     for (int e0 = 0; e0 < it.width; e0 += SCH) {
-        double xv[SCH];
+        double pr[SCH];
 #pragma unroll
-        for (int u = 0; u < SCH; ++u) xv[u] = (it.j[u] >= 0 && it.j[u] != it.k) ? ld_x<COH>(x + it.j[u]) : 0.0;
+        for (int u = 0; u < SCH; ++u) {
+            const bool off = it.j[u] >= 0 && it.j[u] != it.k;
+            const double xv = off ? ld_x<COH>(x + it.j[u]) : 0.0;
+            pr[u] = off ? __dmul_rn(it.a[u], xv) : 0.0;
+            d = it.j[u] == it.k ? it.a[u] : d;
+        }
         int jn[SCH];
         double an[SCH];
         const bool more = e0 + SCH < it.width;
@@ -214,10 +229,7 @@ __device__ __forceinline__ void gs_finish_sell(SellItem<SCH> &it, double *x) {
             }
         }
 #pragma unroll
-        for (int u = 0; u < SCH; ++u) {
-            if (it.j[u] == it.k) d = it.a[u];
-            else if (it.j[u] >= 0) t = __dsub_rn(t, __dmul_rn(it.a[u], xv[u]));
-        }
+        for (int u = 0; u < SCH; ++u) t = __dsub_rn(t, pr[u]);
         if (more) {
 #pragma unroll
             for (int u = 0; u < SCH; ++u) { it.j[u] = jn[u]; it.a[u] = an[u]; }
@@ -231,9 +243,13 @@ template <int SCH, bool COH = false>
 __device__ __forceinline__ double spmv_finish_sell(SellItem<SCH> &it, const double *__restrict__ x) {
     double t = 0.0;
     for (int e0 = 0; e0 < it.width; e0 += SCH) {
-        double xv[SCH];
+        double pr[SCH];
 #pragma unroll
-        for (int u = 0; u < SCH; ++u) xv[u] = it.j[u] >= 0 ? ld_x<COH>(x + it.j[u]) : 0.0;
+        for (int u = 0; u < SCH; ++u) {
+            const bool on = it.j[u] >= 0;
+            const double xv = on ? ld_x<COH>(x + it.j[u]) : 0.0;
+            pr[u] = on ? __dmul_rn(it.a[u], xv) : -0.0;
+        }
         int jn[SCH];
         double an[SCH];
         const bool more = e0 + SCH < it.width;
@@ -245,8 +261,7 @@ __device__ __forceinline__ double spmv_finish_sell(SellItem<SCH> &it, const doub
             }
         }
 #pragma unroll
-        for (int u = 0; u < SCH; ++u)
-            if (it.j[u] >= 0) t = __dadd_rn(t, __dmul_rn(it.a[u], xv[u]));
+        for (int u = 0; u < SCH; ++u) t = __dadd_rn(t, pr[u]);
         if (more) {
 #pragma unroll
             for (int u = 0; u < SCH; ++u) { it.j[u] = jn[u]; it.a[u] = an[u]; }
@@ -1670,7 +1685,7 @@ __global__ void __launch_bounds__(DF_BLOCK, DF_MINB) gs_dataflow_kernel(DMat A, 
                 for (int v = 0; v < DF_BATCH; ++v) {
                     const int u = u0 + v;
                     if (u < SCH) {
-                        if (j[u] == k) d = a[u];
+                        if (j[u] == k) { d = a[u]; a[u] = 0.0; }                               // (+0.0: neutral in the chain below)
                         else if (j[u] >= 0) {
                             double xv;
                             if (s == 0 && j[u] > k) a[u] = __dmul_rn(a[u], xo[v]);
@@ -1722,10 +1737,11 @@ __global__ void __launch_bounds__(DF_BLOCK, DF_MINB) gs_dataflow_kernel(DMat A, 
                 }
             }
             DF_CLK(c3)
-            // ---- in-order chain over the separately rounded products
+            // ---- in-order chain over the separately rounded products: branch-free (padding and the diagonal slot hold +0.0, and
+            // t - (+0.0) = t bit for bit); a per-entry `if` costs a divergence region of ~125 cycles per entry on the dependency path
+            // (tools/ubench5.cu)
 #pragma unroll
-            for (int u = 0; u < SCH; ++u)
-                if (j[u] >= 0 && j[u] != k) tacc = __dsub_rn(tacc, a[u]);
+            for (int u = 0; u < SCH; ++u) tacc = __dsub_rn(tacc, a[u]);
 #ifdef AMGB200_DF_TIMING
             tf += c1 - c0; tg += c2 - c1; tp_ += c3 - c2;
 #endif
