@@ -170,46 +170,16 @@ struct SellItem {
 // order; x_i = t / a_ii when |a_ii| > 1e-20
 // rows no longer than one chunk (max row length <= SCH, e.g. level 0 of the 5-/7-point problems): no loop,
 // no next-chunk registers -> ~40 registers, 6 blocks/SM for the HBM-bound kernels
-// Branch-free on purpose: written as `if (valid) t -= a * x` per entry, ptxas turns every entry into its own divergence region
-// (BSSY / BRA / DMUL / DADD / BSYNC: ~125 cycles per entry ON the dependency chain, 2 700 cycles for a 20-slot row against 145 for the
-// division -- tools/ubench5.cu).  Instead all products are formed first (independent, pipelined), padding and the diagonal slot get the
-// neutral element -- t - (+0.0) = t and t + (-0.0) = t bit for bit, for every t including the signed zeros -- and the chain is SCH
-// dependent DSUB / DADD and nothing else (8.1 cycles each).
-template <bool COH, int SCH>
+// Two forms of the same arithmetic.  LAT = false (throughput-bound kernels: gs_pass, spmv, resid_restrict): a per-entry `if`, which skips the
+// work of padding slots and measured 5-10 % more HBM throughput.  LAT = true (latency-bound ordered sweeps): branch-free -- ptxas turns every
+// per-entry `if` into its own divergence region (BSSY / BRA / DMUL / DADD / BSYNC: ~125 cycles per entry ON the dependency chain, 2 700 cycles
+// for a 20-slot row against 145 for the division; tools/ubench5.cu).  There all products are formed first (independent, pipelined), padding
+// and the diagonal slot get the neutral element -- t - (+0.0) = t and t + (-0.0) = t bit for bit, for every t including the signed zeros --
+// and the chain is SCH dependent DSUB / DADD and nothing else (8.1 cycles each).  Both forms give the same bits.
+template <bool COH, int SCH, bool LAT = false>
 __device__ __forceinline__ void gs_finish_sell_one(SellItem<SCH> &it, double *x) {
     double t = it.bk, d = 0.0;
-    double pr[SCH];
-#pragma unroll
-    for (int u = 0; u < SCH; ++u) {
-        const bool off = it.j[u] >= 0 && it.j[u] != it.k;
-        const double xv = off ? ld_x<COH>(x + it.j[u]) : 0.0;
-        pr[u] = off ? __dmul_rn(it.a[u], xv) : 0.0;
-        d = it.j[u] == it.k ? it.a[u] : d;
-    }
-#pragma unroll
-    for (int u = 0; u < SCH; ++u) t = __dsub_rn(t, pr[u]);
-    if (it.k < it.r1 && fabs(d) > GS_TINY) x[it.k] = gs_quotient(t, d, it.recip);
-}
-template <int SCH, bool COH = false>
-__device__ __forceinline__ double spmv_finish_sell_one(SellItem<SCH> &it, const double *__restrict__ x) {
-    double t = 0.0;
-    double pr[SCH];
-#pragma unroll
-    for (int u = 0; u < SCH; ++u) {
-        const bool on = it.j[u] >= 0;
-        const double xv = on ? ld_x<COH>(x + it.j[u]) : 0.0;
-        pr[u] = on ? __dmul_rn(it.a[u], xv) : -0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < SCH; ++u) t = __dadd_rn(t, pr[u]);
-    return t;
-}
-
-template <bool COH, int SCH>
-__device__ __forceinline__ void gs_finish_sell(SellItem<SCH> &it, double *x) {
-    const bool active = it.k < it.r1;
-    double t = it.bk, d = 0.0;
-    for (int e0 = 0; e0 < it.width; e0 += SCH) {
+    if constexpr (LAT) {
         double pr[SCH];
 #pragma unroll
         for (int u = 0; u < SCH; ++u) {
@@ -218,6 +188,52 @@ __device__ __forceinline__ void gs_finish_sell(SellItem<SCH> &it, double *x) {
             pr[u] = off ? __dmul_rn(it.a[u], xv) : 0.0;
             d = it.j[u] == it.k ? it.a[u] : d;
         }
+#pragma unroll
+        for (int u = 0; u < SCH; ++u) t = __dsub_rn(t, pr[u]);
+    } else {
+        double xv[SCH];
+#pragma unroll
+        for (int u = 0; u < SCH; ++u) xv[u] = (it.j[u] >= 0 && it.j[u] != it.k) ? ld_x<COH>(x + it.j[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < SCH; ++u) {
+            if (it.j[u] == it.k) d = it.a[u];
+            else if (it.j[u] >= 0) t = __dsub_rn(t, __dmul_rn(it.a[u], xv[u]));
+        }
+    }
+    if (it.k < it.r1 && fabs(d) > GS_TINY) x[it.k] = gs_quotient(t, d, it.recip);
+}
+template <int SCH, bool COH = false, bool LAT = false>
+__device__ __forceinline__ double spmv_finish_sell_one(SellItem<SCH> &it, const double *__restrict__ x) {
+    double t = 0.0;
+    if constexpr (LAT) {
+        double pr[SCH];
+#pragma unroll
+        for (int u = 0; u < SCH; ++u) {
+            const bool on = it.j[u] >= 0;
+            const double xv = on ? ld_x<COH>(x + it.j[u]) : 0.0;
+            pr[u] = on ? __dmul_rn(it.a[u], xv) : -0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < SCH; ++u) t = __dadd_rn(t, pr[u]);
+    } else {
+        double xv[SCH];
+#pragma unroll
+        for (int u = 0; u < SCH; ++u) xv[u] = it.j[u] >= 0 ? ld_x<COH>(x + it.j[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < SCH; ++u)
+            if (it.j[u] >= 0) t = __dadd_rn(t, __dmul_rn(it.a[u], xv[u]));
+    }
+    return t;
+}
+
+template <bool COH, int SCH, bool LAT = false>
+__device__ __forceinline__ void gs_finish_sell(SellItem<SCH> &it, double *x) {
+    const bool active = it.k < it.r1;
+    double t = it.bk, d = 0.0;
+    for (int e0 = 0; e0 < it.width; e0 += SCH) {
+        double xv[SCH];
+#pragma unroll
+        for (int u = 0; u < SCH; ++u) xv[u] = (it.j[u] >= 0 && it.j[u] != it.k) ? ld_x<COH>(x + it.j[u]) : 0.0;
         int jn[SCH];
         double an[SCH];
         const bool more = e0 + SCH < it.width;
@@ -228,8 +244,22 @@ __device__ __forceinline__ void gs_finish_sell(SellItem<SCH> &it, double *x) {
                 else { jn[u] = -1; an[u] = 0.0; }
             }
         }
+        if constexpr (LAT) {
 #pragma unroll
-        for (int u = 0; u < SCH; ++u) t = __dsub_rn(t, pr[u]);
+            for (int u = 0; u < SCH; ++u) {
+                const bool off = it.j[u] >= 0 && it.j[u] != it.k;
+                d = it.j[u] == it.k ? it.a[u] : d;
+                xv[u] = off ? __dmul_rn(it.a[u], xv[u]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < SCH; ++u) t = __dsub_rn(t, xv[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < SCH; ++u) {
+                if (it.j[u] == it.k) d = it.a[u];
+                else if (it.j[u] >= 0) t = __dsub_rn(t, __dmul_rn(it.a[u], xv[u]));
+            }
+        }
         if (more) {
 #pragma unroll
             for (int u = 0; u < SCH; ++u) { it.j[u] = jn[u]; it.a[u] = an[u]; }
@@ -239,17 +269,13 @@ __device__ __forceinline__ void gs_finish_sell(SellItem<SCH> &it, double *x) {
 }
 
 // row sum t = sum_k a_k x_{j_k} from 0.0 in storage order (amg/SSS_utils.c:169-177, :190-200)
-template <int SCH, bool COH = false>
+template <int SCH, bool COH = false, bool LAT = false>
 __device__ __forceinline__ double spmv_finish_sell(SellItem<SCH> &it, const double *__restrict__ x) {
     double t = 0.0;
     for (int e0 = 0; e0 < it.width; e0 += SCH) {
-        double pr[SCH];
+        double xv[SCH];
 #pragma unroll
-        for (int u = 0; u < SCH; ++u) {
-            const bool on = it.j[u] >= 0;
-            const double xv = on ? ld_x<COH>(x + it.j[u]) : 0.0;
-            pr[u] = on ? __dmul_rn(it.a[u], xv) : -0.0;
-        }
+        for (int u = 0; u < SCH; ++u) xv[u] = it.j[u] >= 0 ? ld_x<COH>(x + it.j[u]) : 0.0;
         int jn[SCH];
         double an[SCH];
         const bool more = e0 + SCH < it.width;
@@ -260,8 +286,16 @@ __device__ __forceinline__ double spmv_finish_sell(SellItem<SCH> &it, const doub
                 else { jn[u] = -1; an[u] = 0.0; }
             }
         }
+        if constexpr (LAT) {
 #pragma unroll
-        for (int u = 0; u < SCH; ++u) t = __dadd_rn(t, pr[u]);
+            for (int u = 0; u < SCH; ++u) xv[u] = it.j[u] >= 0 ? __dmul_rn(it.a[u], xv[u]) : -0.0;
+#pragma unroll
+            for (int u = 0; u < SCH; ++u) t = __dadd_rn(t, xv[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < SCH; ++u)
+                if (it.j[u] >= 0) t = __dadd_rn(t, __dmul_rn(it.a[u], xv[u]));
+        }
         if (more) {
 #pragma unroll
             for (int u = 0; u < SCH; ++u) { it.j[u] = jn[u]; it.a[u] = an[u]; }
@@ -702,7 +736,7 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
         if (have) ++tm_items;
 #endif
         if (have) {
-            if constexpr (KIND == 0) gs_finish_sell<false>(ws, x);
+            if constexpr (KIND == 0) gs_finish_sell<false, 20, true>(ws, x);
             else if constexpr (TWO_PHASE) {
                 double t;
                 if (nlate >= 0) {                 // patch the few products that needed the wavefront just completed, then fold
@@ -720,7 +754,7 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CTA_MAX_WARPS_SELL : 32 * CTA
                 TL_MARK(5)
             } else gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod);
             for (int it = i0 + r + G; it < i1; it += G) {              // wavefront wider than the group
-                if constexpr (KIND == 0) { ws.prologue(A, it, lane, b); gs_finish_sell<false>(ws, x); }
+                if constexpr (KIND == 0) { ws.prologue(A, it, lane, b); gs_finish_sell<false, 20, true>(ws, x); }
                 else { wc.prologue(A, it, lane, b); gs_finish_csr<false, EXACT>(A, wc, x, lane, sprod); }
             }
         }
@@ -1445,8 +1479,8 @@ __global__ void __launch_bounds__(KIND == 0 ? 32 * CLUSTER_WARPS_SELL : 32 * CLU
     const int totalw = W * nsweeps;
     double *sp = sprod + (KIND == 1 ? warp * STAGE : 0);
     auto finish = [&](Item &w) {
-        if constexpr (KIND == 0 && ONE) gs_finish_sell_one<true>(w, x);
-        else if constexpr (KIND == 0) gs_finish_sell<true>(w, x);
+        if constexpr (KIND == 0 && ONE) gs_finish_sell_one<true, SCH, true>(w, x);
+        else if constexpr (KIND == 0) gs_finish_sell<true, SCH, true>(w, x);
         else gs_finish_csr<true, EXACT>(A, w, x, lane, sp);
     };
     constexpr bool DB = KIND == 0 && ONE && SCH <= 20;
@@ -2201,7 +2235,7 @@ __device__ __forceinline__ void cg_spmv(const DMat &A, const double *x, const do
         if constexpr (KIND == 0) {
             SellItem<8> w;
             w.prologue(A, it, lane);
-            const double t = spmv_finish_sell<8, true>(w, x);
+            const double t = spmv_finish_sell<8, true, true>(w, x);
             if (w.k < w.r1) __stcg(y + w.k, RESID ? __dadd_rn(__ldcg(b + w.k), __dmul_rn(t, -1.0)) : t);
         } else {
             CsrItem w;

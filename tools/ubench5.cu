@@ -9,7 +9,7 @@
 #include "../amg_b200/csrc/kernels.cuh"
 using namespace amgb200;
 
-template <int MODE>      // 0: x in shared, generic finish | 1: x in global (L1) | 2: x in global at L2 (COH) | 3: x in shared, single-chunk finish
+template <int MODE, bool LAT>      // LAT: branch-free form (kernels.cuh); 0: x in shared, generic finish | 1: x in global (L1) | 2: x in global at L2 (COH) | 3: x in shared, single-chunk finish
 __global__ void __launch_bounds__(32) slice_kernel(DMat A, const double *b, double *xg, int n, long long *out) {
     extern __shared__ double xs[];
     const int lane = threadIdx.x;
@@ -29,9 +29,9 @@ __global__ void __launch_bounds__(32) slice_kernel(DMat A, const double *b, doub
         if (probe == 1.2345e300) sink += 1;
         __syncwarp();
         const long long c1 = clock64();
-        if (MODE == 3) gs_finish_sell_one<false, 20>(ws, x);
-        else if (MODE == 2) gs_finish_sell<true, 20>(ws, x);
-        else gs_finish_sell<false, 20>(ws, x);
+        if (MODE == 3) gs_finish_sell_one<false, 20, LAT>(ws, x);
+        else if (MODE == 2) gs_finish_sell<true, 20, LAT>(ws, x);
+        else gs_finish_sell<false, 20, LAT>(ws, x);
         __syncwarp();
         __threadfence_block();
         const double back = x[ws.k < ws.r1 ? ws.k : 0];
@@ -71,18 +71,14 @@ int main() {
         A.slice_row = d_sr; A.slice_ptr = d_sp; A.col = d_col; A.val = d_val;
         long long h[5];
         const char *names[4] = {"x in shared memory, gs_finish_sell", "x in global memory (L1)", "x in global memory (L2, COH)", "x in shared memory, gs_finish_sell_one"};
-        for (int mode = 0; mode < 4; ++mode) {
-            cudaFuncSetAttribute(slice_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8);
-            cudaFuncSetAttribute(slice_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8);
-            cudaFuncSetAttribute(slice_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8);
-            cudaFuncSetAttribute(slice_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8);
-            if (mode == 0) slice_kernel<0><<<1, 32, n * 8>>>(A, d_b, d_x, n, d_out);
-            if (mode == 1) slice_kernel<1><<<1, 32, n * 8>>>(A, d_b, d_x, n, d_out);
-            if (mode == 2) slice_kernel<2><<<1, 32, n * 8>>>(A, d_b, d_x, n, d_out);
-            if (mode == 3) slice_kernel<3><<<1, 32, n * 8>>>(A, d_b, d_x, n, d_out);
+        for (int lat = 0; lat < 2; ++lat) for (int mode = 0; mode < 4; ++mode) {
+            if (mode == 0) { if (lat) { cudaFuncSetAttribute(slice_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8); slice_kernel<0, true><<<1, 32, n * 8>>>(A, d_b, d_x, n, d_out); } else { cudaFuncSetAttribute(slice_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8); slice_kernel<0, false><<<1, 32, n * 8>>>(A, d_b, d_x, n, d_out); } }
+            if (mode == 1) { if (lat) { cudaFuncSetAttribute(slice_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8); slice_kernel<1, true><<<1, 32, n * 8>>>(A, d_b, d_x, n, d_out); } else { cudaFuncSetAttribute(slice_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8); slice_kernel<1, false><<<1, 32, n * 8>>>(A, d_b, d_x, n, d_out); } }
+            if (mode == 2) { if (lat) { cudaFuncSetAttribute(slice_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8); slice_kernel<2, true><<<1, 32, n * 8>>>(A, d_b, d_x, n, d_out); } else { cudaFuncSetAttribute(slice_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8); slice_kernel<2, false><<<1, 32, n * 8>>>(A, d_b, d_x, n, d_out); } }
+            if (mode == 3) { if (lat) { cudaFuncSetAttribute(slice_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8); slice_kernel<3, true><<<1, 32, n * 8>>>(A, d_b, d_x, n, d_out); } else { cudaFuncSetAttribute(slice_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 8); slice_kernel<3, false><<<1, 32, n * 8>>>(A, d_b, d_x, n, d_out); } }
             cudaMemcpy(h, d_out, 40, cudaMemcpyDeviceToHost);
-            printf("width %2d  %-40s prologue (descriptor + entries from L2) %5lld   finish (gathers + chain + division + store) %5lld   division alone %4lld   total %5lld cycles  (%s)\n",
-                   width, names[mode], h[0], h[1], h[2], h[3], cudaGetErrorString(cudaGetLastError()));
+            printf("width %2d  %s  %-40s prologue (descriptor + entries from L2) %5lld   finish (gathers + chain + division + store) %5lld   division alone %4lld   total %5lld cycles  (%s)\n",
+                   width, lat ? "branch-free" : "per-entry if", names[mode], h[0], h[1], h[2], h[3], cudaGetErrorString(cudaGetLastError()));
         }
         cudaFree(d_sr); cudaFree(d_sp); cudaFree(d_col); cudaFree(d_val); cudaFree(d_b); cudaFree(d_x); cudaFree(d_out);
     }
