@@ -1293,7 +1293,12 @@ amgb200_hier *amgb200_upload(const amgb200_amg *mg, const amgb200_options *opt_i
         }
     }
     // streaming cluster smoother: the other ordered levels (any layout; the packer works from the host matrix)
-    if (lv.ordered && h->exact && lv.strategy != 4 && lv.strategy != 7 && lv.W >= 4 && !getenv("AMGB200_GS_STRATEGY") && !(getenv("AMGB200_NO_XC") && atoi(getenv("AMGB200_NO_XC")))) {
+    // (not for narrow thread-per-row levels whose x fits in one SM's shared memory: with branch-free chains the single-CTA barrier kernel
+    // is faster there -- 2D 256^2 levels 2-5: 8.6 / 4.2 / 2.1 / 1.3 ms per solve against 11.3 / 5.3 / 2.3 / 1.4 on the cluster)
+    // (rows of one register chunk only: a second chunk is fetched on the dependency path -- anisotropic 64^3 level 4, 22 entries per row: 998 us
+    // per sweep against ~700 on the cluster)
+    const bool cta_keeps = lv.strategy == 2 && lay.kind == KIND_SELL && lv.x_in_smem && lay.max_row <= 20 && !(getenv("AMGB200_XC_SMALL") && atoi(getenv("AMGB200_XC_SMALL")));
+    if (lv.ordered && h->exact && lv.strategy != 4 && lv.strategy != 7 && !cta_keeps && lv.W >= 4 && !getenv("AMGB200_GS_STRATEGY") && !(getenv("AMGB200_NO_XC") && atoi(getenv("AMGB200_NO_XC")))) {
         ClusterStreamLayout SL;
         const double tl = now_s();
         build_stream_cluster(Amat, S, XC_CTAS, SL, (long long)h->max_dyn_smem - XC_HDR - 128, getenv("AMGB200_XC_LD") ? atoi(getenv("AMGB200_XC_LD")) : 3);

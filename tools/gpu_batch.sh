@@ -1,9 +1,4 @@
-export AMGB200_TIMEOP_SWEEPS=2
-B=$PWD/build_tl/libamgb200_base.so
-for r in 1 2 3; do
-python tools/sweep.py p3d 128 1,2 2>&1 | tail -1; AMGB200_LIB=$B python tools/sweep.py p3d 128 1,2 2>&1 | tail -1
-done
-for r in 1 2; do
-python tools/sweep.py aniso3d 128 0,1,2,3 2>&1 | tail -1; AMGB200_LIB=$B python tools/sweep.py aniso3d 128 0,1,2,3 2>&1 | tail -1
-python tools/sweep.py v27 96 0,1,2 2>&1 | tail -1; AMGB200_LIB=$B python tools/sweep.py v27 96 0,1,2 2>&1 | tail -1
-done
+AMGB200_CTA_G=4 AMGB200_CTA_D=2 python tools/quick_time.py aniso3d 64 2>&1 | grep -E "^solve|^L[45]" | cut -c1-120
+AMGB200_CTA_G=2 AMGB200_CTA_D=2 python tools/quick_time.py aniso3d 64 2>&1 | grep -E "^solve|^L[45]" | cut -c1-120
+AMGB200_CTA_G=1 AMGB200_CTA_D=2 python tools/quick_time.py aniso3d 64 2>&1 | grep -E "^solve|^L[45]" | cut -c1-120
+AMGB200_CTA_G=2 AMGB200_CTA_D=2 python tools/quick_time.py p2d 256 2>&1 | grep -E "^solve" | cut -c1-120
