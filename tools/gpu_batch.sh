@@ -1,4 +1,4 @@
-AMGB200_CTA_G=4 AMGB200_CTA_D=2 python tools/quick_time.py aniso3d 64 2>&1 | grep -E "^solve|^L[45]" | cut -c1-120
-AMGB200_CTA_G=2 AMGB200_CTA_D=2 python tools/quick_time.py aniso3d 64 2>&1 | grep -E "^solve|^L[45]" | cut -c1-120
-AMGB200_CTA_G=1 AMGB200_CTA_D=2 python tools/quick_time.py aniso3d 64 2>&1 | grep -E "^solve|^L[45]" | cut -c1-120
-AMGB200_CTA_G=2 AMGB200_CTA_D=2 python tools/quick_time.py p2d 256 2>&1 | grep -E "^solve" | cut -c1-120
+(time python -m pytest tests -m gpu -x -q) > gpurun_out/r2_pytest_gpu_h.log 2>&1; tail -4 gpurun_out/r2_pytest_gpu_h.log | head -2
+bash tools/final_runs.sh 2>&1 | grep -v "^\s*$" | head -8
+bash tools/profile_r2.sh > gpurun_out/r2_profile_script.log 2>&1; tail -8 gpurun_out/r2_profile_script.log
+du -sh gpurun_out

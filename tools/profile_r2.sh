@@ -18,4 +18,6 @@ done
 C="python tools/prof_coarse.py p3d 128"
 $C > gpurun_out/r2_plain_coarse_cg.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:coarse_cg_kernel -s 1 -c 1 -o gpurun_out/r2_coarse_cg -f $C > gpurun_out/r2_ncu_coarse_cg.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+# the reports of one call exceed gpurun's 64 MiB return limit: keep their raw pages as CSV (what tools/summarize_profiles.py reads)
+for r in gpurun_out/r2_*.ncu-rep; do ncu -i $r --page raw --csv > ${r%.ncu-rep}.raw.csv 2>/dev/null && rm -f $r; done
+ls -la gpurun_out/*.raw.csv
