@@ -78,7 +78,7 @@ EXPORTS = [
     "amgb200_l0_residual", "amgb200_l0_prolong", "amgb200_restrict_from", "amgb200_cycle_from",
     "amgb200_vec_to_schedule", "amgb200_vec_to_natural", "amgb200_sync", "amgb200_setup_ex", "amgb200_interp_device",
     "amgb200_ipc_export", "amgb200_ipc_open", "amgb200_peer_plan", "amgb200_peer_run", "amgb200_read_mtx", "amgb200_level_download",
-    "amgb200_level_resid_restrict", "amgb200_level_fused", "amgb200_rap_device", "amgb200_ghost_lists",
+    "amgb200_level_resid_restrict", "amgb200_level_fused", "amgb200_rap_device", "amgb200_ghost_lists", "amgb200_ghost_lists_ex", "amgb200_peer_start", "amgb200_peer_wait",
 ]
 
 _lib = None
@@ -170,6 +170,8 @@ def lib():
         L.amgb200_peer_plan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(c_int_p), c_int_p,
                                         c_int_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, c_int_p]
         L.amgb200_peer_run.argtypes = [C.c_void_p, C.c_int]
+        L.amgb200_peer_start.argtypes = [C.c_void_p, C.c_int]
+        L.amgb200_peer_wait.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
 

@@ -2075,7 +2075,11 @@ void amgb200_peer_plan(amgb200_hier *h, int plan, int npush, const double *my_ve
     pl.d_src = nsrc ? dev_upload(sr) : nullptr;
     pl.epoch = 0;
 }
-void amgb200_peer_run(amgb200_hier *h, int plan) {
+// one exchange = start (store my entries into the peers' vectors, then raise the epoch in their flag words) + wait (for the peers' epochs in
+// my flag words).  Kernels launched between the two run while the peers' stores are in flight: the interior rows of a level-0 pass, which
+// read no ghost entry, overlap the halo exchange (amg_b200/distributed.py: smooth).
+void amgb200_peer_start(amgb200_hier *h, int plan) {
+    if (plan < 0 || plan >= amgb200_hier::PEER_MAX_PLANS) { fprintf(stderr, "libamgb200: peer plan %d out of range\n", plan); exit(72); }
     amgb200_hier::PeerPlan &pl = h->peer_plan[plan];
     ++pl.epoch;
     if (pl.npush) {
@@ -2084,8 +2088,17 @@ void amgb200_peer_run(amgb200_hier *h, int plan) {
         ++g_launches;
     }
     if (pl.nflag) { peer_flag_kernel<<<1, 64, 0, h->stream>>>(pl.d_flag_ptr, pl.nflag, pl.epoch); ++g_launches; }
+    CUDA_CHECK(cudaGetLastError());
+}
+void amgb200_peer_wait(amgb200_hier *h, int plan) {
+    if (plan < 0 || plan >= amgb200_hier::PEER_MAX_PLANS) { fprintf(stderr, "libamgb200: peer plan %d out of range\n", plan); exit(72); }
+    amgb200_hier::PeerPlan &pl = h->peer_plan[plan];
     if (pl.nsrc) { peer_wait_kernel<<<1, 64, 0, h->stream>>>(h->d_peer_flags, pl.d_src, pl.nsrc, pl.epoch); ++g_launches; }
     CUDA_CHECK(cudaGetLastError());
+}
+void amgb200_peer_run(amgb200_hier *h, int plan) {
+    amgb200_peer_start(h, plan);
+    amgb200_peer_wait(h, plan);
 }
 void amgb200_sync(amgb200_hier *h) { CUDA_CHECK(cudaStreamSynchronize(h->stream)); }
 

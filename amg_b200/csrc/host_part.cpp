@@ -23,9 +23,16 @@ inline int owner_of(int k, int nF, int world, const long long *fb, const long lo
 // order[n]: schedule position -> natural row of level 0; f_bounds / c_bounds: world + 1 ascending schedule-row offsets of the F / C
 // blocks.  Returns the concatenated lists in *idx (malloc'ed, caller frees with free()) and their offsets in ptr[world*world*2 + 1]:
 // list key = (reader * world + owner) * 2 + pass of the ghost (0 F, 1 C); each list holds ascending, distinct schedule indices.
+extern "C" __attribute__((visibility("default"))) long long amgb200_ghost_lists_ex(const amgb200_mat *A, const int *order, int nF, int world, const long long *f_bounds,
+                                                                                     const long long *c_bounds, int **idx, long long *ptr, unsigned char *reads_ghost);
 extern "C" __attribute__((visibility("default"))) long long amgb200_ghost_lists(const amgb200_mat *A, const int *order, int nF, int world, const long long *f_bounds,
                                                                                   const long long *c_bounds, int **idx, long long *ptr) {
+    return amgb200_ghost_lists_ex(A, order, nF, world, f_bounds, c_bounds, idx, ptr, nullptr);
+}
+extern "C" __attribute__((visibility("default"))) long long amgb200_ghost_lists_ex(const amgb200_mat *A, const int *order, int nF, int world, const long long *f_bounds,
+                                                                                     const long long *c_bounds, int **idx, long long *ptr, unsigned char *reads_ghost) {
     const int n = A->num_rows;
+    if (reads_ghost) memset(reads_ghost, 0, (size_t)n);
     std::vector<int> pos((size_t)n);
 #pragma omp parallel for schedule(static)
     for (int k = 0; k < n; ++k) pos[order[k]] = k;
@@ -43,6 +50,7 @@ extern "C" __attribute__((visibility("default"))) long long amgb200_ghost_lists(
             for (int q = A->row_ptr[i]; q < A->row_ptr[i + 1]; ++q) {
                 const int cp = pos[A->col_idx[q]];
                 const int src = own[cp];
+                if (src != reader && reads_ghost) __atomic_store_n(&reads_ghost[pos[i]], (unsigned char)1, __ATOMIC_RELAXED);
                 if (src != reader) mine.push_back((unsigned long long)(((long long)reader * world + src) * 2 + (cp >= nF)) << 32 | (unsigned)cp);
             }
         }

@@ -111,8 +111,27 @@ def all_ghost_lists(A_nat, order, part):
     return out
 
 
-def all_ghost_lists_native(A_nat, order, part):
-    """the same lists from libamgb200.so's host helper (amgb200_ghost_lists: one OpenMP pass; the numpy version above takes 1.3 s at 256^3)"""
+def interior_split(item_flags, a, b):
+    """items [a, b) of a pass, item_flags[it] = the item has a row that reads a ghost entry.  Returns (interior, boundary): the longest run of
+    unflagged items (they can run while the halo exchange is in flight) and the at most two ranges around it (after the wait)."""
+    if b <= a:
+        return (a, a), []
+    f = np.asarray(item_flags[a:b], dtype=bool)
+    best, run0 = (0, 0), None
+    for i, v in enumerate(np.append(f, True)):
+        if not v and run0 is None:
+            run0 = i
+        elif v and run0 is not None:
+            if i - run0 > best[1] - best[0]:
+                best = (run0, i)
+            run0 = None
+    i0, i1 = a + best[0], a + best[1]
+    return (i0, i1), [r for r in ((a, i0), (i1, b)) if r[1] > r[0]]
+
+
+def all_ghost_lists_native(A_nat, order, part, reads_ghost=None):
+    """the same lists from libamgb200.so's host helper (amgb200_ghost_lists: one OpenMP pass; the numpy version above takes 1.3 s at 256^3);
+    reads_ghost: optional uint8 array of n entries, set to 1 for every schedule row that reads an entry owned by another rank"""
     import ctypes as C
     from . import capi
     L = capi.lib()
@@ -122,9 +141,10 @@ def all_ghost_lists_native(A_nat, order, part):
     order32 = np.ascontiguousarray(order, dtype=np.int32)
     ptr = np.zeros(world * world * 2 + 1, np.int64)
     idx = C.POINTER(C.c_int)()
-    L.amgb200_ghost_lists.restype = C.c_longlong
-    L.amgb200_ghost_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(C.c_int)), C.c_void_p]
-    total = L.amgb200_ghost_lists(C.byref(A_nat.c), order32.ctypes.data, int(part.nF), int(world), fb.ctypes.data, cb.ctypes.data, C.byref(idx), ptr.ctypes.data)
+    L.amgb200_ghost_lists_ex.restype = C.c_longlong
+    L.amgb200_ghost_lists_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(C.c_int)), C.c_void_p, C.c_void_p]
+    total = L.amgb200_ghost_lists_ex(C.byref(A_nat.c), order32.ctypes.data, int(part.nF), int(world), fb.ctypes.data, cb.ctypes.data, C.byref(idx), ptr.ctypes.data,
+                                     reads_ghost.ctypes.data if reads_ghost is not None else None)
     flat = np.ctypeslib.as_array(idx, shape=(max(int(total), 1),))[:int(total)].astype(np.int64)
     C.CDLL(None).free(idx)
     out = {r: {0: {}, 1: {}} for r in range(world)}
@@ -159,7 +179,9 @@ class ShardedSolver:
         self.pre, self.post = pre, post
         order = backend.order()
         # what I need from each peer, and (same function evaluated for the peer) what each peer needs from me
-        allg = all_ghost_lists_native(A_nat, order, self.part) if hasattr(A_nat, "c") and getattr(backend, "native_lists", False) else all_ghost_lists(A_nat, order, self.part)
+        native = hasattr(A_nat, "c") and getattr(backend, "native_lists", False)
+        reads_ghost = np.zeros(sh["n"], np.uint8) if native else None
+        allg = all_ghost_lists_native(A_nat, order, self.part, reads_ghost) if native else all_ghost_lists(A_nat, order, self.part)
         mine = allg[rank]
         self.recv_idx = {w: {src: torch.as_tensor(v, dtype=torch.long, device=backend.device) for src, v in mine[w].items()} for w in (0, 1)}
         self.send_idx = {0: {}, 1: {}}
@@ -188,6 +210,17 @@ class ShardedSolver:
                         "srcs": [0] if rank else []}
             backend.peer_setup(dist, rank, world, plans)
         rpi = sh["rows_per_item"]
+        # interior / boundary split of my items of each pass (peer mode): the interior items read no ghost entry and run while the exchange
+        # is in flight, the boundary items after the wait
+        self.split = None
+        import os
+        if self.peer and reads_ghost is not None and hasattr(backend, "peer_start") and not int(os.environ.get("AMGB200_NO_OVERLAP", "0")):
+            nF, n = sh["nF"], sh["n"]
+            def item_flags(rows):                                 # rows of one pass -> flag per item of rpi rows
+                pad = (-len(rows)) % rpi
+                return np.pad(rows, (0, pad)).reshape(-1, rpi).any(axis=1)
+            flags = {0: item_flags(reads_ghost[:nF]), 1: item_flags(reads_ghost[nF:n])}
+            self.split = {0: interior_split(flags[0], *self.part.f_items[rank]), 1: interior_split(flags[1], *self.part.c_items[rank])}
         self.p_ranges = []
         for a, b in (self.part.f_rows[rank], self.part.c_rows[rank]):
             if b > a:
@@ -247,6 +280,18 @@ class ShardedSolver:
     def smooth(self, sweeps):
         fa, fb = self.part.f_items[self.rank]
         ca, cb = self.part.c_items[self.rank]
+        if self.split is not None:
+            # halo exchange overlapped with the interior rows: start (stores + flags), interior items, wait, boundary items
+            for _ in range(sweeps):
+                for which in (0, 1):                     # the F pass reads C ghosts (plan 1), the C pass reads F ghosts (plan 0)
+                    (i0, i1), boundary = self.split[which]
+                    self.be.peer_start(1 - which)
+                    if i1 > i0:
+                        self.be.gs_pass(which, i0, i1)
+                    self.be.peer_wait(1 - which)
+                    for a, b in boundary:
+                        self.be.gs_pass(which, a, b)
+            return
         for _ in range(sweeps):
             self.exchange(1)                 # F rows read C neighbours
             self.be.gs_pass(0, fa, fb)
@@ -420,6 +465,12 @@ class GpuBackend:
 
     def peer_run(self, plan):
         self.L.amgb200_peer_run(self.h, plan)
+
+    def peer_start(self, plan):
+        self.L.amgb200_peer_start(self.h, plan)
+
+    def peer_wait(self, plan):
+        self.L.amgb200_peer_wait(self.h, plan)
 
     def order(self):
         o = np.zeros(self._shape["n"], np.int32)

@@ -252,6 +252,10 @@ void *amgb200_ipc_open(amgb200_hier *h, const unsigned char *handle);
 void amgb200_peer_plan(amgb200_hier *h, int plan, int npush, const double *my_vec, void *const *peer_vec, const int *const *idx, const int *count,
                        const int *range0, int nflag, void *const *flag_slot, int nsrc, const int *src);
 void amgb200_peer_run(amgb200_hier *h, int plan);
+/* the two halves of amgb200_peer_run: start = store into the peers + raise the epochs in their flag words, wait = for the peers' epochs;
+ * kernels launched in between overlap the exchange (the interior rows of a level-0 pass read no ghost entry) */
+void amgb200_peer_start(amgb200_hier *h, int plan);
+void amgb200_peer_wait(amgb200_hier *h, int plan);
 
 /* ---- 3. host-side helpers (pure C++, no device): synthetic operators + RS setup ---------- */
 /* Synthetic level-0 operators of SURVEY.md Appendix B, CSR with ascending columns:
@@ -296,6 +300,10 @@ int amgb200_rap_device(const amgb200_mat *A, const amgb200_mat *P, amgb200_mat *
  * ghost entry (0 F, 1 C); every list holds ascending, distinct schedule indices.  Returns the total length. */
 long long amgb200_ghost_lists(const amgb200_mat *A, const int *order, int nF, int world, const long long *f_bounds, const long long *c_bounds, int **idx,
                               long long *ptr);
+/* the same, and reads_ghost[k] = 1 for every schedule row k that reads an entry owned by another rank (n bytes, zeroed by the callee; may be NULL):
+ * the rows of a pass that have to wait for the halo exchange */
+long long amgb200_ghost_lists_ex(const amgb200_mat *A, const int *order, int nF, int world, const long long *f_bounds, const long long *c_bounds, int **idx,
+                                 long long *ptr, unsigned char *reads_ghost);
 void amgb200_amg_destroy(amgb200_amg *mg);
 void amgb200_default_pars(amgb200_pars *p);   /* SSS_main.c:25-64 */
 

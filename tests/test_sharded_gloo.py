@@ -200,3 +200,42 @@ def test_native_ghost_lists_equal_the_numpy_ones(kind, N, world):
             assert sorted(a[r][w]) == sorted(b[r][w]) == sorted(g[w])
             for src in a[r][w]:
                 assert np.array_equal(a[r][w][src], b[r][w][src]) and np.array_equal(g[w][src], b[r][w][src])
+
+
+@pytest.mark.parametrize("kind,N,world", [("p3d", 16, 2), ("p3d", 20, 4), ("p2d", 64, 3)])
+def test_interior_items_read_no_ghost(kind, N, world):
+    """the interior / boundary split that lets the interior rows of a level-0 pass run while the halo exchange is in flight: no interior item
+    holds a row that reads an entry of another rank; interior + boundary cover every item of the rank exactly once"""
+    from amg_b200 import HostHierarchy, generate
+    from amg_b200.distributed import Partition, all_ghost_lists_native, ghost_lists, interior_split
+    A = generate(kind, N)
+    hier = HostHierarchy(A, tol=1e-8)
+    import torch
+    be = CpuBackend(hier, torch)
+    sh = be.shape()
+    rpi = 32
+    part = Partition(sh["n"], sh["nF"], sh["itemsF"], sh["itemsC"], rpi, world)
+    order = be.order()
+    rg = np.zeros(sh["n"], np.uint8)
+    all_ghost_lists_native(A, order, part, rg)
+    pos = np.empty(sh["n"], np.int64); pos[order] = np.arange(sh["n"])
+    owner = part.owner(np.arange(sh["n"]))
+    # reads_ghost against a direct evaluation
+    want = np.zeros(sh["n"], np.uint8)
+    for i in range(sh["n"]):
+        cols = pos[A.col_idx[A.row_ptr[i]:A.row_ptr[i + 1]]]
+        want[pos[i]] = (owner[cols] != owner[pos[i]]).any()
+    assert np.array_equal(rg, want)
+    nF, n = sh["nF"], sh["n"]
+    for which, rows0, items in ((0, 0, part.f_items), (1, nF, part.c_items)):
+        seg = rg[:nF] if which == 0 else rg[nF:n]
+        flags = np.pad(seg, (0, (-len(seg)) % rpi)).reshape(-1, rpi).any(axis=1)
+        for r in range(world):
+            a, b = items[r]
+            (i0, i1), boundary = interior_split(flags, a, b)
+            assert not flags[i0:i1].any()
+            covered = sorted([(i0, i1)] + boundary)
+            covered = [c for c in covered if c[1] > c[0]]
+            assert (covered[0][0] == a and covered[-1][1] == b and all(x[1] == y[0] for x, y in zip(covered, covered[1:]))) if b > a else True
+            if world > 1 and b - a > 8:
+                assert i1 - i0 > 0, "a slab partition must have interior items"
